@@ -1,0 +1,127 @@
+/* nsr_b200 -- C ABI of the B200-native per-ray rendering hot path (drop-in for the tiny-cuda-nn +
+ * nerfacc 0.3.3 calls made by bennyguo/instant-nsr-pl's models/).
+ *
+ * Conventions:
+ *  - plain pointers + sizes, no torch types.  Every pointer is a DEVICE pointer unless it says host.
+ *  - the caller owns all memory (inputs, outputs, workspace); the library never allocates or frees
+ *    device memory and keeps no pointer after return.
+ *  - every entry point takes the CUDA stream explicitly (void* = cudaStream_t), is re-entrant and
+ *    thread-safe (forward runs on the main Python thread, backward on autograd's worker thread).
+ *  - return 0 on success; non-zero => message in nsr_last_error() (thread-local).
+ *  - variable-length outputs use count -> (caller allocates) -> write, or device-side counts with
+ *    caller-provided capacity.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef NSR_B200_H
+#define NSR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSR_MAX_LEVELS 32
+#define NSR_VERSION 100
+
+/* Hash-grid geometry.  Replaces the encoding_config dict handed to tcnn.Encoding /
+ * tcnn.NetworkWithInputEncoding (models/network_utils.py:47,90,209; configs/nerf-blender.yaml:43-49).
+ * The per-level table is computed once on the host (fp32, identical to oracle/hashgrid.py). */
+typedef struct {
+  int32_t n_levels;
+  int32_t n_features;              /* per level; only 2 is implemented (every reference config) */
+  float scale[NSR_MAX_LEVELS];     /* exp2(l*log2(pls))*base - 1 */
+  uint32_t res[NSR_MAX_LEVELS];    /* ceil(scale)+1 */
+  uint32_t size[NSR_MAX_LEVELS];   /* entries in level */
+  uint32_t offset[NSR_MAX_LEVELS]; /* first entry of level */
+  uint32_t dense_mask;             /* bit l set: dense indexing, else coherent-prime hash */
+} nsr_grid_t;
+
+/* Fully-fused MLP description.  Replaces network_config of tcnn.Network (models/network_utils.py:181;
+ * configs/nerf-blender.yaml:50-55,62-67).  Width is fixed at 64 (every reference config). */
+typedef struct {
+  int32_t n_in;        /* logical input width; padded to a multiple of 16 with ones */
+  int32_t n_out;       /* logical output width (<= 16) */
+  int32_t n_hidden;    /* number of hidden layers (1..3) */
+  int32_t activation;  /* hidden: 0 none, 1 relu */
+  int32_t out_activation; /* 0 none, 1 relu, 2 sigmoid, 3 exponential */
+} nsr_mlp_t;
+
+/* Occupancy grid + marching parameters.  Replaces nerfacc.OccupancyGrid state and the kwargs of
+ * nerfacc.ray_marching (models/nerf.py:36-41,82-93; models/neus.py:63-74,159-169,210-220). */
+typedef struct {
+  float roi[6];            /* roi_aabb */
+  int32_t res;             /* grid resolution per axis */
+  int32_t contraction;     /* 0 AABB, 2 UN_BOUNDED_SPHERE (nerfacc.ContractionType) */
+  float step;              /* render_step_size */
+  float cone_angle;
+} nsr_march_t;
+
+const char* nsr_last_error(void);
+int nsr_version(void);
+int nsr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- encodings / networks (tiny-cuda-nn surface) -------------------------------------------- */
+
+/* tcnn.Encoding(HashGrid).forward  (models/network_utils.py:47,90).  x [n,3] f32 in [0,1];
+ * table fp16 [entries,2]; out fp16 [n, L*2]. */
+int nsr_hashgrid_fwd(const nsr_grid_t* g, const float* x, const void* table_h, void* out_h, int64_t n, void* stream);
+/* autograd of the above w.r.t. the table: grad_table f32 [entries*2] += dy_scale * scatter (atomic, one
+ * 8-byte vector RED per corner). dy fp16 [n,L*2] (possibly loss-scaled; dy_scale undoes it in fp32). */
+int nsr_hashgrid_bwd(const nsr_grid_t* g, const float* x, const void* dy_h, float* grad_table, float dy_scale, int64_t n, void* stream);
+/* ... w.r.t. the input (NeuS analytic normals, models/geometry.py:177-180): dx f32 [n,3]. dy f32 [n,L*2]. */
+int nsr_hashgrid_bwd_input(const nsr_grid_t* g, const float* x, const void* table_h, const float* dy, float* dx, int64_t n, void* stream);
+/* double backward of bwd_input (eikonal loss, systems/neus.py:106-108): given ddx f32 [n,3]
+ * -> grad_table += d/dtable, grad_dy f32 [n,L*2] (either may be NULL). */
+int nsr_hashgrid_bwd_bwd(const nsr_grid_t* g, const float* x, const void* table_h, const float* dy, const float* ddx,
+                         float* grad_table, float* grad_dy, int64_t n, void* stream);
+
+/* tcnn.Encoding(SphericalHarmonics, degree 4).forward (models/network_utils.py:90; texture.py:24-25).
+ * v [n,3] f32 in [0,1]; out fp16 [n,16]. */
+int nsr_sh4_fwd(const float* v, void* out_h, int64_t n, void* stream);
+
+/* tcnn.Network(FullyFusedMLP).forward (models/network_utils.py:181).  x fp16 [n, in_pad]; params fp16
+ * flat (row-major [out,in] matrices, tcnn layout); out fp16 [n,16]. */
+int nsr_mlp_fwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, void* out_h, int64_t n, void* stream);
+/* autograd of the above: dy fp16 [n,16] (w.r.t. post-activation output).  dy is multiplied by loss_scale
+ * on load (tcnn uses 128) so the fp16 dgrad chain stays in range; grad_params f32 flat += TRUE gradient;
+ * dx fp16 [n,in_pad] (may be NULL) = loss_scale * true gradient. */
+int nsr_mlp_bwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, const void* y_h, const void* dy_h,
+                float* grad_params, void* dx_h, float loss_scale, int64_t n, void* stream);
+
+/* ---- marching / compositing (nerfacc 0.3.3 surface) ----------------------------------------- */
+
+/* nerfacc.intersection.ray_aabb_intersect (models/neus.py:153). */
+int nsr_ray_aabb(const float* rays_o, const float* rays_d, const float* aabb6, float* t_min, float* t_max, int64_t n, void* stream);
+/* nerfacc.ray_marching, pass 1: per-ray sample counts (models/nerf.py:83).  t_min/t_max are the
+ * prepared per-ray intervals; bits = packed occupancy (bit idx&31 of word idx>>5). */
+int nsr_march_count(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                    const uint32_t* bits, int32_t* counts, int64_t n_rays, void* stream);
+/* exclusive scan of counts -> offsets[n+1] (offsets[n] = total). */
+int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, void* stream);
+/* pass 2: write samples at offsets. */
+int nsr_march_write(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                    const uint32_t* bits, const int64_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
+                    int64_t n_rays, void* stream);
+
+/* nerfacc render_visibility (inside ray_marching, models/nerf.py:87-92): per ray, exclusive
+ * transmittance from alpha; keep[i] = T_i >= eps && (alpha_thre<=0 || alpha>=thre). */
+int nsr_visibility(const float* alphas, const int64_t* offsets, uint8_t* keep, float* trans, int32_t* kept_counts,
+                   float early_stop_eps, float alpha_thre, int64_t n_rays, void* stream);
+/* nerfacc.render_weight_from_density / _from_alpha fwd+bwd (models/nerf.py:105, neus.py:237).
+ * `trans` (exclusive transmittance T_i, may be NULL in fwd) is what the backward needs:
+ *   d sigma_i = delta_i [ g_i (T_i - w_i) - sum_{j>i} g_j w_j ],  d alpha_i = g_i T_i - sum_{j>i} g_j w_j / (1 - alpha_i). */
+int nsr_weight_from_density_fwd(const float* t_starts, const float* t_ends, const float* sigmas, const int64_t* offsets,
+                                float* weights, float* trans, int64_t n_rays, void* stream);
+int nsr_weight_from_density_bwd(const float* t_starts, const float* t_ends, const float* weights, const float* trans,
+                                const float* grad_weights, const int64_t* offsets, float* grad_sigmas, int64_t n_rays, void* stream);
+int nsr_weight_from_alpha_fwd(const float* alphas, const int64_t* offsets, float* weights, float* trans, int64_t n_rays, void* stream);
+int nsr_weight_from_alpha_bwd(const float* alphas, const float* weights, const float* trans, const float* grad_weights,
+                              const int64_t* offsets, float* grad_alphas, int64_t n_rays, void* stream);
+/* nerfacc.accumulate_along_rays (models/nerf.py:106-108): out[n_rays,d] = segmented sum of w*v. */
+int nsr_accumulate(const float* weights, const float* values, const int64_t* offsets, float* out, int32_t d, int64_t n_rays, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,164 @@
+// Shared device/host helpers for the nsr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/nsr_b200.h"
+
+#define NSR_PRIME_Y 2654435761u
+#define NSR_PRIME_Z 805459861u
+
+void nsr_set_error(const char* fmt, ...);
+
+#define NSR_CHECK_LAUNCH(name)                                              \
+  do {                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) {                                               \
+      nsr_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return 2;                                                             \
+    }                                                                       \
+  } while (0)
+
+#define NSR_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      nsr_set_error(__VA_ARGS__);   \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+int nsr_sm_count();
+
+static inline int nsr_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// Hash-grid corner addressing (tiny-cuda-nn Grid/Hash/Linear semantics; oracle/hashgrid.py).
+// ------------------------------------------------------------------------------------------------
+struct LevelInfo {
+  float scale;
+  uint32_t res, size, offset;
+  bool dense;
+};
+
+__device__ __forceinline__ LevelInfo nsr_level(const nsr_grid_t& g, int l) {
+  LevelInfo li;
+  li.scale = g.scale[l];
+  li.res = g.res[l];
+  li.size = g.size[l];
+  li.offset = g.offset[l];
+  li.dense = (g.dense_mask >> l) & 1u;
+  return li;
+}
+
+// pos = fma(scale, x, 0.5); cell = floor(pos); frac = pos - cell
+__device__ __forceinline__ void nsr_pos_fract(float x, float scale, uint32_t& cell, float& frac) {
+  float p = __fmaf_rn(scale, x, 0.5f);
+  float fl = floorf(p);
+  cell = (uint32_t)(int)fl;
+  frac = p - fl;
+}
+
+// entry indices (absolute, in entries) of the 8 corners; corner c = bx | by<<1 | bz<<2
+__device__ __forceinline__ void nsr_corner_indices(const LevelInfo& li, uint32_t cx, uint32_t cy, uint32_t cz,
+                                                   uint32_t (&idx)[8]) {
+  if (li.dense) {
+    const uint32_t r = li.res, r2 = li.res * li.res;
+    const uint32_t b = cx + cy * r + cz * r2;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t i = b + (c & 1) + ((c >> 1) & 1) * r + ((c >> 2) & 1) * r2;
+      idx[c] = (i % li.size) + li.offset;
+    }
+  } else {
+    const uint32_t m = li.size - 1u;  // hashed levels always have size == 2^log2_hashmap_size
+    const uint32_t hx0 = cx, hx1 = cx + 1u;
+    const uint32_t hy0 = cy * NSR_PRIME_Y, hy1 = (cy + 1u) * NSR_PRIME_Y;
+    const uint32_t hz0 = cz * NSR_PRIME_Z, hz1 = (cz + 1u) * NSR_PRIME_Z;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t h = ((c & 1) ? hx1 : hx0) ^ (((c >> 1) & 1) ? hy1 : hy0) ^ (((c >> 2) & 1) ? hz1 : hz0);
+      idx[c] = (h & m) + li.offset;
+    }
+  }
+}
+
+__device__ __forceinline__ float nsr_corner_weight(int c, float fx, float fy, float fz) {
+  return ((c & 1) ? fx : 1.f - fx) * (((c >> 1) & 1) ? fy : 1.f - fy) * (((c >> 2) & 1) ? fz : 1.f - fz);
+}
+
+// d(weight)/d(frac_d) for axis d
+__device__ __forceinline__ float nsr_corner_dweight(int c, int d, float fx, float fy, float fz) {
+  float wx = (c & 1) ? fx : 1.f - fx, wy = ((c >> 1) & 1) ? fy : 1.f - fy, wz = ((c >> 2) & 1) ? fz : 1.f - fz;
+  float sx = (c & 1) ? 1.f : -1.f, sy = ((c >> 1) & 1) ? 1.f : -1.f, sz = ((c >> 2) & 1) ? 1.f : -1.f;
+  return d == 0 ? sx * wy * wz : (d == 1 ? wx * sy * wz : wx * wy * sz);
+}
+
+// vectorised fp32 reduction into global memory: one 8-byte RED per corner (sm_90+)
+__device__ __forceinline__ void nsr_red_add_f32x2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ float2 nsr_ld_table(const __half2* table, uint32_t idx) {
+  return __half22float2(__ldg(table + idx));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-level tensor-core primitives (legacy HMMA path; fp16 in, fp32 accumulate)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nsr_mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void nsr_ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ void nsr_ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ void nsr_ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_ptr) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+__device__ __forceinline__ void nsr_ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_ptr) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+__device__ __forceinline__ uint32_t nsr_pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// real spherical harmonics, degree 4 (16 coefficients) of the unit vector (x,y,z)
+__device__ __forceinline__ void nsr_sh4(float x, float y, float z, float (&s)[16]) {
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  s[0] = 0.28209479177387814f;
+  s[1] = -0.48860251190291987f * y;
+  s[2] = 0.48860251190291987f * z;
+  s[3] = -0.48860251190291987f * x;
+  s[4] = 1.0925484305920792f * xy;
+  s[5] = -1.0925484305920792f * yz;
+  s[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  s[7] = -1.0925484305920792f * xz;
+  s[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  s[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  s[10] = 2.8906114426405538f * xy * z;
+  s[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  s[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  s[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  s[14] = 1.4453057213202769f * z * (x2 - y2);
+  s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}

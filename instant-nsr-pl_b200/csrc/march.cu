@@ -1,0 +1,225 @@
+// Occupancy-grid ray marching: nerfacc 0.3.3 `ray_aabb_intersect` + `ray_marching` kernels
+// (models/nerf.py:82-93, models/neus.py:153-169,209-220).
+//
+// THIS FILE IS COMPILED WITH -fmad=false: every float op below is a separate IEEE fp32 op (or an
+// explicit __fmaf_rn) in exactly the order oracle/march.py performs it, so that the emitted sample
+// SET is bit-identical to the oracle's.
+//
+// B200 design: instead of nerfacc's one-thread-per-ray serial march (<= ~1024 dependent iterations,
+// long-tail divergence), the cone_angle == 0 case tests the step lattice in parallel -- one warp per
+// ray, 32 lattice points per iteration, ballot + popc compaction -- against a packed BITfield
+// (128^3 bits = 256 KB, L1/L2 resident; nerfacc reads 2 MB of bools).  Two passes (count, write)
+// around a device-side exclusive scan keep nerfacc's exact-size, ray-ordered output contract.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool occupied(const nsr_march_t& p, const uint32_t* __restrict__ bits, float px, float py, float pz) {
+  const float lx = p.roi[0], ly = p.roi[1], lz = p.roi[2], hx = p.roi[3], hy = p.roi[4], hz = p.roi[5];
+  float ux = (px - lx) / (hx - lx), uy = (py - ly) / (hy - ly), uz = (pz - lz) / (hz - lz);
+  if (p.contraction == 0) {
+    if (!(px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz)) return false;
+  } else {
+    float vx = ux * 2.f - 1.f, vy = uy * 2.f - 1.f, vz = uz * 2.f - 1.f;
+    const float n = sqrtf((vx * vx + vy * vy) + vz * vz);
+    if (n > 1.f) {
+      const float s = 2.f - 1.f / n;
+      vx = s * (vx / n);
+      vy = s * (vy / n);
+      vz = s * (vz / n);
+    }
+    ux = vx * 0.25f + 0.5f;
+    uy = vy * 0.25f + 0.5f;
+    uz = vz * 0.25f + 0.5f;
+  }
+  const int R = p.res;
+  const float fR = (float)R;
+  int cx = (int)(ux * fR), cy = (int)(uy * fR), cz = (int)(uz * fR);
+  cx = min(max(cx, 0), R - 1);
+  cy = min(max(cy, 0), R - 1);
+  cz = min(max(cz, 0), R - 1);
+  const uint32_t idx = (uint32_t)cx * R * R + (uint32_t)cy * R + (uint32_t)cz;
+  return (__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u;
+}
+
+__global__ void ray_aabb_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ aabb,
+                                float* __restrict__ t_min, float* __restrict__ t_max, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float near = -INFINITY, far = INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float oa = o[i * 3 + a], da = d[i * 3 + a];
+    const float t1 = (aabb[a] - oa) / da, t2 = (aabb[3 + a] - oa) / da;
+    near = fmaxf(near, fminf(t1, t2));
+    far = fminf(far, fmaxf(t1, t2));
+  }
+  const float near0 = fmaxf(near, 0.f);
+  const bool hit = far > near0;
+  t_min[i] = hit ? near0 : 1e10f;
+  t_max[i] = hit ? far : 1e10f;
+}
+
+constexpr int kMarchWarps = 8;
+constexpr uint32_t kMaxLattice = 1u << 24;
+
+// cone_angle == 0: warp-per-ray lattice test.  WRITE=false: counts; WRITE=true: samples at offsets.
+template <bool WRITE>
+__global__ void __launch_bounds__(kMarchWarps * 32) march_lattice_kernel(nsr_march_t p, const float* __restrict__ rays_o,
+                                                                         const float* __restrict__ rays_d,
+                                                                         const float* __restrict__ t_min,
+                                                                         const float* __restrict__ t_max,
+                                                                         const uint32_t* __restrict__ bits, int32_t* __restrict__ counts,
+                                                                         const int64_t* __restrict__ offsets,
+                                                                         int32_t* __restrict__ ray_indices, float* __restrict__ t_starts,
+                                                                         float* __restrict__ t_ends, int64_t n_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float ox = rays_o[ray * 3 + 0], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+  const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float tmin = t_min[ray], tmax = t_max[ray], step = p.step;
+  int64_t out = WRITE ? offsets[ray] : 0;
+  int cnt = 0;
+  for (uint32_t base = 0; base < kMaxLattice; base += 32) {
+    const float k = (float)(base + lane);
+    const float t0 = __fmaf_rn(k, step, tmin);
+    const float t1 = __fmaf_rn(k + 1.f, step, tmin);
+    const float tm = (t0 + t1) * 0.5f;
+    const bool valid = tm < tmax;
+    bool occ = false;
+    if (valid) occ = occupied(p, bits, __fmaf_rn(tm, dx, ox), __fmaf_rn(tm, dy, oy), __fmaf_rn(tm, dz, oz));
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
+    if (WRITE) {
+      if (occ) {
+        const int64_t pos = out + __popc(m & ((1u << lane) - 1u));
+        ray_indices[pos] = (int32_t)ray;
+        t_starts[pos] = t0;
+        t_ends[pos] = t1;
+      }
+      out += __popc(m);
+    } else {
+      cnt += __popc(m);
+    }
+    if (!__shfl_sync(0xffffffffu, (int)valid, 31)) break;  // tm is monotone in k
+  }
+  if (!WRITE && lane == 0) counts[ray] = cnt;
+}
+
+// cone_angle > 0 (contracted background pass): blind sequential stepping, one thread per ray
+template <bool WRITE>
+__global__ void march_seq_kernel(nsr_march_t p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                 const float* __restrict__ t_min, const float* __restrict__ t_max, const uint32_t* __restrict__ bits,
+                                 int32_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ ray_indices,
+                                 float* __restrict__ t_starts, float* __restrict__ t_ends, int64_t n_rays) {
+  const int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  const float ox = rays_o[ray * 3 + 0], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+  const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float tmax = t_max[ray], step = p.step, cone = p.cone_angle;
+  int64_t out = WRITE ? offsets[ray] : 0;
+  int cnt = 0;
+  float t0 = t_min[ray];
+  float t1 = t0 + fminf(fmaxf(t0 * cone, step), 1e10f);
+  float tm = (t0 + t1) * 0.5f;
+  for (int it = 0; it < (1 << 16) && tm < tmax; ++it) {
+    if (occupied(p, bits, __fmaf_rn(tm, dx, ox), __fmaf_rn(tm, dy, oy), __fmaf_rn(tm, dz, oz))) {
+      if (WRITE) {
+        ray_indices[out] = (int32_t)ray;
+        t_starts[out] = t0;
+        t_ends[out] = t1;
+        ++out;
+      } else {
+        ++cnt;
+      }
+    }
+    t0 = t1;
+    t1 = t0 + fminf(fmaxf(t0 * cone, step), 1e10f);
+    tm = (t0 + t1) * 0.5f;
+  }
+  if (!WRITE) counts[ray] = cnt;
+}
+
+// exclusive scan of int32 counts into int64 offsets[n+1]; one CTA (n is a ray count: small)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets, int64_t n) {
+  __shared__ int64_t warp_sums[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
+  int64_t s = 0;
+  for (int64_t i = b; i < e; ++i) s += counts[i];
+  int64_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int64_t i = b; i < e; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (tid == 1023) offsets[n] = warp_sums[31];
+}
+
+template <bool WRITE>
+int launch_march(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                 const uint32_t* bits, int32_t* counts, const int64_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
+                 int64_t n_rays, cudaStream_t st, const char* name) {
+  NSR_REQUIRE(p != nullptr, "%s: march descriptor is NULL", name);
+  NSR_REQUIRE(p->res >= 1 && p->res <= 1024, "%s: grid resolution %d out of range", name, p->res);
+  NSR_REQUIRE(p->contraction == 0 || p->contraction == 2, "%s: contraction type %d not implemented (AABB=0, UN_BOUNDED_SPHERE=2)", name,
+              p->contraction);
+  NSR_REQUIRE(p->step > 0.f, "%s: render_step_size must be > 0", name);
+  if (n_rays == 0) return 0;
+  if (p->cone_angle == 0.f) {
+    march_lattice_kernel<WRITE><<<nsr_blocks(n_rays, kMarchWarps), kMarchWarps * 32, 0, st>>>(
+        *p, rays_o, rays_d, t_min, t_max, bits, counts, offsets, ray_indices, t_starts, t_ends, n_rays);
+  } else {
+    march_seq_kernel<WRITE><<<nsr_blocks(n_rays, 128), 128, 0, st>>>(*p, rays_o, rays_d, t_min, t_max, bits, counts, offsets,
+                                                                      ray_indices, t_starts, t_ends, n_rays);
+  }
+  NSR_CHECK_LAUNCH(name);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int nsr_ray_aabb(const float* rays_o, const float* rays_d, const float* aabb6, float* t_min, float* t_max, int64_t n,
+                            void* stream) {
+  if (n == 0) return 0;
+  ray_aabb_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb6, t_min, t_max, n);
+  NSR_CHECK_LAUNCH("nsr_ray_aabb");
+  return 0;
+}
+
+extern "C" int nsr_march_count(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                               const uint32_t* bits, int32_t* counts, int64_t n_rays, void* stream) {
+  return launch_march<false>(p, rays_o, rays_d, t_min, t_max, bits, counts, nullptr, nullptr, nullptr, nullptr, n_rays,
+                             (cudaStream_t)stream, "nsr_march_count");
+}
+
+extern "C" int nsr_march_write(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                               const uint32_t* bits, const int64_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
+                               int64_t n_rays, void* stream) {
+  return launch_march<true>(p, rays_o, rays_d, t_min, t_max, bits, nullptr, offsets, ray_indices, t_starts, t_ends, n_rays,
+                            (cudaStream_t)stream, "nsr_march_write");
+}
+
+extern "C" int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, void* stream) {
+  scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, offsets, n);
+  NSR_CHECK_LAUNCH("nsr_scan_counts");
+  return 0;
+}
