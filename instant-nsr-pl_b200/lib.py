@@ -1,0 +1,140 @@
+"""ctypes binding of libnsr_b200.so (the C ABI declared in include/nsr_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, we raise.  Device memory is
+owned by torch; only raw pointers, sizes and the current CUDA stream cross the boundary.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NSR_MAX_LEVELS = 32
+
+
+class NsrError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(HERE, 'libnsr_b200.so')
+
+
+class GridT(C.Structure):
+    _fields_ = [('n_levels', C.c_int32), ('n_features', C.c_int32),
+                ('scale', C.c_float * NSR_MAX_LEVELS), ('res', C.c_uint32 * NSR_MAX_LEVELS),
+                ('size', C.c_uint32 * NSR_MAX_LEVELS), ('offset', C.c_uint32 * NSR_MAX_LEVELS),
+                ('dense_mask', C.c_uint32)]
+
+
+class MlpT(C.Structure):
+    _fields_ = [('n_in', C.c_int32), ('n_out', C.c_int32), ('n_hidden', C.c_int32),
+                ('activation', C.c_int32), ('out_activation', C.c_int32)]
+
+
+class MarchT(C.Structure):
+    _fields_ = [('roi', C.c_float * 6), ('res', C.c_int32), ('contraction', C.c_int32),
+                ('step', C.c_float), ('cone_angle', C.c_float)]
+
+
+class NerfT(C.Structure):
+    """nsr_nerf_t: fused NeRF field description (hash grid + density MLP + SH4 + colour MLP)."""
+    _fields_ = [('grid', GridT), ('radius', C.c_float), ('contraction', C.c_int32), ('density_bias', C.c_float),
+                ('density_hidden', C.c_int32), ('color_hidden', C.c_int32), ('feature_dim', C.c_int32)]
+
+
+P, I64, F32, I32 = C.c_void_p, C.c_int64, C.c_float, C.c_int32
+
+# name -> argtypes (all return int)
+_SIGNATURES = {
+    'nsr_device_info': [P, P, P],
+    'nsr_hashgrid_fwd': [P, P, P, P, I64, P],
+    'nsr_hashgrid_bwd': [P, P, P, P, F32, I64, P],
+    'nsr_hashgrid_bwd_input': [P, P, P, P, P, I64, P],
+    'nsr_hashgrid_bwd_bwd': [P, P, P, P, P, P, P, I64, P],
+    'nsr_sh4_fwd': [P, P, I64, P],
+    'nsr_mlp_fwd': [P, P, P, P, I64, P],
+    'nsr_mlp_bwd': [P, P, P, P, P, P, P, F32, I64, P],
+    'nsr_ray_aabb': [P, P, P, P, P, I64, P],
+    'nsr_march_count': [P, P, P, P, P, P, P, I64, P],
+    'nsr_scan_counts': [P, P, I64, P],
+    'nsr_march_write': [P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_visibility': [P, P, P, P, P, F32, F32, I64, P],
+    'nsr_weight_from_density_fwd': [P, P, P, P, P, P, I64, P],
+    'nsr_weight_from_density_bwd': [P, P, P, P, P, P, P, I64, P],
+    'nsr_weight_from_alpha_fwd': [P, P, P, P, I64, P],
+    'nsr_weight_from_alpha_bwd': [P, P, P, P, P, P, I64, P],
+    'nsr_accumulate': [P, P, P, P, I32, I64, P],
+}
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+
+    def _load(self):
+        path = library_path()
+        if not os.path.exists(path):
+            raise NsrError(f'{path} not found: build it with `python instant-nsr-pl_b200/build.py` '
+                           '(there is no CPU / PyTorch fallback for the hot path)')
+        dll = C.CDLL(path)
+        dll.nsr_last_error.restype = C.c_char_p
+        dll.nsr_version.restype = C.c_int
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(dll, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        self._dll = dll
+
+    @property
+    def dll(self):
+        if self._dll is None:
+            self._load()
+        return self._dll
+
+    def symbols(self):
+        return ['nsr_last_error', 'nsr_version'] + list(_SIGNATURES)
+
+    def call(self, name, *args):
+        fn = getattr(self.dll, name)
+        rc = fn(*args)
+        if rc != 0:
+            raise NsrError(f'{name} failed ({rc}): {self.dll.nsr_last_error().decode()}')
+
+
+lib = _Lib()
+
+
+def register_signatures(sigs):
+    """Let later modules (fused kernels) add entry points before the library is first loaded."""
+    _SIGNATURES.update(sigs)
+    if lib._dll is not None:
+        for name, argtypes in sigs.items():
+            fn = getattr(lib._dll, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check_cuda(*tensors, what='nsr_b200'):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError(f'{what}: only CUDA tensors are supported (got {t.device}); there is no CPU path')
+
+
+def contig(t, dtype=None):
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()

@@ -1,0 +1,367 @@
+"""Autograd-aware wrappers over the C ABI: one torch.autograd.Function per differentiable entry point.
+
+Host logic only (argument checks, output allocation, descriptor structs); all arithmetic is in
+libnsr_b200.so.  Mirrors what tiny-cuda-nn's torch binding / nerfacc's python wrappers do around
+their CUDA kernels.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .lib import lib, ptr, stream, check_cuda, contig, GridT, MlpT, MarchT, NSR_MAX_LEVELS
+
+LOSS_SCALE = 128.0  # same constant tiny-cuda-nn uses for fp16 backward passes
+
+_ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
+
+
+# --------------------------------------------------------------------------------------------------
+# descriptors
+# --------------------------------------------------------------------------------------------------
+class GridSpec:
+    """Per-level geometry of a tcnn HashGrid config (encoding_config dict of
+    models/network_utils.py:47,90,209).  Computed on the host in fp32 exactly like the oracle."""
+
+    def __init__(self, cfg, n_input_dims=3):
+        if n_input_dims != 3:
+            raise NotImplementedError('HashGrid: only 3-D inputs are implemented')
+        otype = cfg.get('otype', 'HashGrid')
+        if otype not in ('HashGrid', 'Grid'):
+            raise NotImplementedError(f'grid encoding otype={otype!r} not implemented')
+        if cfg.get('type', 'Hash') != 'Hash' or cfg.get('interpolation', 'Linear') != 'Linear':
+            raise NotImplementedError('only type=Hash, interpolation=Linear grids are implemented')
+        L = int(cfg['n_levels'])
+        F = int(cfg.get('n_features_per_level', 2))
+        if F != 2:
+            raise NotImplementedError('only n_features_per_level=2 is implemented')
+        if not 1 <= L <= NSR_MAX_LEVELS:
+            raise ValueError(f'n_levels={L} out of range')
+        T = 1 << int(cfg.get('log2_hashmap_size', 19))
+        base = np.float32(cfg.get('base_resolution', 16))
+        log2_pls = np.log2(np.float32(cfg.get('per_level_scale', 2.0))).astype(np.float32)
+        self.n_levels, self.n_features = L, F
+        self.scale = np.zeros(L, np.float32)
+        self.res = np.zeros(L, np.int64)
+        self.size = np.zeros(L, np.int64)
+        self.dense = np.zeros(L, bool)
+        for l in range(L):
+            self.scale[l] = np.float32(np.exp2(np.float32(np.float32(l) * log2_pls))) * base - np.float32(1.0)
+            r = int(math.ceil(float(self.scale[l]))) + 1
+            self.res[l] = r
+            n8 = (r ** 3 + 7) // 8 * 8
+            self.size[l] = min(n8, T)
+            self.dense[l] = r ** 3 <= self.size[l]
+        self.offset = np.zeros(L + 1, np.int64)
+        self.offset[1:] = np.cumsum(self.size)
+        self.n_entries = int(self.offset[-1])
+        self.n_params = self.n_entries * F
+        self.n_output_dims = L * F
+        s = GridT()
+        s.n_levels, s.n_features = L, F
+        mask = 0
+        for l in range(L):
+            s.scale[l] = float(self.scale[l])
+            s.res[l] = int(self.res[l])
+            s.size[l] = int(self.size[l])
+            s.offset[l] = int(self.offset[l])
+            mask |= int(self.dense[l]) << l
+        s.dense_mask = mask
+        self.struct = s
+
+    def ref(self):
+        import ctypes
+        return ctypes.byref(self.struct)
+
+
+class MlpSpec:
+    """FullyFusedMLP description (network_config dict of models/network_utils.py:181)."""
+
+    def __init__(self, n_in, n_out, cfg):
+        otype = cfg.get('otype', 'FullyFusedMLP')
+        if otype not in ('FullyFusedMLP', 'CutlassMLP'):
+            raise NotImplementedError(f'network otype={otype!r} not implemented')
+        self.n_in, self.n_out = int(n_in), int(n_out)
+        self.n_neurons = int(cfg.get('n_neurons', 64))
+        self.n_hidden = int(cfg.get('n_hidden_layers', 1))
+        if self.n_neurons != 64:
+            raise NotImplementedError('only n_neurons=64 is implemented (every reference config)')
+        if not 1 <= self.n_hidden <= 3:
+            raise NotImplementedError('n_hidden_layers must be 1..3')
+        if not 1 <= self.n_out <= 16 or not 1 <= self.n_in <= 64:
+            raise NotImplementedError('FullyFusedMLP: n_in <= 64 and n_out <= 16 are implemented')
+        act = str(cfg.get('activation', 'ReLU')).lower()
+        oact = str(cfg.get('output_activation', 'None')).lower()
+        if act not in ('none', 'relu') or oact not in _ACT:
+            raise NotImplementedError(f'activation={act!r}/output_activation={oact!r} not implemented')
+        self.in_pad = (self.n_in + 15) // 16 * 16
+        self.out_pad = 16
+        self.shapes = [(64, self.in_pad)] + [(64, 64)] * (self.n_hidden - 1) + [(self.out_pad, 64)]
+        self.n_params = sum(a * b for a, b in self.shapes)
+        s = MlpT()
+        s.n_in, s.n_out, s.n_hidden, s.activation, s.out_activation = self.n_in, self.n_out, self.n_hidden, _ACT[act], _ACT[oact]
+        self.struct = s
+
+    def ref(self):
+        import ctypes
+        return ctypes.byref(self.struct)
+
+    def init_params(self, generator=None):
+        """Xavier-uniform per matrix (tcnn default)."""
+        parts = []
+        for (o, i) in self.shapes:
+            bound = math.sqrt(6.0 / (i + o))
+            parts.append(((torch.rand(o, i, generator=generator) * 2 - 1) * bound).flatten())
+        return torch.cat(parts)
+
+
+def march_struct(roi, res, contraction, step, cone_angle):
+    s = MarchT()
+    for i in range(6):
+        s.roi[i] = float(roi[i])
+    s.res, s.contraction, s.step, s.cone_angle = int(res), int(contraction), float(step), float(cone_angle)
+    return s
+
+
+# --------------------------------------------------------------------------------------------------
+# hash grid (first + second order)
+# --------------------------------------------------------------------------------------------------
+class _HashGridBwd(torch.autograd.Function):
+    """(dx, dtable) = backward(x, table, dy); itself differentiable (double backward w.r.t. dy and
+    the table, as tiny-cuda-nn provides for the eikonal loss, models/geometry.py:177-180).
+    `table_f32` is the differentiable fp32 master (gradients are fp32); `table_h` its fp16 copy the
+    kernels read."""
+
+    @staticmethod
+    def forward(ctx, spec, x, table_f32, table_h, dy, need_dx, need_dtable):
+        ctx.spec = spec
+        n = x.shape[0]
+        dyf = contig(dy, torch.float32)
+        ctx.save_for_backward(x, table_h, dyf)
+        dx = dtable = None
+        if need_dx:
+            dx = torch.empty(n, 3, dtype=torch.float32, device=x.device)
+            lib.call('nsr_hashgrid_bwd_input', spec.ref(), ptr(x), ptr(table_h), ptr(dyf), ptr(dx), n, stream())
+        if need_dtable:
+            dtable = torch.zeros(spec.n_params, dtype=torch.float32, device=x.device)
+            dyh = contig(dy, torch.float16)
+            lib.call('nsr_hashgrid_bwd', spec.ref(), ptr(x), ptr(dyh), ptr(dtable), 1.0, n, stream())
+        return dx, dtable
+
+    @staticmethod
+    def backward(ctx, ddx, ddtable):
+        # ddtable (a gradient flowing into the table gradient) is ignored, like tiny-cuda-nn
+        spec = ctx.spec
+        x, table_h, dyf = ctx.saved_tensors
+        n = x.shape[0]
+        if ddx is None:
+            return (None,) * 7
+        ddx = contig(ddx, torch.float32)
+        gtable = torch.zeros(spec.n_params, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None
+        gdy = torch.empty(n, spec.n_output_dims, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[4] else None
+        if gtable is not None or gdy is not None:
+            lib.call('nsr_hashgrid_bwd_bwd', spec.ref(), ptr(x), ptr(table_h), ptr(dyf), ptr(ddx), ptr(gtable), ptr(gdy), n, stream())
+        # d/dx of dx (second derivative of a trilinear interpolant w.r.t. position) is not implemented;
+        # no reference path consumes it (positions never receive gradients).
+        return None, None, gtable, None, gdy, None, None
+
+
+class _HashGridFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, x, table_f32, table_h):
+        ctx.spec = spec
+        n = x.shape[0]
+        out = torch.empty(n, spec.n_output_dims, dtype=torch.float16, device=x.device)
+        lib.call('nsr_hashgrid_fwd', spec.ref(), ptr(x), ptr(table_h), ptr(out), n, stream())
+        ctx.save_for_backward(x, table_f32, table_h)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table_f32, table_h = ctx.saved_tensors
+        dx, dtable = _HashGridBwd.apply(ctx.spec, x, table_f32, table_h, dy, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return None, dx, dtable, None
+
+
+def hashgrid(spec, x, table_f32, table_h):
+    """x [N,3] fp32 cuda in [0,1]; table_f32: differentiable fp32 master [n_params]; table_h: its
+    fp16 copy (what the kernels read)."""
+    check_cuda(x, table_h, what='HashGrid')
+    return _HashGridFwd.apply(spec, contig(x, torch.float32), table_f32, table_h)
+
+
+def sh4(v01):
+    check_cuda(v01, what='SphericalHarmonics')
+    v = contig(v01, torch.float32)
+    out = torch.empty(v.shape[0], 16, dtype=torch.float16, device=v.device)
+    lib.call('nsr_sh4_fwd', ptr(v), ptr(out), v.shape[0], stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fully fused MLP
+# --------------------------------------------------------------------------------------------------
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, x_h, params_f32, params_h):
+        n = x_h.shape[0]
+        out = torch.empty(n, 16, dtype=torch.float16, device=x_h.device)
+        lib.call('nsr_mlp_fwd', spec.ref(), ptr(x_h), ptr(params_h), ptr(out), n, stream())
+        ctx.spec = spec
+        ctx.save_for_backward(x_h, params_h, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        x_h, params_h, out = ctx.saved_tensors
+        n = x_h.shape[0]
+        dy = contig(dy, torch.float16)
+        gparams = torch.zeros(spec.n_params, dtype=torch.float32, device=x_h.device)
+        dx = torch.empty_like(x_h) if ctx.needs_input_grad[1] else None
+        lib.call('nsr_mlp_bwd', spec.ref(), ptr(x_h), ptr(params_h), ptr(out), ptr(dy), ptr(gparams), ptr(dx), LOSS_SCALE, n, stream())
+        if dx is not None:
+            dx = (dx.float() / LOSS_SCALE).to(x_h.dtype)
+        return None, dx, (gparams if ctx.needs_input_grad[2] else None), None
+
+
+def mlp(spec, x, params_f32, params_h):
+    """x [N, n_in] (any float dtype) -> fp16 [N, n_out].  Input is padded to in_pad with ones."""
+    check_cuda(x, params_h, what='FullyFusedMLP')
+    n = x.shape[0]
+    xh = x.to(torch.float16)
+    if spec.in_pad > spec.n_in:
+        xh = torch.cat([xh, torch.ones(n, spec.in_pad - spec.n_in, dtype=torch.float16, device=x.device)], dim=-1)
+    out = _MlpFn.apply(spec, xh.contiguous(), params_f32, params_h)
+    return out[:, :spec.n_out]
+
+
+# --------------------------------------------------------------------------------------------------
+# marching / compositing
+# --------------------------------------------------------------------------------------------------
+def offsets_from_ray_indices(ray_indices, n_rays):
+    counts = torch.bincount(ray_indices.long(), minlength=n_rays)
+    off = torch.zeros(n_rays + 1, dtype=torch.int64, device=ray_indices.device)
+    torch.cumsum(counts, 0, out=off[1:])
+    return off
+
+
+def ray_aabb_intersect(rays_o, rays_d, aabb):
+    check_cuda(rays_o, rays_d, aabb, what='ray_aabb_intersect')
+    o, d, a = contig(rays_o, torch.float32), contig(rays_d, torch.float32), contig(aabb, torch.float32)
+    n = o.shape[0]
+    t_min = torch.empty(n, dtype=torch.float32, device=o.device)
+    t_max = torch.empty_like(t_min)
+    lib.call('nsr_ray_aabb', ptr(o), ptr(d), ptr(a), ptr(t_min), ptr(t_max), n, stream())
+    return t_min, t_max
+
+
+def march(mstruct, rays_o, rays_d, t_min, t_max, bits):
+    """-> ray_indices int32 [M], t_starts [M], t_ends [M], offsets int64 [N+1]."""
+    import ctypes
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    ref = ctypes.byref(mstruct)
+    lib.call('nsr_march_count', ref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(counts), n, stream())
+    lib.call('nsr_scan_counts', ptr(counts), ptr(offsets), n, stream())
+    total = int(offsets[n].item())  # exact-size output contract of nerfacc.ray_marching => one host sync
+    ri = torch.empty(total, dtype=torch.int32, device=dev)
+    ts = torch.empty(total, dtype=torch.float32, device=dev)
+    te = torch.empty(total, dtype=torch.float32, device=dev)
+    if total > 0:
+        lib.call('nsr_march_write', ref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(offsets), ptr(ri), ptr(ts),
+                 ptr(te), n, stream())
+    return ri, ts, te, offsets
+
+
+def visibility(alphas, offsets, early_stop_eps, alpha_thre):
+    n_rays = offsets.shape[0] - 1
+    a = contig(alphas.reshape(-1), torch.float32)
+    keep = torch.empty(a.shape[0], dtype=torch.uint8, device=a.device)
+    trans = torch.empty_like(a)
+    kept = torch.empty(n_rays, dtype=torch.int32, device=a.device)
+    lib.call('nsr_visibility', ptr(a), ptr(offsets), ptr(keep), ptr(trans), ptr(kept), float(early_stop_eps), float(alpha_thre), n_rays,
+             stream())
+    return keep.bool(), trans, kept
+
+
+class _WeightFromDensity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t_starts, t_ends, sigmas, offsets):
+        n_rays = offsets.shape[0] - 1
+        w = torch.empty_like(sigmas)
+        T = torch.empty_like(sigmas)
+        lib.call('nsr_weight_from_density_fwd', ptr(t_starts), ptr(t_ends), ptr(sigmas), ptr(offsets), ptr(w), ptr(T), n_rays, stream())
+        ctx.save_for_backward(t_starts, t_ends, w, T, offsets)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        t_starts, t_ends, w, T, offsets = ctx.saved_tensors
+        gw = contig(gw, torch.float32)
+        gs = torch.empty_like(w)
+        lib.call('nsr_weight_from_density_bwd', ptr(t_starts), ptr(t_ends), ptr(w), ptr(T), ptr(gw), ptr(offsets), ptr(gs),
+                 offsets.shape[0] - 1, stream())
+        return None, None, gs, None
+
+
+class _WeightFromAlpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alphas, offsets):
+        n_rays = offsets.shape[0] - 1
+        w = torch.empty_like(alphas)
+        T = torch.empty_like(alphas)
+        lib.call('nsr_weight_from_alpha_fwd', ptr(alphas), ptr(offsets), ptr(w), ptr(T), n_rays, stream())
+        ctx.save_for_backward(alphas, w, T, offsets)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        alphas, w, T, offsets = ctx.saved_tensors
+        gw = contig(gw, torch.float32)
+        ga = torch.empty_like(w)
+        lib.call('nsr_weight_from_alpha_bwd', ptr(alphas), ptr(w), ptr(T), ptr(gw), ptr(offsets), ptr(ga), offsets.shape[0] - 1, stream())
+        return ga, None
+
+
+class _Accumulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, values, offsets, ray_indices):
+        n_rays = offsets.shape[0] - 1
+        d = 1 if values is None else values.shape[-1]
+        out = torch.empty(n_rays, d, dtype=torch.float32, device=weights.device)
+        lib.call('nsr_accumulate', ptr(weights), ptr(values), ptr(offsets), ptr(out), d, n_rays, stream())
+        ctx.save_for_backward(weights, values, ray_indices)
+        ctx.has_values = values is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        weights, values, ray_indices = ctx.saved_tensors
+        g = gout.index_select(0, ray_indices.long())          # [K, d]
+        if ctx.has_values:
+            gw = (g * values).sum(-1, keepdim=True) if ctx.needs_input_grad[0] else None
+            gv = g * weights if ctx.needs_input_grad[1] else None
+        else:
+            gw, gv = (g if ctx.needs_input_grad[0] else None), None
+        return gw, gv, None, None
+
+
+def weight_from_density(t_starts, t_ends, sigmas, offsets):
+    shape = sigmas.shape
+    w = _WeightFromDensity.apply(contig(t_starts.reshape(-1), torch.float32), contig(t_ends.reshape(-1), torch.float32),
+                                 contig(sigmas.reshape(-1), torch.float32), offsets)
+    return w.reshape(shape)
+
+
+def weight_from_alpha(alphas, offsets):
+    shape = alphas.shape
+    return _WeightFromAlpha.apply(contig(alphas.reshape(-1), torch.float32), offsets).reshape(shape)
+
+
+def accumulate(weights, values, offsets, ray_indices):
+    w = contig(weights.reshape(-1, 1), torch.float32)
+    v = None if values is None else contig(values.reshape(w.shape[0], -1), torch.float32)
+    return _Accumulate.apply(w, v, offsets, ray_indices)

@@ -1,0 +1,243 @@
+"""Analytic known-answer tests pinning the oracle's restatement of the un-vendored third-party
+arithmetic (tiny-cuda-nn / nerfacc 0.3.3) -- SURVEY.md §4.  These are the only anchors available:
+the reference ships no tests or golden vectors for those pieces (parity unpinned, see oracle/__init__)."""
+import numpy as np
+import torch
+
+from oracle import hashgrid, sh, mlp, march, render, neus, occgrid
+
+NERF_CFG = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=1.447269237440378)
+NEUS_CFG = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=1.3195079107728942)
+
+
+def test_level_table_matches_survey():
+    lt = hashgrid.level_table(NERF_CFG)
+    assert list(lt['res'][:6]) == [16, 24, 34, 49, 71, 102]
+    assert list(lt['size'][:5]) == [4096, 13824, 39304, 117656, 357912] and all(lt['size'][5:] == 1 << 19)
+    assert int(lt['offset'][-1]) == 6299960 and lt['n_params'] == 12599920
+    assert list(lt['dense']) == [True] * 5 + [False] * 11
+    lt = hashgrid.level_table(NEUS_CFG)
+    assert list(lt['res'][:5]) == [32, 43, 56, 74, 98]
+    assert int(lt['offset'][-1]) == 6984576 and list(lt['dense']) == [True] * 4 + [False] * 12
+
+
+def test_hash_index_python_int_restatement():
+    rng = np.random.default_rng(0)
+    xyz = rng.integers(0, 4097, size=(256, 3))
+    T = 1 << 19
+    want = [((int(x) * 1) ^ (int(y) * 2654435761) ^ (int(z) * 805459861)) % (1 << 32) % T for x, y, z in xyz]
+    t = torch.from_numpy(xyz)
+    got = hashgrid.corner_index(t[:, 0], t[:, 1], t[:, 2], res=4096, size=T, dense=False)
+    assert got.tolist() == want
+    got = hashgrid.corner_index(t[:, 0] % 16, t[:, 1] % 16, t[:, 2] % 16, res=16, size=4096, dense=True)
+    assert got.tolist() == [(int(x) % 16 + (int(y) % 16) * 16 + (int(z) % 16) * 256) % 4096 for x, y, z in xyz]
+
+
+def test_hashgrid_reproduces_affine_function_on_dense_levels():
+    cfg = dict(NERF_CFG, n_levels=3)
+    lt = hashgrid.level_table(cfg)
+    table = torch.zeros(int(lt['offset'][-1]), 2, dtype=torch.float64)
+    a, b = torch.tensor([0.3, -0.7, 0.2], dtype=torch.float64), torch.tensor([-0.1, 0.5, 0.9], dtype=torch.float64)
+    for l in range(3):
+        r, off, scale = int(lt['res'][l]), int(lt['offset'][l]), float(lt['scale'][l])
+        g = torch.arange(r, dtype=torch.float64)
+        X, Y, Z = torch.meshgrid(g, g, g, indexing='ij')
+        idx = (X + Y * r + Z * r * r).long().flatten() + off
+        # vertex v sits at x = (v - 0.5)/scale
+        P = torch.stack([X, Y, Z], -1).reshape(-1, 3)
+        xs = (P - 0.5) / scale
+        table[idx, 0] = xs @ a + 0.25
+        table[idx, 1] = xs @ b - 0.5
+    # keep pos = x*scale+0.5 below res-1 so the +1 corner exists (at x ~ 1 it wraps into the next row: inherent to tcnn)
+    x = torch.rand(500, 3, generator=torch.Generator().manual_seed(1), dtype=torch.float64) * 0.9 + 0.01
+    out = hashgrid.hashgrid_fwd(x.float(), table, lt)
+    xf = x.float().double()
+    for l in range(3):
+        np.testing.assert_allclose(out[:, 2 * l].numpy(), (xf @ a + 0.25).numpy(), atol=1e-5)
+        np.testing.assert_allclose(out[:, 2 * l + 1].numpy(), (xf @ b - 0.5).numpy(), atol=1e-5)
+
+
+def test_hashgrid_autograd_gradcheck():
+    cfg = dict(n_levels=4, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4, per_level_scale=1.7)
+    lt = hashgrid.level_table(cfg)
+    g = torch.Generator().manual_seed(2)
+    table = torch.randn(int(lt['offset'][-1]), 2, generator=g, dtype=torch.float64, requires_grad=True)
+    x = (torch.rand(6, 3, generator=g) * 0.8 + 0.1)
+    xd = x.double().requires_grad_(True)
+    # gradcheck w.r.t. the table (linear) and x (piecewise-trilinear; points are away from cell faces w.h.p.)
+    f = lambda t: hashgrid.hashgrid_fwd(x, t, lt)
+    assert torch.autograd.gradcheck(f, (table,), eps=1e-6, atol=1e-6)
+    assert torch.autograd.gradcheck(lambda xx: hashgrid.hashgrid_fwd(xx, table.detach(), lt), (xd,), eps=1e-6, atol=1e-4)
+    # second order: d/dtable of (dy/dx . v) exists and matches finite differences
+    def gx(t):
+        xx = xd.detach().clone().requires_grad_(True)
+        y = hashgrid.hashgrid_fwd(xx, t, lt)
+        g, = torch.autograd.grad(y.sum(), xx, create_graph=True)
+        return g
+    assert torch.autograd.gradcheck(gx, (table,), eps=1e-6, atol=1e-5)
+
+
+def test_sh4_axes_and_orthonormality():
+    def S(d):
+        return sh.sh4((torch.tensor([d], dtype=torch.float64) + 1) / 2)[0]
+    c0, c1 = 0.28209479177387814, 0.48860251190291987
+    z = S([0., 0., 1.])
+    assert abs(z[0] - c0) < 1e-12 and abs(z[2] - c1) < 1e-12 and abs(z[1]) < 1e-12 and abs(z[3]) < 1e-12
+    assert abs(z[6] - (0.94617469575755997 - 0.31539156525251999)) < 1e-12
+    assert abs(S([1., 0., 0.])[3] + c1) < 1e-12 and abs(S([0., 1., 0.])[1] + c1) < 1e-12
+    # orthonormality under quadrature: Gauss-Legendre in cos(theta) x uniform in phi
+    mu, w = np.polynomial.legendre.leggauss(16)
+    phi = (np.arange(32) + 0.5) / 32 * 2 * np.pi
+    MU, PHI = np.meshgrid(mu, phi, indexing='ij')
+    W = np.repeat(w[:, None], 32, 1) * (2 * np.pi / 32)
+    st = np.sqrt(1 - MU ** 2)
+    d = torch.from_numpy(np.stack([st * np.cos(PHI), st * np.sin(PHI), MU], -1).reshape(-1, 3))
+    Y = sh.sh4((d + 1) / 2).numpy()
+    G = (Y * W.reshape(-1, 1)).T @ Y
+    np.testing.assert_allclose(G, np.eye(16), atol=1e-10)
+
+
+def test_ffmlp_layout_matches_reference_doc():
+    # models/network_utils.py:156: (in_pad + out_pad) * W + (n_hidden - 1) * W^2
+    for n_in, n_out, nh in [(32, 16, 1), (32, 3, 2), (35, 13, 1), (16, 3, 3)]:
+        shapes, n = mlp.ffmlp_layout(n_in, n_out, 64, nh)
+        assert n == (mlp.pad16(n_in) + mlp.pad16(n_out)) * 64 + (nh - 1) * 64 * 64
+    # padded inputs are ones: a 35-wide input behaves like 48 with 13 trailing ones
+    p = mlp.ffmlp_init(35, 13, 64, 1)
+    x = torch.randn(5, 35)
+    y = mlp.ffmlp_fwd(x, p, 35, 13, emulate_fp16=False, compute_dtype=torch.float64)
+    W1, W2 = p[:64 * 48].view(64, 48).double(), p[64 * 48:].view(16, 64).double()
+    xp = torch.cat([x.double(), torch.ones(5, 13, dtype=torch.float64)], -1)
+    np.testing.assert_allclose(y.numpy(), (torch.relu(xp @ W1.t()) @ W2.t())[:, :13].numpy(), atol=1e-12)
+
+
+def _box_scene(R=16):
+    binary = np.zeros((R, R, R), bool)
+    binary[R // 4: 3 * R // 4, R // 4: 3 * R // 4, R // 4: 3 * R // 4] = True
+    return binary
+
+
+def test_ray_aabb_and_march_kats():
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    o = np.array([[-3, 0, 0], [-3, 0, 0], [0, 0, 0], [-3, 5, 0]], np.float32)
+    d = np.array([[1, 0, 0], [-1, 0, 0], [0, 0, 1], [1, 0, 0]], np.float32)
+    tmin, tmax = march.ray_aabb_intersect(o, d, aabb)
+    np.testing.assert_allclose(tmin, [2, 1e10, 0, 1e10])
+    np.testing.assert_allclose(tmax, [4, 1e10, 1, 1e10])
+    step = np.float32(0.01)
+    # all-ones grid: contiguous samples covering [t_min, t_max); empty grid / miss: nothing
+    ones = np.ones((4, 4, 4), bool)
+    ri, ts, te, pk = march.march_lattice(o, d, aabb, ones, step, tmin, tmax)
+    assert pk[:, 1].tolist() == [200, 0, 100, 0] or abs(pk[0, 1] - 200) <= 1 and abs(pk[2, 1] - 100) <= 1
+    assert pk[1, 1] == 0 and pk[3, 1] == 0
+    r0 = ri == 0
+    np.testing.assert_allclose(ts[r0][1:], te[r0][:-1])  # contiguous
+    np.testing.assert_allclose(te[r0] - ts[r0], step, rtol=1e-3)
+    ri, *_ = march.march_lattice(o, d, aabb, np.zeros((4, 4, 4), bool), step, tmin, tmax)
+    assert ri.size == 0
+    # box of half the extent: ray 0 crosses [-0.5, 0.5] => ~100 samples with midpoints inside
+    ri, ts, te, pk = march.march_lattice(o, d, aabb, _box_scene(), step, tmin, tmax)
+    tm = 0.5 * (ts + te)[ri == 0]
+    assert abs(pk[0, 1] - 100) <= 1 and (np.abs(-3 + tm) <= 0.5 + 1e-6).all()
+
+
+def test_lattice_equals_dda_reference():
+    rng = np.random.default_rng(3)
+    R = 16
+    binary = rng.random((R, R, R)) < 0.3
+    aabb = np.array([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], np.float32)
+    n = 24
+    o = (rng.normal(size=(n, 3)) * 0.2 + np.array([0, 0, -4.0])).astype(np.float32)
+    d = rng.normal(size=(n, 3)) * 0.25 + np.array([0, 0, 1.0])
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    step = np.float32(1.732 * 3 / 256)
+    tmin, tmax = march.ray_aabb_intersect(o, d, aabb)
+    ri, ts, te, pk = march.march_lattice(o, d, aabb, binary, step, tmin, tmax)
+    mismatched = 0
+    for r in range(n):
+        ref = march.march_dda_reference(o[r], d[r], aabb, binary, float(step), float(tmin[r]), float(tmax[r]))
+        mine = list(zip(ts[ri == r], te[ri == r]))
+        if len(ref) != len(mine):
+            mismatched += 1  # a midpoint within rounding of a cell face may flip; must be rare
+            continue
+        if ref:
+            np.testing.assert_allclose(np.array(ref), np.array(mine), atol=2e-4)
+    assert mismatched <= 2
+
+
+def test_march_sequential_cone():
+    # all-occupied contracted grid: steps grow geometrically once t*cone > step
+    o = np.zeros((1, 3), np.float32)
+    d = np.array([[0, 0, 1]], np.float32)
+    roi = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    cone = 10 ** (3 / 64) - 1
+    ri, ts, te, pk = march.march_sequential(o, d, roi, np.ones((2, 2, 2), bool), 0.01, cone, np.array([0.1], np.float32),
+                                            np.array([1e3], np.float32), march.UN_BOUNDED_SPHERE)
+    dt = te - ts
+    assert (np.abs(ts[1:] - te[:-1]) == 0).all()
+    assert np.allclose(dt[ts * cone < 0.01], 0.01, rtol=1e-5)
+    big = ts * cone > 0.0101
+    assert np.allclose(dt[big] / ts[big], cone, rtol=1e-4)
+    assert 80 <= len(ts) <= 110
+
+
+def test_render_closed_forms_and_gradients():
+    sigma, L, n = 3.0, 1.2, 60
+    t = torch.linspace(0, L, n + 1, dtype=torch.float64)
+    ts, te = t[:-1, None], t[1:, None]
+    ri = torch.zeros(n, dtype=torch.long)
+    sig = torch.full((n, 1), sigma, dtype=torch.float64, requires_grad=True)
+    w = render.render_weight_from_density(ts, te, sig, ri, 1)
+    op = render.accumulate_along_rays(w, ri, None, 1)
+    np.testing.assert_allclose(op.item(), 1 - np.exp(-sigma * L), rtol=1e-12)
+    # alpha path agrees with density path
+    alpha = 1 - torch.exp(-sig.detach() * (te - ts))
+    w2 = render.render_weight_from_alpha(alpha, ri, 1)
+    np.testing.assert_allclose(w2.numpy(), w.detach().numpy(), rtol=1e-10)
+    # analytic gradient: d w_j / d sigma_i
+    g = torch.randn(n, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    gs, = torch.autograd.grad((w * g).sum(), sig)
+    T = render.transmittance_from_density(sig.detach().view(-1), (te - ts).view(-1), ri, 1)
+    wd, gd, dl = w.detach().view(-1), g.view(-1), (te - ts).view(-1)
+    suffix = torch.flip(torch.cumsum(torch.flip(gd * wd, [0]), 0), [0]) - gd * wd
+    np.testing.assert_allclose(gs.view(-1).numpy(), (dl * (gd * (T - wd) - suffix)).numpy(), rtol=1e-9, atol=1e-12)
+    # two rays, visibility: early termination drops a suffix only
+    a = torch.tensor([0.5] * 20 + [0.8] * 10, dtype=torch.float64)
+    ri2 = torch.tensor([0] * 20 + [1] * 10)
+    keep, Tr = render.render_visibility(a, ri2, 2, 1e-4)
+    assert keep[:14].all() and not keep[14:20].any()      # 0.5^13 = 1.2e-4 >= 1e-4 > 0.5^14
+    assert keep[20:26].all() and not keep[26:].any()      # 0.2^5 = 3.2e-4 kept, 0.2^6 = 6.4e-5 dropped
+    assert abs(Tr[20].item() - 1.0) < 1e-15
+
+
+def test_neus_alpha_planar_closed_form():
+    # planar SDF f(x) = x.n - c, ray hitting the plane frontally: cos = -1
+    s, dist = 20.0, 0.01
+    sdf = torch.tensor([0.03, 0.0, -0.02], dtype=torch.float64)
+    nrm = torch.tensor([[0., 0., 1.]] * 3, dtype=torch.float64)
+    dirs = torch.tensor([[0., 0., -1.]] * 3, dtype=torch.float64)
+    for ratio in (0.0, 1.0):
+        a = neus.get_alpha(sdf, nrm, dirs, torch.full((3, 1), dist, dtype=torch.float64), torch.tensor(s, dtype=torch.float64), ratio)
+        prev, nxt = torch.sigmoid((sdf + dist / 2) * s), torch.sigmoid((sdf - dist / 2) * s)
+        np.testing.assert_allclose(a.numpy(), ((prev - nxt + 1e-5) / (prev + 1e-5)).numpy(), rtol=1e-12)
+    # back-facing ray at ratio 1: iter_cos = 0 => alpha = 1e-5/(c+1e-5)
+    a = neus.get_alpha(sdf, nrm, -dirs, torch.full((3, 1), dist, dtype=torch.float64), torch.tensor(s, dtype=torch.float64), 1.0)
+    c = torch.sigmoid(sdf * s)
+    np.testing.assert_allclose(a.numpy(), (1e-5 / (c + 1e-5)).numpy(), rtol=1e-9)
+
+
+def test_occgrid_update_rule_and_bit_packing():
+    R = 8
+    occs = torch.zeros(R ** 3)
+    cells = torch.arange(R ** 3)
+    jit = torch.full((R ** 3, 3), 0.5)
+    fn = lambda x: (x.norm(dim=-1) < 0.8).float()[:, None] * 0.5
+    occs1, b1 = occgrid.update(occs, cells, jit, fn, 1.5, 0, R, occ_thre=0.01)
+    centers = ((occgrid.cell_coords(cells, R).float() + 0.5) / R * 3 - 1.5)
+    assert torch.equal(b1.view(-1), centers.norm(dim=-1) < 0.8)
+    occs2, _ = occgrid.update(occs1, cells, jit, lambda x: torch.zeros(len(x), 1), 1.5, 0, R)
+    np.testing.assert_allclose(occs2.numpy(), occs1.numpy() * 0.95, rtol=1e-6)
+    bits = occgrid.pack_bits(b1.numpy())
+    flat = b1.view(-1).numpy()
+    for idx in (0, 1, 37, 255, 300, 511):
+        assert bool((bits[idx >> 5] >> (idx & 31)) & 1) == bool(flat[idx])
