@@ -57,6 +57,19 @@ typedef struct {
   float cone_angle;
 } nsr_march_t;
 
+/* Fused NeRF field of the nerf-blender shape (configs/nerf-blender.yaml:30-67): HashGrid(L=16,F=2) ->
+ * FullyFused 32->64->feature_dim(16), density = trunc_exp(out0 + density_bias); colour = sigmoid(FullyFused
+ * [feature(16) | SH4(dir)(16)] -> 64 -> 64 -> 3); AABB contraction x01 = (x + radius) / (2 radius).
+ * Replaces VolumeDensity.forward + VolumeRadiance.forward (models/geometry.py:122-130, models/texture.py:23-30). */
+typedef struct {
+  nsr_grid_t grid;
+  float radius;
+  float density_bias;
+  int32_t feature_dim;     /* must be 16 */
+  int32_t density_hidden;  /* must be 1 */
+  int32_t color_hidden;    /* must be 2 */
+} nsr_nerf_t;
+
 const char* nsr_last_error(void);
 int nsr_version(void);
 int nsr_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -120,6 +133,42 @@ int nsr_weight_from_alpha_bwd(const float* alphas, const float* weights, const f
                               const int64_t* offsets, float* grad_alphas, int64_t n_rays, void* stream);
 /* nerfacc.accumulate_along_rays (models/nerf.py:106-108): out[n_rays,d] = segmented sum of w*v. */
 int nsr_accumulate(const float* weights, const float* values, const int64_t* offsets, float* out, int32_t d, int64_t n_rays, void* stream);
+
+/* ---- fused NeRF path (module-level surface: NeRFModel.forward_, models/nerf.py:61-127) ---------------- */
+
+/* density at world positions (occ_eval_fn of models/nerf.py:49-52; VolumeDensity.forward density-only).
+ * positions f32 [n,3]; dparams fp16 flat [3072 MLP | table]; density f32 [n]. */
+int nsr_nerf_density(const nsr_nerf_t* f, const float* positions, const void* dparams_h, float* density, int64_t n, void* stream);
+/* sigma_fn pre-pass of ray_marching (models/nerf.py:65-71,87): marched samples (ray_indices i32, t_starts,
+ * t_ends [m]) over rays f32 [n_rays,6] -> alphas[m] = 1 - exp(-sigma * (t_end - t_start)). */
+int nsr_nerf_prepass(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                     const void* dparams_h, float* alphas, int64_t m, void* stream);
+/* boolean-mask compaction of the pre-pass (the three `tensor[mask]` of nerfacc.ray_marching): with alpha_thre == 0
+ * the kept samples of a ray are a prefix, so ray r's first kept_counts[r] samples move from offsets_m[r] to
+ * offsets_k[r].  trans (exclusive transmittance from nsr_visibility) travels with them. */
+int nsr_compact_prefix(const int64_t* offsets_m, const int64_t* offsets_k, const int32_t* ray_indices_m, const float* t_starts_m,
+                       const float* t_ends_m, const float* trans_m, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
+                       float* trans_k, int64_t n_rays, void* stream);
+/* main pass (models/nerf.py:95-108): kept samples -> per-sample sigma, rgb, weights (= trans * (1 - exp(-sigma delta)))
+ * and per-ray sums acc_rgb[n_rays,3], opacity[n_rays], depth[n_rays] (must be zeroed by the caller; atomically
+ * accumulated).  enc_save (fp16 [k,32], may be NULL) keeps the encoded features for the backward pass. */
+int nsr_nerf_render_fwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                        const float* trans, const void* dparams_h, const void* cparams_h, void* enc_save_h, float* sigmas, float* rgbs,
+                        float* weights, float* acc_rgb, float* opacity, float* depth, int64_t k, void* stream);
+/* backward through the compositing (autograd of render_weight_from_density + accumulate_along_rays x3) and the
+ * density activation: per-ray grads (g_rgb [n_rays,3], g_opacity, g_depth [n_rays]; g_weights [k] optional) ->
+ * d_sraw [k] = dL/d(out0) (trunc_exp backward, models/utils.py:64-66, folded in), d_rgb [k,3].
+ * amax (device float, zeroed by the caller, may be NULL) receives max(|d_sraw|, |d_rgb|/4) for loss scaling. */
+int nsr_nerf_ray_bwd(const int64_t* offsets_k, const float* t_starts, const float* t_ends, const float* trans, const float* weights,
+                     const float* sigmas, const float* rgbs, const float* g_rgb, const float* g_opacity, const float* g_depth,
+                     const float* g_weights, float* d_sraw, float* d_rgb, float* amax, int64_t n_rays, void* stream);
+/* backward through both networks and the hash grid (autograd of VolumeRadiance + VolumeDensity + HashGrid):
+ * recomputes the forward from enc_save on tensor cores; grad_dparams f32 [3072 + table] and grad_cparams f32 [7168]
+ * are accumulated atomically (caller zeroes).  loss_scale keeps the fp16 dgrad chain in range; <= 0 selects it
+ * on the device from *amax (no host sync). */
+int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                       const void* enc_save_h, const void* dparams_h, const void* cparams_h, const float* d_sraw, const float* d_rgb,
+                       float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, void* stream);
 
 #ifdef __cplusplus
 }

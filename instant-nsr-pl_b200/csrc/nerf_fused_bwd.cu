@@ -1,0 +1,291 @@
+// Fused NeRF backward through both networks and the hash grid (autograd of VolumeRadiance + VolumeDensity +
+// HashGrid, models/texture.py:23-30, models/geometry.py:122-130), one launch.
+//
+// Per 128-sample CTA tile (8 warps x 16 rows): reload the 64 B/sample encoded features saved by the forward,
+// recompute every activation on tensor cores (cheaper than storing 416 B/sample of hidden state), run the dgrad
+// chain in registers, scatter dL/d(table) straight from the mma accumulator layout (each thread owns 2 samples x 4
+// levels) with 8-byte vector REDs into the fp32 gradient table, then split the five weight-gradient GEMMs
+// (dW = dPre^T * Act, K = 128 samples) over the 8 warps with register accumulators that persist for the whole
+// kernel; one atomicAdd per weight per CTA at the end (tcnn: split-K CUTLASS GEMMs over K = batch + reduction).
+#include "nerf_fused.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRows = kWarps * 16;  // 128
+
+// smem tile offsets (halves) after the weights
+constexpr int T_X0 = 0;                         // [128][40]  encoded features
+constexpr int T_H1 = T_X0 + kRows * NF_LD32;    // [128][72]  density hidden (post ReLU)
+constexpr int T_CI = T_H1 + kRows * NSR_LD64;   // [128][40]  colour input: out16 | SH16
+constexpr int T_G1 = T_CI + kRows * NF_LD32;    // [128][72]
+constexpr int T_G2 = T_G1 + kRows * NSR_LD64;   // [128][72]
+constexpr int T_DC3 = T_G2 + kRows * NSR_LD64;  // [128][24]  d(rgb pre-activation)
+constexpr int T_DG2 = T_DC3 + kRows * 24;       // [128][72]
+constexpr int T_DG1 = T_DG2 + kRows * NSR_LD64; // [128][72]
+constexpr int T_DO = T_DG1 + kRows * NSR_LD64;  // [128][24]  d(out16)
+constexpr int T_DH1 = T_DO + kRows * 24;        // [128][72]
+constexpr int T_TOTAL = T_DH1 + kRows * NSR_LD64;
+constexpr size_t kSmemBytes = (size_t)(NF_W_TOTAL + T_TOTAL) * sizeof(__half);
+
+constexpr int kSlots = 5;  // 40 wgrad pair-tiles / 8 warps
+
+struct WgradTile {
+  int dy_off, ldy, x_off, ldx, m0, n0;  // smem tiles
+  int net, base, in_dim;                // destination in the flat parameter gradient (net 0 density, 1 colour)
+};
+
+__device__ __forceinline__ WgradTile wgrad_tile(int t) {
+  WgradTile w;
+  if (t < 8) {          // density W1 [64][32]
+    w = {T_DH1, NSR_LD64, T_X0, NF_LD32, (t / 2) * 16, (t % 2) * 16, 0, 0, 32};
+  } else if (t < 12) {  // density W2 [16][64]
+    w = {T_DO, 24, T_H1, NSR_LD64, 0, (t - 8) * 16, 0, 64 * 32, 64};
+  } else if (t < 20) {  // colour W1 [64][32]
+    const int u = t - 12;
+    w = {T_DG1, NSR_LD64, T_CI, NF_LD32, (u / 2) * 16, (u % 2) * 16, 1, 0, 32};
+  } else if (t < 36) {  // colour W2 [64][64]
+    const int u = t - 20;
+    w = {T_DG2, NSR_LD64, T_G1, NSR_LD64, (u / 4) * 16, (u % 4) * 16, 1, 64 * 32, 64};
+  } else {              // colour W3 [16][64]
+    w = {T_DC3, 24, T_G2, NSR_LD64, 0, (t - 36) * 16, 1, 64 * 32 + 64 * 64, 64};
+  }
+  return w;
+}
+
+// mask a dgrad accumulator with the ReLU of the post-activation fragments and pack to fp16 A fragments
+__device__ __forceinline__ void relu_mask_pack(const float (&acc)[1][8][4], const uint32_t (&post)[1][4][4], uint32_t (&out)[1][4][4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 hv = *reinterpret_cast<const __half2*>(&post[0][k][j]);
+      const int nt = 2 * k + (j >> 1), i0 = (j & 1) * 2;
+      const float d0 = __low2float(hv) > 0.f ? acc[0][nt][i0] : 0.f;
+      const float d1 = __high2float(hv) > 0.f ? acc[0][nt][i0 + 1] : 0.f;
+      out[0][k][j] = nsr_pack_h2(d0, d1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) nerf_bwd_kernel(const __grid_constant__ nsr_nerf_t P, const float* __restrict__ rays,
+                                                               const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
+                                                               const float* __restrict__ t_ends, const __half* __restrict__ enc_save,
+                                                               const __half* __restrict__ dparams, const __half* __restrict__ cparams,
+                                                               const float* __restrict__ d_sraw, const float* __restrict__ d_rgb,
+                                                               float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
+                                                               float loss_scale, const float* __restrict__ amax_ptr, int64_t n) {
+  extern __shared__ __align__(16) __half smem[];
+  __half* T = smem + NF_W_TOTAL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int r0 = warp * 16;
+  if (loss_scale <= 0.f) {  // automatic: bring the largest incoming gradient to ~2^8
+    const float amax = fmaxf(__ldg(amax_ptr), 1e-30f);
+    loss_scale = exp2f(fminf(fmaxf(floorf(log2f(256.f / amax)), -24.f), 60.f));
+  }
+  const float inv_scale = 1.f / loss_scale;
+  nf_stage_weights(smem, dparams, cparams, true);
+  float* grad_table = grad_dparams + NF_DENSITY_PARAMS;
+
+  float wacc[kSlots][2][4];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wacc[s][j][i] = 0.f;
+
+  const int64_t n_tiles = (n + kRows - 1) / kRows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kRows;
+    __syncthreads();  // previous tile's wgrad is done with the smem tiles (first iteration: weights are staged)
+    // ---- stage this warp's 16 rows: encoded features and SH of the view direction
+    for (int v = lane; v < 64; v += 32) {
+      const int r = v >> 2, q = v & 3;
+      const int64_t i = row0 + r0 + r;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (i < n) val = __ldg(reinterpret_cast<const uint4*>(enc_save + i * 32) + q);
+      *reinterpret_cast<uint4*>(T + T_X0 + (r0 + r) * NF_LD32 + q * 8) = val;
+    }
+    if (lane < 16) {
+      const int64_t i = row0 + r0 + lane;
+      uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+      if (i < n) {
+        const float* rr = rays + (size_t)ray_indices[i] * 6;
+        float s[16];
+        nsr_sh4(__ldg(rr + 3), __ldg(rr + 4), __ldg(rr + 5), s);
+        s0 = make_uint4(nsr_pack_h2(s[0], s[1]), nsr_pack_h2(s[2], s[3]), nsr_pack_h2(s[4], s[5]), nsr_pack_h2(s[6], s[7]));
+        s1 = make_uint4(nsr_pack_h2(s[8], s[9]), nsr_pack_h2(s[10], s[11]), nsr_pack_h2(s[12], s[13]), nsr_pack_h2(s[14], s[15]));
+      }
+      uint4* sp = reinterpret_cast<uint4*>(T + T_CI + (r0 + lane) * NF_LD32 + 16);
+      sp[0] = s0;
+      sp[1] = s1;
+    }
+    __syncwarp();
+
+    // ---- forward recompute
+    uint32_t a_h1[1][4][4], a_o[1][1][4], a_g1[1][4][4], a_g2[1][4][4];
+    float acc[1][8][4], acc16[1][2][4];
+    {
+      uint32_t a_in[1][2][4];
+      nsr_load_afrag<1, 2>(a_in, T + T_X0, NF_LD32, r0);
+      nsr_zero_acc(acc);
+      nsr_gemm_w<1, 2, 8>(acc, a_in, smem + NF_OFF_DW1, NF_LD32);
+      nsr_acc_to_afrag<1, 8>(acc, a_h1, NSR_ACT_RELU);
+      nsr_store_afrag<1, 4>(a_h1, T + T_H1, NSR_LD64, r0);
+      nsr_zero_acc(acc16);
+      nsr_gemm_w<1, 4, 2>(acc16, a_h1, smem + NF_OFF_DW2, NSR_LD64);
+      nsr_acc_to_afrag<1, 2>(acc16, a_o, NSR_ACT_NONE);
+      nsr_store_afrag<1, 1>(a_o, T + T_CI, NF_LD32, r0, 0);
+    }
+    {
+      uint32_t a_c[1][2][4], a_sh[1][1][4];
+      nsr_load_afrag<1, 1>(a_sh, T + T_CI + 16, NF_LD32, r0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a_c[0][0][j] = a_o[0][0][j];
+        a_c[0][1][j] = a_sh[0][0][j];
+      }
+      nsr_zero_acc(acc);
+      nsr_gemm_w<1, 2, 8>(acc, a_c, smem + NF_OFF_CW1, NF_LD32);
+      nsr_acc_to_afrag<1, 8>(acc, a_g1, NSR_ACT_RELU);
+      nsr_store_afrag<1, 4>(a_g1, T + T_G1, NSR_LD64, r0);
+      nsr_zero_acc(acc);
+      nsr_gemm_w<1, 4, 8>(acc, a_g1, smem + NF_OFF_CW2, NSR_LD64);
+      nsr_acc_to_afrag<1, 8>(acc, a_g2, NSR_ACT_RELU);
+      nsr_store_afrag<1, 4>(a_g2, T + T_G2, NSR_LD64, r0);
+      nsr_zero_acc(acc16);
+      nsr_gemm_w<1, 4, 2>(acc16, a_g2, smem + NF_OFF_CW3, NSR_LD64);
+    }
+    // ---- d(rgb pre-activation) = d_rgb * s (1 - s), s = sigmoid(fp16(raw)); columns 0..2 only
+    const int64_t ia = row0 + r0 + g, ib = ia + 8;
+    uint32_t a_dc3[1][1][4];
+    {
+      float dp[4] = {0.f, 0.f, 0.f, 0.f};  // (row g: col c*2, c*2+1), (row g+8: col c*2, c*2+1)
+      if (c < 2) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int64_t i = hh ? ib : ia;
+          if (i < n) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = c * 2 + e;
+              if (col < 3) {
+                const float raw = __half2float(__float2half_rn(acc16[0][0][hh * 2 + e]));
+                const float s = 1.f / (1.f + expf(-raw));
+                dp[hh * 2 + e] = d_rgb[i * 3 + col] * s * (1.f - s) * loss_scale;
+              }
+            }
+          }
+        }
+      }
+      a_dc3[0][0][0] = nsr_pack_h2(dp[0], dp[1]);
+      a_dc3[0][0][1] = nsr_pack_h2(dp[2], dp[3]);
+      a_dc3[0][0][2] = 0u;
+      a_dc3[0][0][3] = 0u;
+      nsr_store_afrag<1, 1>(a_dc3, T + T_DC3, 24, r0);
+    }
+    // ---- dgrad chain
+    uint32_t a_d[1][4][4];
+    nsr_zero_acc(acc);
+    nsr_gemm_wt<1, 1, 8>(acc, a_dc3, smem + NF_OFF_CW3, NSR_LD64);
+    relu_mask_pack(acc, a_g2, a_d);
+    nsr_store_afrag<1, 4>(a_d, T + T_DG2, NSR_LD64, r0);
+    nsr_zero_acc(acc);
+    nsr_gemm_wt<1, 4, 8>(acc, a_d, smem + NF_OFF_CW2, NSR_LD64);
+    relu_mask_pack(acc, a_g1, a_d);
+    nsr_store_afrag<1, 4>(a_d, T + T_DG1, NSR_LD64, r0);
+    nsr_zero_acc(acc16);
+    nsr_gemm_wt<1, 4, 2>(acc16, a_d, smem + NF_OFF_CW1, NF_LD32);  // first 16 input columns = the geometry features
+    if (c == 0) {  // density path: d(out0) += d sigma / d raw (trunc_exp backward folded in by nsr_nerf_ray_bwd)
+      if (ia < n) acc16[0][0][0] += d_sraw[ia] * loss_scale;
+      if (ib < n) acc16[0][0][2] += d_sraw[ib] * loss_scale;
+    }
+    uint32_t a_do[1][1][4];
+    nsr_acc_to_afrag<1, 2>(acc16, a_do, NSR_ACT_NONE);
+    nsr_store_afrag<1, 1>(a_do, T + T_DO, 24, r0);
+    nsr_zero_acc(acc);
+    nsr_gemm_wt<1, 1, 8>(acc, a_do, smem + NF_OFF_DW2, NSR_LD64);
+    relu_mask_pack(acc, a_h1, a_d);
+    nsr_store_afrag<1, 4>(a_d, T + T_DH1, NSR_LD64, r0);
+    float accE[1][4][4];
+    nsr_zero_acc(accE);
+    nsr_gemm_wt<1, 4, 4>(accE, a_d, smem + NF_OFF_DW1, NF_LD32);
+
+    // ---- hash-table scatter straight from the accumulator layout: this thread owns samples (g, g+8) x levels (c, 4+c, 8+c, 12+c)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int64_t i = hh ? ib : ia;
+      if (i < n) {
+        float x, y, z, dx, dy, dz;
+        nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float d0 = accE[0][nt][hh * 2] * inv_scale, d1 = accE[0][nt][hh * 2 + 1] * inv_scale;
+          if (d0 != 0.f || d1 != 0.f) {
+            const LevelInfo li = nsr_level(P.grid, nt * 4 + c);
+            uint32_t cx, cy, cz, idx[8];
+            float fx, fy, fz;
+            nsr_pos_fract(x, li.scale, cx, fx);
+            nsr_pos_fract(y, li.scale, cy, fy);
+            nsr_pos_fract(z, li.scale, cz, fz);
+            nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float w = nsr_corner_weight(cc, fx, fy, fz);
+              nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], w * d0, w * d1);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- weight gradients over the 128 rows of the tile
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const WgradTile w = wgrad_tile(warp + s * kWarps);
+      nsr_wgrad_tile(wacc[s][0], wacc[s][1], T + w.dy_off, w.ldy, w.m0, T + w.x_off, w.ldx, w.n0, kRows);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const WgradTile w = wgrad_tile(warp + s * kWarps);
+    float* dst = (w.net == 0 ? grad_dparams : grad_cparams) + w.base;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int o = w.m0 + g + ((i >> 1) << 3), ii = w.n0 + j * 8 + c * 2 + (i & 1);
+        atomicAdd(dst + (size_t)o * w.in_dim + ii, wacc[s][j][i] * inv_scale);
+      }
+  }
+}
+
+}  // namespace
+
+extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
+                                  const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
+                                  const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
+                                  const float* amax, int64_t k, void* stream) {
+  NSR_REQUIRE(f != nullptr, "nsr_nerf_field_bwd: field descriptor is NULL");
+  NSR_REQUIRE(f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 && f->color_hidden == 2,
+              "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
+  NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_nerf_field_bwd: loss_scale <= 0 (automatic) needs the amax pointer");
+  if (k == 0) return 0;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nerf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) {
+      nsr_set_error("nsr_nerf_field_bwd: cannot reserve %zu B shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+      return 2;
+    }
+    attr_set = true;
+  }
+  const int64_t tiles = (k + kRows - 1) / kRows;
+  int grid = (int)min((int64_t)nsr_sm_count(), tiles);
+  nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
+                                                                        (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
+                                                                        grad_dparams, grad_cparams, loss_scale, amax, k);
+  NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
+  return 0;
+}

@@ -39,8 +39,8 @@ class MarchT(C.Structure):
 
 class NerfT(C.Structure):
     """nsr_nerf_t: fused NeRF field description (hash grid + density MLP + SH4 + colour MLP)."""
-    _fields_ = [('grid', GridT), ('radius', C.c_float), ('contraction', C.c_int32), ('density_bias', C.c_float),
-                ('density_hidden', C.c_int32), ('color_hidden', C.c_int32), ('feature_dim', C.c_int32)]
+    _fields_ = [('grid', GridT), ('radius', C.c_float), ('density_bias', C.c_float), ('feature_dim', C.c_int32),
+                ('density_hidden', C.c_int32), ('color_hidden', C.c_int32)]
 
 
 P, I64, F32, I32 = C.c_void_p, C.c_int64, C.c_float, C.c_int32
@@ -65,6 +65,12 @@ _SIGNATURES = {
     'nsr_weight_from_alpha_fwd': [P, P, P, P, I64, P],
     'nsr_weight_from_alpha_bwd': [P, P, P, P, P, P, I64, P],
     'nsr_accumulate': [P, P, P, P, I32, I64, P],
+    'nsr_nerf_density': [P, P, P, P, I64, P],
+    'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P],
+    'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_nerf_render_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_nerf_ray_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_nerf_field_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, F32, P, I64, P],
 }
 
 

@@ -1,0 +1,191 @@
+"""Geometry and texture fields: 'volume-density', 'volume-sdf', 'volume-radiance', 'volume-color'
+(models/geometry.py:17-29,115-238 and models/texture.py:10-57 of the reference), same constructor
+config, forward signatures and return conventions.  Isosurface extraction (marching cubes) is an
+export-time feature outside the rendering hot path and is not provided."""
+import torch
+import torch.nn as nn
+
+from . import register
+from ..nerfacc import ContractionType
+from .common import BaseModel, get_activation, scale_anything, update_module_step
+from .networks import get_encoding, get_mlp, get_encoding_with_network
+
+
+def contract_to_unisphere(x, radius, contraction_type):
+    """world -> [0,1]^3: affine for AABB; NeRF++/mip-360 style sphere contraction otherwise."""
+    u = scale_anything(x, (-radius, radius), (0, 1))
+    if contraction_type == ContractionType.AABB:
+        return u
+    if contraction_type == ContractionType.UN_BOUNDED_SPHERE:
+        v = u * 2 - 1
+        mag = v.norm(dim=-1, keepdim=True)
+        v = torch.where(mag > 1, (2 - 1 / mag) * (v / mag), v)
+        return v / 4 + 0.5
+    raise NotImplementedError
+
+
+class BaseImplicitGeometry(BaseModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.radius = self.config.radius
+        self.contraction_type = None  # assigned by the renderer that owns this field
+
+    def isosurface(self):
+        raise NotImplementedError('isosurface extraction (marching cubes export) is outside the rendering hot path '
+                                  'and not provided by nsr_b200')
+
+
+@register('volume-density')
+class VolumeDensity(BaseImplicitGeometry):
+    def setup(self):
+        self.n_input_dims = self.config.get('n_input_dims', 3)
+        self.n_output_dims = self.config.feature_dim
+        self.encoding_with_network = get_encoding_with_network(self.n_input_dims, self.n_output_dims, self.config.xyz_encoding_config,
+                                                               self.config.mlp_network_config)
+
+    def _raw(self, points):
+        unit = contract_to_unisphere(points, self.radius, self.contraction_type)
+        out = self.encoding_with_network(unit.reshape(-1, self.n_input_dims))
+        return out.reshape(*points.shape[:-1], self.n_output_dims)
+
+    def _density(self, raw0):
+        if 'density_activation' in self.config:
+            return get_activation(self.config.density_activation)(raw0 + float(self.config.density_bias))
+        return raw0
+
+    def forward(self, points):
+        out = self._raw(points).float()
+        feature = out
+        if 'feature_activation' in self.config:
+            feature = get_activation(self.config.feature_activation)(feature)
+        return self._density(out[..., 0]), feature
+
+    def forward_level(self, points):
+        return -self._density(self._raw(points)[..., 0])
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding_with_network, epoch, global_step)
+
+
+@register('volume-sdf')
+class VolumeSDF(BaseImplicitGeometry):
+    def setup(self):
+        self.n_output_dims = self.config.feature_dim
+        self.encoding = get_encoding(3, self.config.xyz_encoding_config)
+        self.network = get_mlp(self.encoding.n_output_dims, self.n_output_dims, self.config.mlp_network_config)
+        self.grad_type = self.config.grad_type
+        self.finite_difference_eps = self.config.get('finite_difference_eps', 1e-3)
+        self._finite_difference_eps = None  # value in use; updated per step when "progressive"
+
+    def _query(self, unit_points):
+        return self.network(self.encoding(unit_points.reshape(-1, 3)))
+
+    def _sdf_of(self, out0):
+        if 'sdf_activation' in self.config:
+            return get_activation(self.config.sdf_activation)(out0 + float(self.config.sdf_bias))
+        return out0
+
+    def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
+        analytic = with_grad and self.grad_type == 'analytic'
+        with torch.inference_mode(torch.is_inference_mode_enabled() and not analytic):
+            with torch.set_grad_enabled(self.training or analytic):
+                if analytic:
+                    if not self.training:
+                        points = points.clone()  # may come from inference mode
+                    points.requires_grad_(True)
+                world = points
+                unit = contract_to_unisphere(world, self.radius, self.contraction_type)
+                out = self._query(unit).reshape(*world.shape[:-1], self.n_output_dims).float()
+                sdf = self._sdf_of(out[..., 0])
+                feature = out
+                if 'feature_activation' in self.config:
+                    feature = get_activation(self.config.feature_activation)(feature)
+                grad = laplace = None
+                if analytic:
+                    grad = torch.autograd.grad(sdf, world, grad_outputs=torch.ones_like(sdf), create_graph=True, retain_graph=True,
+                                               only_inputs=True)[0]
+                elif with_grad and self.grad_type == 'finite_difference':
+                    eps = self._finite_difference_eps
+                    offs = torch.zeros(6, 3, device=world.device, dtype=world.dtype)
+                    for a in range(3):
+                        offs[2 * a, a], offs[2 * a + 1, a] = eps, -eps
+                    nb = (world[..., None, :] + offs).clamp(-self.radius, self.radius)
+                    nb_unit = scale_anything(nb, (-self.radius, self.radius), (0, 1))
+                    nb_sdf = self._query(nb_unit)[..., 0].reshape(*world.shape[:-1], 6).float()
+                    grad = 0.5 * (nb_sdf[..., 0::2] - nb_sdf[..., 1::2]) / eps
+                    if with_laplace:
+                        laplace = (nb_sdf[..., 0::2] + nb_sdf[..., 1::2] - 2 * sdf[..., None]).sum(-1) / (eps ** 2)
+        rv = [sdf]
+        if with_grad:
+            rv.append(grad)
+        if with_feature:
+            rv.append(feature)
+        if with_laplace:
+            assert self.config.grad_type == 'finite_difference', "Laplace computation is only supported with grad_type='finite_difference'"
+            rv.append(laplace)
+        rv = [v if self.training else v.detach() for v in rv]
+        return rv[0] if len(rv) == 1 else rv
+
+    def forward_level(self, points):
+        unit = contract_to_unisphere(points, self.radius, self.contraction_type)
+        return self._sdf_of(self._query(unit).reshape(*points.shape[:-1], self.n_output_dims)[..., 0])
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+        update_module_step(self.network, epoch, global_step)
+        if self.grad_type != 'finite_difference':
+            return
+        if isinstance(self.finite_difference_eps, float):
+            self._finite_difference_eps = self.finite_difference_eps
+        elif self.finite_difference_eps == 'progressive':
+            hg = self.config.xyz_encoding_config
+            assert hg.otype == 'ProgressiveBandHashGrid', "finite_difference_eps='progressive' only works with ProgressiveBandHashGrid"
+            level = min(hg.start_level + max(global_step - hg.start_step, 0) // hg.update_steps, hg.n_levels)
+            self._finite_difference_eps = 2 * self.config.radius / (hg.base_resolution * hg.per_level_scale ** (level - 1))
+        else:
+            raise ValueError(f'Unknown finite_difference_eps={self.finite_difference_eps}')
+
+
+@register('volume-radiance')
+class VolumeRadiance(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.n_dir_dims = self.config.get('n_dir_dims', 3)
+        self.n_output_dims = 3
+        self.encoding = get_encoding(self.n_dir_dims, self.config.dir_encoding_config)
+        self.n_input_dims = self.config.input_feature_dim + self.encoding.n_output_dims
+        self.network = get_mlp(self.n_input_dims, self.n_output_dims, self.config.mlp_network_config)
+
+    def forward(self, features, dirs, *args):
+        emb = self.encoding(((dirs + 1.) / 2.).reshape(-1, self.n_dir_dims))  # (-1,1) -> (0,1)
+        parts = [features.reshape(-1, features.shape[-1]), emb] + [a.reshape(-1, a.shape[-1]) for a in args]
+        color = self.network(torch.cat(parts, dim=-1)).reshape(*features.shape[:-1], self.n_output_dims).float()
+        if 'color_activation' in self.config:
+            color = get_activation(self.config.color_activation)(color)
+        return color
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+
+    def regularizations(self, out):
+        return {}
+
+
+@register('volume-color')
+class VolumeColor(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.n_output_dims = 3
+        self.n_input_dims = self.config.input_feature_dim
+        self.network = get_mlp(self.n_input_dims, self.n_output_dims, self.config.mlp_network_config)
+
+    def forward(self, features, *args):
+        color = self.network(features.reshape(-1, features.shape[-1])).reshape(*features.shape[:-1], self.n_output_dims).float()
+        if 'color_activation' in self.config:
+            color = get_activation(self.config.color_activation)(color)
+        return color
+
+    def regularizations(self, out):
+        return {}

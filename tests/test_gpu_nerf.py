@@ -1,0 +1,136 @@
+"""Module-level parity of the drop-in 'nerf' model (fused kernels AND composed per-op path) against the
+CPU oracle's NeRFModel.forward_ restatement, on seeded synthetic rays / occupancy / parameters.
+
+Tolerances: kept-sample sets exactly equal except samples whose transmittance sits within 1e-3 (relative)
+of early_stop_eps; per-ray colour |d| <= 5e-3; opacity/depth |d| <= 2e-3; network gradients cosine >= 0.995,
+table gradient cosine >= 0.99 and max error <= 6e-2 of the max entry (fp16 dgrad + atomic order)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import models as omodels, hashgrid as ohash
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def build(fused, n_rays=600, seed=0, peak=10.0):
+    from nsr_b200 import models, configs, synthetic
+    D = torch.device('cuda:0')
+    cfg = configs.nerf_blender()
+    cfg['fused'] = fused
+    torch.manual_seed(1234)
+    model = models.make('nerf', cfg).to(D)
+    net = model.geometry.encoding_with_network
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        p = net.params.detach().cpu().clone()
+        # a rougher table than tcnn's 1e-4 init so every level matters, then the density bump
+        p[net.mlp.n_params:] = ((torch.rand(net.grid.n_params, generator=g) * 2 - 1) * 0.1)
+        synthetic.shape_density(p, net.grid, net.mlp.n_params, peak_logit=peak)
+        net.params.copy_(p.to(D))
+    binary = synthetic.occupancy()
+    model.occupancy_grid.set_binary(torch.from_numpy(binary))
+    rays = synthetic.sample_rays(n_rays, seed=seed)
+    jitter = np.random.default_rng(seed + 1).random(n_rays).astype(np.float32)
+    bg = torch.tensor([0.3, 0.6, 0.9])
+    model.background_color = bg.to(D)
+    model.train()
+    return model, cfg, binary, rays, jitter, bg
+
+
+def oracle_run(model, binary, rays, jitter, bg, target):
+    net, cnet = model.geometry.encoding_with_network, model.texture.network
+    dflat = net.params.detach().cpu().clone().requires_grad_(True)
+    cflat = cnet.params.detach().cpu().clone().requires_grad_(True)
+    from nsr_b200 import configs
+    P = omodels.NerfParams(configs.nerf_blender()['geometry']['xyz_encoding_config'], dflat, cflat)
+    out = omodels.nerf_render(P, rays, binary, 1.5, np.float32(model.render_step_size), bg, jitter=jitter, emulate_fp16=True)
+    loss = omodels.smooth_l1_masked(out['comp_rgb'], target, out['rays_valid']) + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean()
+    loss.backward()
+    return out, loss, dflat.grad, cflat.grad
+
+
+@pytest.mark.parametrize('fused', [True, False])
+def test_nerf_model_forward_backward_parity(fused):
+    model, cfg, binary, rays, jitter, bg = build(fused)
+    assert (model._fused is not None) == fused
+    D = torch.device('cuda:0')
+    target = torch.rand(len(rays), 3, generator=torch.Generator().manual_seed(3))
+    out = model.forward_(torch.from_numpy(rays).to(D), jitter=torch.from_numpy(jitter))
+    assert set(out) == {'comp_rgb', 'opacity', 'depth', 'rays_valid', 'num_samples', 'weights', 'points', 'intervals', 'ray_indices'}
+    assert out['comp_rgb'].shape == (len(rays), 3) and out['opacity'].shape == (len(rays), 1) and out['rays_valid'].dtype == torch.bool
+    assert out['ray_indices'].dtype == torch.int64 and out['num_samples'].dtype == torch.int32
+    loss = omodels.smooth_l1_masked(out['comp_rgb'], target.to(D), out['rays_valid']) + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean()
+    loss.backward()
+    ref, loss_r, gd_r, gc_r = oracle_run(model, binary, rays, jitter, bg, target)
+
+    # ---- sample sets
+    k, k_r = int(out['num_samples'].item()), int(ref['num_samples'].item())
+    ambiguous = int(((ref['trans_pre'] / 1e-4 - 1).abs() < 1e-3).sum())
+    assert ref['num_marched'] > 10000 and 0.2 * ref['num_marched'] < k_r < ref['num_marched']
+    assert abs(k - k_r) <= ambiguous
+    if k == k_r:
+        assert torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
+        assert np.array_equal(out['points'].detach().cpu().numpy(), ref['points'].numpy())
+        assert (out['weights'].detach().cpu() - ref['weights'].detach()).abs().max().item() <= 2e-3
+    # ---- per-ray outputs
+    assert (out['comp_rgb'].detach().cpu() - ref['comp_rgb'].detach()).abs().max().item() <= 5e-3
+    assert (out['opacity'].detach().cpu() - ref['opacity'].detach()).abs().max().item() <= 2e-3
+    assert (out['depth'].detach().cpu() - ref['depth'].detach()).abs().max().item() <= 5e-3
+    assert abs(loss.item() - loss_r.item()) <= 2e-3 * abs(loss_r.item()) + 1e-5
+    # ---- gradients
+    net, cnet = model.geometry.encoding_with_network, model.texture.network
+    gd, gc = net.params.grad.cpu(), cnet.params.grad.cpu()
+    nm = net.mlp.n_params
+    assert cos(gc, gc_r) >= 0.995 and cos(gd[:nm], gd_r[:nm]) >= 0.995
+    assert cos(gd[nm:], gd_r[nm:]) >= 0.99
+    assert (gd[nm:] - gd_r[nm:]).abs().max().item() <= 6e-2 * gd_r[nm:].abs().max().item()
+    assert (gc - gc_r).abs().max().item() <= 6e-2 * gc_r.abs().max().item()
+
+
+def test_fused_equals_composed_and_eval_mode():
+    mf, cfg, binary, rays, jitter, bg = build(True, n_rays=400, seed=5)
+    mc, *_ = build(False, n_rays=400, seed=5)
+    D = torch.device('cuda:0')
+    r = torch.from_numpy(rays).to(D)
+    a = mf.forward_(r, jitter=torch.from_numpy(jitter))
+    b = mc.forward_(r, jitter=torch.from_numpy(jitter))
+    assert abs(int(a['num_samples']) - int(b['num_samples'])) <= 3
+    assert (a['comp_rgb'] - b['comp_rgb']).abs().max().item() <= 5e-3
+    # eval: chunked, no jitter, outputs on the CPU, no per-sample tensors (models/nerf.py:129-144)
+    mf.eval()
+    mf.config['ray_chunk'] = 150
+    with torch.no_grad():
+        e = mf(r)
+    assert set(e) == {'comp_rgb', 'opacity', 'depth', 'rays_valid', 'num_samples'}
+    assert e['comp_rgb'].device.type == 'cpu' and e['comp_rgb'].shape == (400, 3) and e['num_samples'].shape == (3,)
+    # occupancy refresh through the fused density kernel
+    mf.train()
+    mf.update_step(0, 0)
+    frac = mf.occupancy_grid.binary.float().mean().item()
+    assert 0.0 < frac < 1.0
+    x = (torch.rand(1000, 3, device=D) * 2 - 1) * 1.4
+    d_f = mf._fused.density(x)
+    d_c, _ = mc.geometry(x)
+    assert (d_f - d_c).abs().max().item() <= 2e-2 * d_c.abs().max().item()
+
+
+def test_empty_and_degenerate_batches():
+    model, cfg, binary, rays, jitter, bg = build(True, n_rays=64)
+    D = torch.device('cuda:0')
+    # all rays miss the box
+    r = torch.from_numpy(rays).to(D).clone()
+    r[:, :3] = 10.0
+    out = model.forward_(r)
+    assert int(out['num_samples']) == 0 and torch.equal(out['comp_rgb'], model.background_color.expand(64, 3))
+    out['comp_rgb'].sum().backward()  # no samples: gradients are zeros, not errors
+    assert float(model.texture.network.params.grad.abs().sum()) == 0.0
+    # empty occupancy
+    model.occupancy_grid.set_binary(torch.zeros(128, 128, 128, dtype=torch.bool))
+    out = model.forward_(torch.from_numpy(rays).to(D))
+    assert int(out['num_samples']) == 0 and not out['rays_valid'].any()
