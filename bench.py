@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray rendering hot path (BASELINE.json metric: rays/s, fwd+bwd, NeRF-Synthetic-lego
+shape) -- config C2: nerf-blender HashGrid L16/F2/T2^19 + FullyFused-64 fields, 8192 rays per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic rays: march + sigma_fn visibility pre-pass
++ compaction + render forward + masked smooth-L1 loss + backward to every parameter gradient (+ NCCL all-reduce
+of the gradients when N > 1).  The optimizer is outside the path and is not run.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 8192            # per GPU (max_train_num_rays, configs/nerf-blender.yaml:24)
+POOL = 8                 # distinct ray batches cycled through
+CPU_SAMPLE_RAYS = 1024   # rays per step of the CPU arms (bounded sample of the same workload)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arms: the oracle port of the same workload (the reference's own stack -- tiny-cuda-nn + nerfacc --
+# is CUDA-only and not installable offline)
+# --------------------------------------------------------------------------------------------------
+def cpu_workload(n_rays, seed):
+    from oracle import models as om
+    from nsr_b200 import configs, synthetic, ops
+    cfg = configs.nerf_blender()
+    grid = ops.GridSpec(cfg['geometry']['xyz_encoding_config'])
+    mlp = ops.MlpSpec(32, 16, cfg['geometry']['mlp_network_config'])
+    cmlp = ops.MlpSpec(32, 3, cfg['texture']['mlp_network_config'])
+    g = torch.Generator().manual_seed(7)
+    dflat = torch.cat([mlp.init_params(g), (torch.rand(grid.n_params, generator=g) * 2 - 1) * 0.1])
+    synthetic.shape_density(dflat, grid, mlp.n_params)
+    cflat = cmlp.init_params(g)
+    dflat.requires_grad_(True)
+    cflat.requires_grad_(True)
+    P = om.NerfParams(cfg['geometry']['xyz_encoding_config'], dflat, cflat)
+    binary = synthetic.occupancy()
+    step = np.float32(synthetic.render_step_size())
+    tg = torch.Generator().manual_seed(seed)
+
+    def run(i):
+        rays = synthetic.sample_rays(n_rays, seed=seed * 1000 + i)
+        jit = np.random.default_rng(seed * 1000 + i + 1).random(n_rays).astype(np.float32)
+        target = torch.rand(n_rays, 3, generator=tg)
+        bg = torch.rand(3, generator=tg)
+        dflat.grad = cflat.grad = None
+        out = om.nerf_render(P, rays, binary, 1.5, step, bg, jitter=jit, emulate_fp16=False)
+        loss = om.smooth_l1_masked(out['comp_rgb'], target, out['rays_valid'])
+        loss.backward()
+        return int(out['num_samples']), out['num_marched']
+    return run
+
+
+def time_cpu(steps, warmup, n_rays=CPU_SAMPLE_RAYS):
+    torch.set_num_threads(os.cpu_count())
+    run = cpu_workload(n_rays, seed=3)
+    for i in range(warmup):
+        run(i)
+    t0 = time.perf_counter()
+    kept = marched = 0
+    for i in range(steps):
+        k, m = run(warmup + i)
+        kept += k
+        marched += m
+    dt = time.perf_counter() - t0
+    return {'rays_per_s': n_rays * steps / dt, 'ms_per_step': dt / steps * 1e3, 'kept': kept / steps, 'marched': marched / steps,
+            'cores': torch.get_num_threads(), 'n_rays': n_rays}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = time_cpu(max(1, args.steps), max(0, args.warmup))
+    line = {
+        'impl': 'reference', 'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': r['rays_per_s'], 'unit': 'rays/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'nerf-blender lego shape, HashGrid L16 F2 T2^19 + 64-wide MLPs, {N_RAYS} rays/GPU (C2)',
+                   'note': 'the reference stack (tiny-cuda-nn + nerfacc 0.3.3) is CUDA-only and not installable offline; this arm times '
+                           'the fp32 CPU oracle port of the same path on the host cores'},
+        'cpu_baseline': {'value': r['rays_per_s'], 'unit': 'rays/s', 'cores': r['cores'], 'kind': 'port',
+                         'sample': f"{r['n_rays']} rays/step of the C2 workload (marched {r['marched']:.0f}, kept {r['kept']:.0f} samples/step), "
+                                   f"fwd+bwd, torch CPU fp32, {r['cores']} threads"},
+        'e2e': {'value': r['rays_per_s'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f'/tmp/nsr_clocks_{os.getpid()}.csv'
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in open(self.path):
+            c = [x.strip() for x in ln.split(',')]
+            if len(c) < 8 or not c[0].isdigit() or int(c[0]) != self.idx:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def build_model(device, seed=0):
+    from nsr_b200 import models, configs, synthetic
+    cfg = configs.nerf_blender()
+    torch.manual_seed(seed)
+    model = models.make('nerf', cfg).to(device)
+    if model._fused is None:
+        raise RuntimeError('bench: the fused CUDA path was not selected')
+    net = model.geometry.encoding_with_network
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        p = net.params.detach().cpu().clone()
+        p[net.mlp.n_params:] = (torch.rand(net.grid.n_params, generator=g) * 2 - 1) * 0.1
+        synthetic.shape_density(p, net.grid, net.mlp.n_params)
+        net.params.copy_(p.to(device))
+    model.occupancy_grid.set_binary(torch.from_numpy(synthetic.occupancy()))
+    model.train()
+    return model
+
+
+def masked_smooth_l1(comp_rgb, target, valid):
+    """systems/nerf.py:97 without the host sync of boolean indexing: mean over valid rays x 3 channels."""
+    m = valid.float()
+    per = F.smooth_l1_loss(comp_rgb, target, reduction='none') * m
+    return per.sum() / (m.sum() * 3.0).clamp(min=1.0)
+
+
+def gpu_arm(args):
+    import torch.distributed as dist
+    from nsr_b200 import synthetic
+    from nsr_b200.lib import lib
+    from nsr_b200.parallel import GradSync
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = build_model(dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    sync = GradSync(params, world) if world > 1 else None
+    # inputs: POOL batches of rays / targets, different per rank (the reference seeds all ranks alike)
+    rays_np = [synthetic.sample_rays(N_RAYS, seed=1000 * rank + i) for i in range(POOL)]
+    tg = torch.Generator().manual_seed(99 + rank)
+    tgt_np = [torch.rand(N_RAYS, 3, generator=tg) for _ in range(POOL)]
+    rays_dev = [torch.from_numpy(r).to(dev) for r in rays_np]
+    tgt_dev = [t.to(dev) for t in tgt_np]
+    rays_pin = [torch.from_numpy(r).pin_memory() for r in rays_np]
+    tgt_pin = [t.pin_memory() for t in tgt_np]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    stats = {'kept': 0, 'marched': 0}
+
+    def step(rays, target, do_sync=True):
+        model.background_color = torch.rand(3, device=dev)  # systems/nerf.py:71
+        out = model(rays)                                    # public API: NeRFModel.forward
+        loss = masked_smooth_l1(out['comp_rgb'], target, out['rays_valid'])
+        for p in params:
+            p.grad = None
+        loss.backward()
+        if sync is not None and do_sync:
+            sync.all_reduce_mean()
+        stats['kept'] += model._fused.last_stats['n_kept']
+        stats['marched'] += model._fused.last_stats['n_marched']
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        """sum of per-step CUDA-event times; L2 flushed (untimed) before every step."""
+        evs = []
+        host_t = 0.0
+        for i in range(nsteps):
+            j = i % POOL
+            flush.fill_(float(i))
+            if e2e:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = rays_pin[j].to(dev, non_blocking=True)
+                t = tgt_pin[j].to(dev, non_blocking=True)
+                loss = step(r, t)
+                _ = loss.item()                         # device -> host read of the step's result
+                host_t += time.perf_counter() - t0
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(rays_dev[j], tgt_dev[j])
+                e1.record()
+                evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if e2e:
+            return host_t * 1e3
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- warm-up
+    for i in range(max(3, args.warmup)):
+        step(rays_dev[i % POOL], tgt_dev[i % POOL])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, inputs resident in HBM
+    stats.update(kept=0, marched=0)
+    lib.launches = 0
+    barrier()
+    ms = timed(args.steps, e2e=False)
+    barrier()
+    launches = lib.launches
+    kept, marched = stats['kept'] / args.steps, stats['marched'] / args.steps
+    # ---- end-to-end: host buffers in, loss out, same K steps
+    barrier()
+    ms_e2e = timed(args.steps, e2e=True)
+    barrier()
+    # keep the GPU under the same load until the clock sampler has seen it (short timed regions)
+    if rank == 0:
+        t_end = time.time() + max(0.0, 1.5 - (ms + ms_e2e) / 1e3)
+        while time.time() < t_end:
+            step(rays_dev[0], tgt_dev[0], do_sync=False)
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        cnt = torch.tensor([kept, marched], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        kept, marched = cnt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel durations (CUDA events around every C-ABI call, separate pass, same workload)
+    lib.profile = {}
+    for i in range(min(args.steps, 20)):
+        flush.fill_(1.0)
+        step(rays_dev[i % POOL], tgt_dev[i % POOL], do_sync=False)
+    torch.cuda.synchronize()
+    kern = {}
+    for name, evs in lib.profile.items():
+        kern[name] = {'ms': sum(a.elapsed_time(b) for a, b in evs) / len(evs), 'launches_per_step': len(evs) / min(args.steps, 20)}
+    lib.profile = None
+    peak, peak_src = peaks()
+    ms_step = ms / args.steps
+    k1, m1 = kept / world, marched / world          # per GPU
+    alg = {'nsr_nerf_prepass': 512.0 * m1, 'nsr_nerf_render_fwd': 512.0 * k1, 'nsr_nerf_field_bwd': 512.0 * k1}
+    dom = max((n for n in alg if n in kern), key=lambda n: kern[n]['ms'] * kern[n]['launches_per_step'], default=None)
+    roofline = None
+    if dom is not None:
+        ach = alg[dom] / (kern[dom]['ms'] * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom],
+                    'whole_step': {'algorithmic_bytes': 1024.0 * k1 + 512.0 * m1,
+                                   'achieved': (1024.0 * k1 + 512.0 * m1) / (ms_step * 1e-3) / 1e9,
+                                   'frac': (1024.0 * k1 + 512.0 * m1) / (ms_step * 1e-3) / 1e9 / peak}}
+    cpu = time_cpu(2, 1) if world == 1 else None
+    line = {
+        'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': f'nerf-blender lego shape, HashGrid L16 F2 T2^19 + FullyFused-64 fields, {N_RAYS} rays/GPU (C2)',
+                   'rays_per_gpu': N_RAYS, 'marched_samples_per_step': marched, 'kept_samples_per_step': kept,
+                   'samples_per_s': kept * args.steps / (ms * 1e-3), 'l2': 'flushed (256 MB write) before every timed step',
+                   'parallelism': f'dp{world}' if world > 1 else 'single', 'step': 'march+prepass+fwd+smooth_l1+bwd' + ('+allreduce' if world > 1 else '')},
+        'e2e': {'value': N_RAYS * world * args.steps / (ms_e2e * 1e-3), 'unit': 'rays/s',
+                'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4 + 2 * 8},
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels_ms': {k: round(v['ms'], 5) for k, v in kern.items()},
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = {'value': cpu['rays_per_s'], 'unit': 'rays/s', 'cores': cpu['cores'], 'kind': 'port',
+                                'sample': f"2 steps x {cpu['n_rays']} rays of the C2 workload (kept {cpu['kept']:.0f} samples/step), fwd+bwd, "
+                                          f"fp32 CPU oracle, {cpu['cores']} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -77,6 +77,8 @@ _SIGNATURES = {
 class _Lib:
     def __init__(self):
         self._dll = None
+        self.launches = 0     # C-ABI calls that launch one of our kernels (bench.py reports it)
+        self.profile = None   # dict name -> [(start_event, end_event)] when per-call CUDA-event timing is on
 
     def _load(self):
         path = library_path()
@@ -103,9 +105,16 @@ class _Lib:
 
     def call(self, name, *args):
         fn = getattr(self.dll, name)
+        if self.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = fn(*args)
         if rc != 0:
             raise NsrError(f'{name} failed ({rc}): {self.dll.nsr_last_error().decode()}')
+        self.launches += 1
+        if self.profile is not None:
+            e1.record()
+            self.profile.setdefault(name, []).append((e0, e1))
 
 
 lib = _Lib()
