@@ -193,19 +193,18 @@ def gpu_arm(args):
     from nsr_b200 import synthetic
     from nsr_b200.lib import lib
     from nsr_b200.parallel import GradSync
+    from nsr_b200.graph import GraphedStep
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit('bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)')
+    if world == 1 and args.gpus > 1:
+        raise SystemExit('bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     model = build_model(dev)
     params = [p for p in model.parameters() if p.requires_grad]
-    sync = GradSync(params, world) if world > 1 else None
     # inputs: POOL batches of rays / targets, different per rank (the reference seeds all ranks alike)
     rays_np = [synthetic.sample_rays(N_RAYS, seed=1000 * rank + i) for i in range(POOL)]
     tg = torch.Generator().manual_seed(99 + rank)
@@ -216,19 +215,28 @@ def gpu_arm(args):
     tgt_pin = [t.pin_memory() for t in tgt_np]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
-    stats = {'kept': 0, 'marched': 0}
+    def loss_fn(out, batch):
+        return masked_smooth_l1(out['comp_rgb'], batch['rgb'], out['rays_valid'])
+
+    # the public fast path: whole step (march .. backward) as one CUDA graph, no host sync inside
+    gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3)
+    sync = GradSync(params, world) if world > 1 else None
 
     def step(rays, target, do_sync=True):
-        model.background_color = torch.rand(3, device=dev)  # systems/nerf.py:71
-        out = model(rays)                                    # public API: NeRFModel.forward
+        bg = torch.rand(3, device=dev)                      # systems/nerf.py:71 (random background per step)
+        loss = gstep(rays, rgb=target, background_color=bg)
+        if sync is not None and do_sync:
+            sync.all_reduce_mean()
+        return loss
+
+    def eager_step(rays, target):
+        """the same step through the eager public API (NeRFModel.forward), exact-size outputs, ~40 launches from Python"""
+        model.background_color = torch.rand(3, device=dev)
+        out = model(rays)
         loss = masked_smooth_l1(out['comp_rgb'], target, out['rays_valid'])
         for p in params:
             p.grad = None
         loss.backward()
-        if sync is not None and do_sync:
-            sync.all_reduce_mean()
-        stats['kept'] += model._fused.last_stats['n_kept']
-        stats['marched'] += model._fused.last_stats['n_marched']
         return loss
 
     def barrier():
@@ -236,33 +244,28 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e):
-        """sum of per-step CUDA-event times; L2 flushed (untimed) before every step."""
-        evs = []
-        host_t = 0.0
+    def timed(nsteps, e2e, fn=step):
+        """sum of per-step times; L2 flushed (untimed) before every step.  e2e: host-clock per step including the
+        H2D copies of that step's inputs and the D2H read of its loss."""
+        evs, host_t = [], 0.0
         for i in range(nsteps):
             j = i % POOL
             flush.fill_(float(i))
             if e2e:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                r = rays_pin[j].to(dev, non_blocking=True)
-                t = tgt_pin[j].to(dev, non_blocking=True)
-                loss = step(r, t)
-                _ = loss.item()                         # device -> host read of the step's result
+                loss = fn(rays_pin[j], tgt_pin[j])
+                _ = loss.item()
                 host_t += time.perf_counter() - t0
             else:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                step(rays_dev[j], tgt_dev[j])
+                fn(rays_dev[j], tgt_dev[j])
                 e1.record()
                 evs.append((e0, e1))
         torch.cuda.synchronize()
-        if e2e:
-            return host_t * 1e3
-        return sum(a.elapsed_time(b) for a, b in evs)
+        return host_t * 1e3 if e2e else sum(a.elapsed_time(b) for a, b in evs)
 
-    # ---- warm-up
     for i in range(max(3, args.warmup)):
         step(rays_dev[i % POOL], tgt_dev[i % POOL])
     barrier()
@@ -270,24 +273,30 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     # ---- timed region: exactly K steps, inputs resident in HBM
-    stats.update(kept=0, marched=0)
     lib.launches = 0
     barrier()
     ms = timed(args.steps, e2e=False)
     barrier()
     launches = lib.launches
-    kept, marched = stats['kept'] / args.steps, stats['marched'] / args.steps
-    # ---- end-to-end: host buffers in, loss out, same K steps
+    # ---- end-to-end: pinned host buffers in, loss out, same K steps
     barrier()
     ms_e2e = timed(args.steps, e2e=True)
     barrier()
-    # keep the GPU under the same load until the clock sampler has seen it (short timed regions)
+    clocks = None
     if rank == 0:
+        # keep the GPU under the same load until the clock sampler has seen it (short timed regions)
         t_end = time.time() + max(0.0, 1.5 - (ms + ms_e2e) / 1e3)
         while time.time() < t_end:
             step(rays_dev[0], tgt_dev[0], do_sync=False)
         torch.cuda.synchronize()
         clocks = sampler.stop()
+    # ---- sample counts of the workload (one replay per pool batch, read back)
+    kept = marched = 0.0
+    for j in range(POOL):
+        step(rays_dev[j], tgt_dev[j], do_sync=False)
+        mm, kk = gstep.counts()
+        marched += mm / POOL
+        kept += kk / POOL
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -295,20 +304,23 @@ def gpu_arm(args):
         cnt = torch.tensor([kept, marched], device=dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         kept, marched = cnt.tolist()
-    if rank != 0:
-        if world > 1:
+        dist.barrier()
+        if rank != 0:
             dist.destroy_process_group()
-        return
+            return
 
-    # ---- per-kernel durations (CUDA events around every C-ABI call, separate pass, same workload)
+    # ---- rank 0: eager-API timing and per-kernel durations (CUDA events around every C-ABI call; same workload)
+    nprof = min(args.steps, 20)
+    for i in range(3):
+        eager_step(rays_dev[i % POOL], tgt_dev[i % POOL])
+    ms_eager = timed(nprof, e2e=False, fn=eager_step) / nprof
     lib.profile = {}
-    for i in range(min(args.steps, 20)):
+    for i in range(nprof):
         flush.fill_(1.0)
-        step(rays_dev[i % POOL], tgt_dev[i % POOL], do_sync=False)
+        eager_step(rays_dev[i % POOL], tgt_dev[i % POOL])
     torch.cuda.synchronize()
-    kern = {}
-    for name, evs in lib.profile.items():
-        kern[name] = {'ms': sum(a.elapsed_time(b) for a, b in evs) / len(evs), 'launches_per_step': len(evs) / min(args.steps, 20)}
+    kern = {name: {'ms': sum(a.elapsed_time(b) for a, b in evs) / len(evs), 'launches_per_step': len(evs) / nprof}
+            for name, evs in lib.profile.items()}
     lib.profile = None
     peak, peak_src = peaks()
     ms_step = ms / args.steps
@@ -318,11 +330,11 @@ def gpu_arm(args):
     roofline = None
     if dom is not None:
         ach = alg[dom] / (kern[dom]['ms'] * 1e-3) / 1e9
+        step_bytes = 1024.0 * k1 + 512.0 * m1
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom],
-                    'whole_step': {'algorithmic_bytes': 1024.0 * k1 + 512.0 * m1,
-                                   'achieved': (1024.0 * k1 + 512.0 * m1) / (ms_step * 1e-3) / 1e9,
-                                   'frac': (1024.0 * k1 + 512.0 * m1) / (ms_step * 1e-3) / 1e9 / peak}}
+                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom], 'kernel_ms': kern[dom]['ms'],
+                    'whole_step': {'algorithmic_bytes': step_bytes, 'achieved': step_bytes / (ms_step * 1e-3) / 1e9,
+                                   'frac': step_bytes / (ms_step * 1e-3) / 1e9 / peak}}
     cpu = time_cpu(2, 1) if world == 1 else None
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
@@ -331,9 +343,11 @@ def gpu_arm(args):
         'config': {'workload': f'nerf-blender lego shape, HashGrid L16 F2 T2^19 + FullyFused-64 fields, {N_RAYS} rays/GPU (C2)',
                    'rays_per_gpu': N_RAYS, 'marched_samples_per_step': marched, 'kept_samples_per_step': kept,
                    'samples_per_s': kept * args.steps / (ms * 1e-3), 'l2': 'flushed (256 MB write) before every timed step',
-                   'parallelism': f'dp{world}' if world > 1 else 'single', 'step': 'march+prepass+fwd+smooth_l1+bwd' + ('+allreduce' if world > 1 else '')},
+                   'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'step': 'march+prepass+fwd+smooth_l1+bwd as one CUDA graph (nsr_b200.graph.GraphedStep)' + (' + NCCL all-reduce of grads' if world > 1 else ''),
+                   'eager_api_ms_per_step': ms_eager},
         'e2e': {'value': N_RAYS * world * args.steps / (ms_e2e * 1e-3), 'unit': 'rays/s',
-                'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4 + 2 * 8},
+                'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels_ms': {k: round(v['ms'], 5) for k, v in kern.items()},
     }
     if cpu is not None:

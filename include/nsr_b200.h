@@ -134,7 +134,10 @@ int nsr_weight_from_alpha_bwd(const float* alphas, const float* weights, const f
 /* nerfacc.accumulate_along_rays (models/nerf.py:106-108): out[n_rays,d] = segmented sum of w*v. */
 int nsr_accumulate(const float* weights, const float* values, const int64_t* offsets, float* out, int32_t d, int64_t n_rays, void* stream);
 
-/* ---- fused NeRF path (module-level surface: NeRFModel.forward_, models/nerf.py:61-127) ---------------- */
+/* ---- fused NeRF path (module-level surface: NeRFModel.forward_, models/nerf.py:61-127) ----------------
+ * Sample counts may live on the device: where an entry point takes (n, n_dev), a non-NULL n_dev (device int64)
+ * holds the true count and n is the buffer capacity -- no host sync, so a whole step can be captured in a CUDA
+ * graph.  n_dev == NULL: n is the count. */
 
 /* density at world positions (occ_eval_fn of models/nerf.py:49-52; VolumeDensity.forward density-only).
  * positions f32 [n,3]; dparams fp16 flat [3072 MLP | table]; density f32 [n]. */
@@ -142,7 +145,7 @@ int nsr_nerf_density(const nsr_nerf_t* f, const float* positions, const void* dp
 /* sigma_fn pre-pass of ray_marching (models/nerf.py:65-71,87): marched samples (ray_indices i32, t_starts,
  * t_ends [m]) over rays f32 [n_rays,6] -> alphas[m] = 1 - exp(-sigma * (t_end - t_start)). */
 int nsr_nerf_prepass(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                     const void* dparams_h, float* alphas, int64_t m, void* stream);
+                     const void* dparams_h, float* alphas, int64_t m, const int64_t* m_dev, void* stream);
 /* boolean-mask compaction of the pre-pass (the three `tensor[mask]` of nerfacc.ray_marching): with alpha_thre == 0
  * the kept samples of a ray are a prefix, so ray r's first kept_counts[r] samples move from offsets_m[r] to
  * offsets_k[r].  trans (exclusive transmittance from nsr_visibility) travels with them. */
@@ -154,7 +157,7 @@ int nsr_compact_prefix(const int64_t* offsets_m, const int64_t* offsets_k, const
  * accumulated).  enc_save (fp16 [k,32], may be NULL) keeps the encoded features for the backward pass. */
 int nsr_nerf_render_fwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
                         const float* trans, const void* dparams_h, const void* cparams_h, void* enc_save_h, float* sigmas, float* rgbs,
-                        float* weights, float* acc_rgb, float* opacity, float* depth, int64_t k, void* stream);
+                        float* weights, float* acc_rgb, float* opacity, float* depth, int64_t k, const int64_t* k_dev, void* stream);
 /* backward through the compositing (autograd of render_weight_from_density + accumulate_along_rays x3) and the
  * density activation: per-ray grads (g_rgb [n_rays,3], g_opacity, g_depth [n_rays]; g_weights [k] optional) ->
  * d_sraw [k] = dL/d(out0) (trunc_exp backward, models/utils.py:64-66, folded in), d_rgb [k,3].
@@ -168,7 +171,8 @@ int nsr_nerf_ray_bwd(const int64_t* offsets_k, const float* t_starts, const floa
  * on the device from *amax (no host sync). */
 int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
                        const void* enc_save_h, const void* dparams_h, const void* cparams_h, const float* d_sraw, const float* d_rgb,
-                       float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, void* stream);
+                       float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_bwd_kernel(const __grid_cons
                                                                const __half* __restrict__ dparams, const __half* __restrict__ cparams,
                                                                const float* __restrict__ d_sraw, const float* __restrict__ d_rgb,
                                                                float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
-                                                               float loss_scale, const float* __restrict__ amax_ptr, int64_t n) {
+                                                               float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + NF_W_TOTAL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_bwd_kernel(const __grid_cons
 extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
                                   const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
                                   const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
-                                  const float* amax, int64_t k, void* stream) {
+                                  const float* amax, int64_t k, const int64_t* k_dev, void* stream) {
   NSR_REQUIRE(f != nullptr, "nsr_nerf_field_bwd: field descriptor is NULL");
   NSR_REQUIRE(f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 && f->color_hidden == 2,
               "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
@@ -283,9 +284,10 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
   }
   const int64_t tiles = (k + kRows - 1) / kRows;
   int grid = (int)min((int64_t)nsr_sm_count(), tiles);
+  if (k_dev != nullptr) grid = nsr_sm_count();
   nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
                                                                         (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                        grad_dparams, grad_cparams, loss_scale, amax, k);
+                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
   return 0;
 }

@@ -31,7 +31,8 @@ struct FwdArgs {
   float* acc_rgb;             // [n_rays,3]
   float* opacity;             // [n_rays]
   float* depth;               // [n_rays]
-  int64_t n;
+  int64_t n;                  // sample count (capacity when n_dev is set)
+  const int64_t* n_dev;       // optional: the count lives on the device (no host sync / graph capture)
 };
 
 template <int MODE>
@@ -46,10 +47,11 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_fwd_kernel(const __grid_cons
   nf_stage_weights(smem, a.dparams, a.cparams, MODE == MODE_RENDER);
   __syncthreads();
 
-  const int64_t n_tiles = (a.n + 31) / 32;
+  const int64_t n_total = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  const int64_t n_tiles = (n_total + 31) / 32;
   for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
     const int64_t i = tile * 32 + lane;
-    const bool valid = i < a.n;
+    const bool valid = i < n_total;
     float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, t0 = 0.f, t1 = 0.f;
     int ray = -1;
     if (valid) {
@@ -294,6 +296,7 @@ int launch_fwd(const nsr_nerf_t* f, const FwdArgs& a, cudaStream_t st, const cha
   const int64_t tiles = (a.n + 31) / 32;
   int grid = (int)min((int64_t)nsr_sm_count() * 2, (tiles + kWarps - 1) / kWarps);
   if (grid < 1) grid = 1;
+  if (a.n_dev != nullptr) grid = nsr_sm_count() * 2;  // count unknown on the host: full persistent grid
   nerf_fwd_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(*f, a);
   NSR_CHECK_LAUNCH(name);
   return 0;
@@ -312,8 +315,9 @@ extern "C" int nsr_nerf_density(const nsr_nerf_t* f, const float* positions, con
 }
 
 extern "C" int nsr_nerf_prepass(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
-                                const float* t_ends, const void* dparams_h, float* alphas, int64_t m, void* stream) {
+                                const float* t_ends, const void* dparams_h, float* alphas, int64_t m, const int64_t* m_dev, void* stream) {
   FwdArgs a = {};
+  a.n_dev = m_dev;
   a.rays = rays;
   a.ray_indices = ray_indices;
   a.t_starts = t_starts;
@@ -327,8 +331,9 @@ extern "C" int nsr_nerf_prepass(const nsr_nerf_t* f, const float* rays, const in
 extern "C" int nsr_nerf_render_fwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
                                    const float* t_ends, const float* trans, const void* dparams_h, const void* cparams_h,
                                    void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* acc_rgb, float* opacity,
-                                   float* depth, int64_t k, void* stream) {
+                                   float* depth, int64_t k, const int64_t* k_dev, void* stream) {
   FwdArgs a = {};
+  a.n_dev = k_dev;
   a.rays = rays;
   a.ray_indices = ray_indices;
   a.t_starts = t_starts;

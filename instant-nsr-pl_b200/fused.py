@@ -5,9 +5,13 @@
     ->  render forward (hash + both MLPs + compositing, one launch)
     <-  ray backward (compositing)  <-  field backward (MLPs + hash scatter, one launch)
 
-All arithmetic is in libnsr_b200.so; this file only allocates outputs, passes pointers and wires autograd.
+Sample counts stay on the device (capacity-sized buffers + device-side counters), so the pipeline contains no
+host synchronisation and can be captured in a CUDA graph (``nsr_b200.graph.GraphedStep``).  The reference's
+exact-size output contract (``ray_indices/weights/...`` of length K) costs one device->host read at the end of
+the forward.  All arithmetic is in libnsr_b200.so; this file only allocates, passes pointers and wires autograd.
 """
 import ctypes
+import math
 
 import torch
 
@@ -17,47 +21,50 @@ from .nerfacc import ContractionType
 
 
 class _NerfRender(torch.autograd.Function):
+    """(dparams, cparams) -> per-ray sums + per-sample weights; everything else rides along non-differentiably."""
+
     @staticmethod
-    def forward(ctx, dparams, cparams, fused, rays, jitter, keep_aux):
+    def forward(ctx, dparams, cparams, fused, rays, jitter):
         st = fused.trace(rays, jitter)
-        n_rays, k = rays.shape[0], st['k']
+        n_rays, cap = rays.shape[0], st['cap']
         dev = rays.device
         acc_rgb = torch.zeros(n_rays, 3, device=dev)
         opacity = torch.zeros(n_rays, 1, device=dev)
         depth = torch.zeros(n_rays, 1, device=dev)
-        sig = torch.empty(k, device=dev)
-        rgbs = torch.empty(k, 3, device=dev)
-        weights = torch.empty(k, device=dev)
+        sig = torch.empty(cap, device=dev)
+        rgbs = torch.empty(cap, 3, device=dev)
+        weights = torch.empty(cap, device=dev)
         need_grad = dparams.requires_grad or cparams.requires_grad
-        enc = torch.empty(k, 32, dtype=torch.float16, device=dev) if need_grad else None
+        enc = torch.empty(cap, 32, dtype=torch.float16, device=dev) if need_grad else None
         dh, ch = fused.dparams_half(), fused.cparams_half()
+        k_dev = st['offsets_k'][n_rays:]
         lib.call('nsr_nerf_render_fwd', fused.ref(), ptr(rays), ptr(st['ri']), ptr(st['ts']), ptr(st['te']), ptr(st['trans']), ptr(dh),
-                 ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(acc_rgb), ptr(opacity), ptr(depth), k, stream())
-        ctx.fused = fused
-        ctx.n_rays, ctx.k = n_rays, k
+                 ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(acc_rgb), ptr(opacity), ptr(depth), cap, ptr(k_dev), stream())
+        ctx.fused, ctx.n_rays, ctx.cap = fused, n_rays, cap
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(rays, st['ri'], st['ts'], st['te'], st['trans'], st['offsets_k'], enc, sig, rgbs, weights, dh, ch)
-        ctx.mark_non_differentiable(st['ri'], st['ts'], st['te'])
-        fused.last_stats = {'n_marched': st['m'], 'n_kept': k}
-        return acc_rgb, opacity, depth, weights, st['ri'], st['ts'], st['te']
+        counts = torch.cat([st['offsets_m'][n_rays:], k_dev])  # [M, K] on the device
+        ctx.mark_non_differentiable(st['ri'], st['ts'], st['te'], counts)
+        return acc_rgb, opacity, depth, weights, st['ri'], st['ts'], st['te'], counts
 
     @staticmethod
     def backward(ctx, g_rgb, g_op, g_depth, g_w, *_):
         fused = ctx.fused
         rays, ri, ts, te, trans, offsets_k, enc, sig, rgbs, weights, dh, ch = ctx.saved_tensors
         dev = rays.device
-        k, n_rays = ctx.k, ctx.n_rays
+        n_rays, cap = ctx.n_rays, ctx.cap
         gd = torch.zeros(fused.n_dparams, device=dev)
         gc = torch.zeros(fused.n_cparams, device=dev)
-        if k > 0:
-            d_sraw = torch.empty(k, device=dev)
-            d_rgb = torch.empty(k, 3, device=dev)
+        if cap > 0 and enc is not None:
+            d_sraw = torch.empty(cap, device=dev)
+            d_rgb = torch.empty(cap, 3, device=dev)
             amax = torch.zeros(1, device=dev)
-            lib.call('nsr_nerf_ray_bwd', ptr(offsets_k), ptr(ts), ptr(te), ptr(trans), ptr(weights), ptr(sig), ptr(rgbs),
-                     ptr(contig(g_rgb, torch.float32)), ptr(contig(g_op, torch.float32)), ptr(contig(g_depth, torch.float32)),
-                     ptr(contig(g_w, torch.float32)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n_rays, stream())
+            f32 = lambda t: None if t is None else contig(t, torch.float32)
+            lib.call('nsr_nerf_ray_bwd', ptr(offsets_k), ptr(ts), ptr(te), ptr(trans), ptr(weights), ptr(sig), ptr(rgbs), ptr(f32(g_rgb)),
+                     ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n_rays, stream())
             lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc), ptr(dh), ptr(ch), ptr(d_sraw),
-                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), k, stream())
-        return gd, gc, None, None, None, None
+                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n_rays:]), stream())
+        return gd, gc, None, None, None
 
 
 class NerfFused:
@@ -70,12 +77,16 @@ class NerfFused:
         self.cnet = tex.network                        # tcnn.Network
         self.grid = self.net.grid
         self.n_dparams, self.n_cparams = self.net.params.numel(), self.cnet.params.numel()
+        r = float(model.config.radius)
         s = NerfT()
         s.grid = self.grid.struct
-        s.radius = float(model.config.radius)
+        s.radius = r
         s.density_bias = float(geo.config.density_bias)
         s.feature_dim, s.density_hidden, s.color_hidden = 16, 1, 2
         self.struct = s
+        self.march = ops.march_struct([-r, -r, -r, r, r, r], model.occupancy_grid_res, ContractionType.AABB.value, model.render_step_size, 0.0)
+        # a ray crosses at most the box diagonal: upper bound on marched samples per ray (capacity of the static buffers)
+        self.cap_per_ray = int(math.ceil(2.0 * math.sqrt(3.0) * r / model.render_step_size)) + 2
         self.loss_scale = 0.0  # <= 0: chosen on the device from the incoming gradient magnitude
         self.early_stop_eps, self.alpha_thre = 1e-4, 0.0
         self.last_stats = {}
@@ -123,50 +134,65 @@ class NerfFused:
 
     @torch.no_grad()
     def trace(self, rays, jitter=None):
-        """march + sigma_fn visibility pre-pass + compaction: the `with torch.no_grad(): ray_marching(...)`
-        block of models/nerf.py:82-93.  Returns the kept samples with their exclusive transmittance."""
+        """march + sigma_fn visibility pre-pass + compaction: the ``with torch.no_grad(): ray_marching(...)`` block of
+        models/nerf.py:82-93, without a host sync.  Buffers have capacity n_rays * cap_per_ray; the true counts
+        are offsets_m[n_rays] (marched) and offsets_k[n_rays] (kept) on the device."""
         m = self.model
         dev = rays.device
         n = rays.shape[0]
+        cap = n * self.cap_per_ray
+        mref = ctypes.byref(self.march)
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
         t_min, t_max = ops.ray_aabb_intersect(rays_o, rays_d, m.scene_aabb)
         if m.randomized:
             u = torch.rand(n, device=dev) if jitter is None else jitter.to(dev, torch.float32)
             t_min = t_min + u * m.render_step_size
-        grid = m.occupancy_grid
-        ms = ops.march_struct(grid.roi_aabb.tolist(), grid._res, ContractionType.AABB.value, m.render_step_size, 0.0)
-        ri_m, ts_m, te_m, off_m = ops.march(ms, rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), grid.bits())
-        mcount = ri_m.shape[0]
-        offsets_k = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        if mcount == 0:
-            e = torch.empty(0, device=dev)
-            return {'ri': ri_m, 'ts': e, 'te': e, 'trans': e, 'offsets_k': offsets_k, 'k': 0, 'm': 0}
-        alphas = torch.empty(mcount, device=dev)
-        lib.call('nsr_nerf_prepass', self.ref(), ptr(rays), ptr(ri_m), ptr(ts_m), ptr(te_m), ptr(self.dparams_half()), ptr(alphas), mcount,
-                 stream())
-        keep = torch.empty(mcount, dtype=torch.uint8, device=dev)
-        trans = torch.empty(mcount, device=dev)
-        kept = torch.empty(n, dtype=torch.int32, device=dev)
-        lib.call('nsr_visibility', ptr(alphas), ptr(off_m), ptr(keep), ptr(trans), ptr(kept), self.early_stop_eps, self.alpha_thre, n, stream())
+        bits = m.occupancy_grid.bits()
+        i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
+        f32 = lambda k: torch.empty(k, dtype=torch.float32, device=dev)
+        counts, offsets_m = i32(n), torch.empty(n + 1, dtype=torch.int64, device=dev)
+        lib.call('nsr_march_count', mref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(counts), n, stream())
+        lib.call('nsr_scan_counts', ptr(counts), ptr(offsets_m), n, stream())
+        ri_m, ts_m, te_m = i32(cap), f32(cap), f32(cap)
+        lib.call('nsr_march_write', mref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(offsets_m), ptr(ri_m), ptr(ts_m),
+                 ptr(te_m), n, stream())
+        alphas = f32(cap)
+        lib.call('nsr_nerf_prepass', self.ref(), ptr(rays), ptr(ri_m), ptr(ts_m), ptr(te_m), ptr(self.dparams_half()), ptr(alphas), cap,
+                 ptr(offsets_m[n:]), stream())
+        keep = torch.empty(cap, dtype=torch.uint8, device=dev)
+        trans, kept = f32(cap), i32(n)
+        lib.call('nsr_visibility', ptr(alphas), ptr(offsets_m), ptr(keep), ptr(trans), ptr(kept), self.early_stop_eps, self.alpha_thre, n, stream())
+        offsets_k = torch.empty(n + 1, dtype=torch.int64, device=dev)
         lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
-        k = int(offsets_k[n].item())  # exact-size outputs are part of the reference's return contract
-        ri = torch.empty(k, dtype=torch.int32, device=dev)
-        ts, te, tr = torch.empty(k, device=dev), torch.empty(k, device=dev), torch.empty(k, device=dev)
-        if k > 0:
-            lib.call('nsr_compact_prefix', ptr(off_m), ptr(offsets_k), ptr(ri_m), ptr(ts_m), ptr(te_m), ptr(trans), ptr(ri), ptr(ts), ptr(te),
-                     ptr(tr), n, stream())
-        return {'ri': ri, 'ts': ts, 'te': te, 'trans': tr, 'offsets_k': offsets_k, 'k': k, 'm': mcount}
+        ri, ts, te, tr = i32(cap), f32(cap), f32(cap), f32(cap)
+        lib.call('nsr_compact_prefix', ptr(offsets_m), ptr(offsets_k), ptr(ri_m), ptr(ts_m), ptr(te_m), ptr(trans), ptr(ri), ptr(ts), ptr(te),
+                 ptr(tr), n, stream())
+        return {'ri': ri, 'ts': ts, 'te': te, 'trans': tr, 'offsets_m': offsets_m, 'offsets_k': offsets_k, 'cap': cap}
 
-    def render(self, rays, jitter=None):
-        """NeRFModel.forward_ (models/nerf.py:61-127) -> the reference's output dict."""
+    def render(self, rays, jitter=None, static=False):
+        """NeRFModel.forward_ (models/nerf.py:61-127) -> the reference's output dict.
+
+        static=False: exact-size per-sample outputs (one device->host read of the counts).
+        static=True : no host sync -- per-sample tensors keep their capacity length (entries past
+        ``num_samples`` are undefined); this is the form CUDA-graph capture uses."""
         m = self.model
         check_cuda(rays, what='NeRFModel')
         rays = contig(rays, torch.float32)
-        acc_rgb, opacity, depth, weights, ri, ts, te = _NerfRender.apply(self.net.params, self.cnet.params, self, rays, jitter, m.training)
+        acc_rgb, opacity, depth, weights, ri, ts, te, counts = _NerfRender.apply(self.net.params, self.cnet.params, self, rays, jitter)
         comp_rgb = acc_rgb + m.background_color * (1.0 - opacity)
         out = {'comp_rgb': comp_rgb, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
-               'num_samples': torch.as_tensor([ts.shape[0]], dtype=torch.int32, device=rays.device)}
-        if m.training:
-            out.update({'weights': weights.view(-1), 'points': ((ts + te) / 2.).view(-1), 'intervals': (te - ts).view(-1),
-                        'ray_indices': ri.long().view(-1)})
+               'num_samples': counts[1:].to(torch.int32)}
+        if static:
+            self.last_stats = {'counts_dev': counts}
+            k = None
+        else:
+            n_marched, k = counts.tolist()
+            self.last_stats = {'n_marched': n_marched, 'n_kept': k}
+        if m.training and static:
+            # capacity-length raw buffers (no per-sample torch ops over the capacity): entries past num_samples are undefined
+            out.update({'weights': weights, 't_starts': ts, 't_ends': te, 'ray_indices': ri})
+        elif m.training:
+            w, ts_, te_, ri_ = weights[:k], ts[:k], te[:k], ri[:k]
+            out.update({'weights': w.view(-1), 'points': ((ts_ + te_) / 2.).view(-1), 'intervals': (te_ - ts_).view(-1),
+                        'ray_indices': ri_.long().view(-1)})
         return out

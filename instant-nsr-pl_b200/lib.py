@@ -66,11 +66,11 @@ _SIGNATURES = {
     'nsr_weight_from_alpha_bwd': [P, P, P, P, P, P, I64, P],
     'nsr_accumulate': [P, P, P, P, I32, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],
-    'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P],
+    'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P, P],
     'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_nerf_render_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_nerf_render_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P],
     'nsr_nerf_ray_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_nerf_field_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, F32, P, I64, P],
+    'nsr_nerf_field_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, F32, P, I64, P, P],
 }
 
 

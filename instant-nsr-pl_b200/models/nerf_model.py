@@ -104,9 +104,13 @@ class NeRFModel(BaseModel):
                         'ray_indices': ray_indices.view(-1)})
         return out
 
-    def forward_(self, rays, jitter=None):
+    def forward_(self, rays, jitter=None, static=False):
+        """static=True (fused path only): no host synchronisation, capacity-length per-sample outputs; this is
+        what ``nsr_b200.graph.GraphedStep`` captures into a CUDA graph."""
         if self._fused is not None:
-            return self._fused.render(rays, jitter=jitter)
+            return self._fused.render(rays, jitter=jitter, static=static)
+        if static:
+            raise RuntimeError('static (sync-free) rendering needs the fused CUDA path')
         return self._render_composed(rays, jitter=jitter)
 
     def forward(self, rays):

@@ -42,8 +42,8 @@ if __name__ == '__main__':
     f = m._fused
     target = torch.rand(n, 3, device=D)
     res = {}
-    st = f.trace(rays)
-    res['M'], res['K'] = st['m'], st['k']
+    out0 = m.forward_(rays)
+    res['M'], res['K'] = f.last_stats['n_marched'], f.last_stats['n_kept']
     res['trace_ms'] = timeit(lambda: f.trace(rays))
 
     def step():
