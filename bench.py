@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 N_RAYS = 8192            # per GPU (max_train_num_rays, configs/nerf-blender.yaml:24)
 POOL = 8                 # distinct ray batches cycled through
 CPU_SAMPLE_RAYS = 1024   # rays per step of the CPU arms (bounded sample of the same workload)
+CPU_MAX_THREADS = 16     # the torch-CPU oracle stops scaling (and then collapses) beyond ~16 threads; `cores` reports what was used
 
 
 def peaks():
@@ -74,7 +75,7 @@ def cpu_workload(n_rays, seed):
 
 
 def time_cpu(steps, warmup, n_rays=CPU_SAMPLE_RAYS):
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(os.cpu_count(), CPU_MAX_THREADS))
     run = cpu_workload(n_rays, seed=3)
     for i in range(warmup):
         run(i)
@@ -335,7 +336,7 @@ def gpu_arm(args):
                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom], 'kernel_ms': kern[dom]['ms'],
                     'whole_step': {'algorithmic_bytes': step_bytes, 'achieved': step_bytes / (ms_step * 1e-3) / 1e9,
                                    'frac': step_bytes / (ms_step * 1e-3) / 1e9 / peak}}
-    cpu = time_cpu(2, 1) if world == 1 else None
+    cpu = time_cpu(2, 1, n_rays=512) if world == 1 else None
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True,

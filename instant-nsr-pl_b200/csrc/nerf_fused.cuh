@@ -41,30 +41,92 @@ __device__ __forceinline__ void nf_sample_position(const nsr_nerf_t& P, const fl
   z = (fmaf(dz, mid, oz) + P.radius) * inv;
 }
 
-// all levels of one sample; features packed as half2 per level (fp16 = what tcnn's encoding emits)
-template <int L>
+// x-adjacent corner pair (i0 = x bit 0, i1 = x bit 1) of one (y,z) combination.
+// One aligned 8-byte load fetches entry i0 and its neighbour i0^1; when x is even that neighbour IS i1
+// (hashed: (cx+1)^A == (cx^A)^1; dense: i0+1), so half of all pairs need a single request instead of two.
+struct NfPair {
+  uint2 pr;       // entries (i0 & ~1, i0 | 1)
+  uint32_t extra; // entry i1 when not paired
+  uint32_t i0;
+  bool paired;
+};
+
+__device__ __forceinline__ uint32_t nf_dense_mod(uint32_t i, uint32_t size) {
+  if (i >= size) i -= size;   // in-range inputs overshoot by less than one table length (SURVEY 8a wrap corner)
+  if (i >= size) i %= size;   // out-of-range inputs: rare slow path
+  return i;
+}
+
+__device__ __forceinline__ void nf_issue_pair(const uint32_t* __restrict__ table_u32, uint32_t i0, uint32_t i1, NfPair& p) {
+  p.i0 = i0;
+  p.paired = (i1 == (i0 ^ 1u));
+  p.pr = __ldg(reinterpret_cast<const uint2*>(table_u32 + (i0 & ~1u)));
+  p.extra = 0u;
+  if (!p.paired) p.extra = __ldg(table_u32 + i1);
+}
+
+__device__ __forceinline__ void nf_pair_values(const NfPair& p, float2& v0, float2& v1) {
+  const uint32_t a = (p.i0 & 1u) ? p.pr.y : p.pr.x;
+  const uint32_t b = p.paired ? ((p.i0 & 1u) ? p.pr.x : p.pr.y) : p.extra;
+  v0 = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  v1 = __half22float2(*reinterpret_cast<const __half2*>(&b));
+}
+
+// all levels of one sample; features packed as half2 per level (fp16 = what tcnn's encoding emits).
+// Levels are processed in batches of NB: all loads of a batch are issued before any is consumed
+// (memory-level parallelism: ~6*NB requests in flight per thread instead of 8).
+template <int L, int NB = 4>
 __device__ __forceinline__ void nf_gather(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z,
                                           uint32_t (&f)[L]) {
+  static_assert(L % NB == 0, "level count must be a multiple of the batch");
+  const uint32_t* tu = reinterpret_cast<const uint32_t*>(table);
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
-    const LevelInfo li = nsr_level(g, l);
-    uint32_t cx, cy, cz, idx[8];
-    float fx, fy, fz;
-    nsr_pos_fract(x, li.scale, cx, fx);
-    nsr_pos_fract(y, li.scale, cy, fy);
-    nsr_pos_fract(z, li.scale, cz, fz);
-    nsr_corner_indices(li, cx, cy, cz, idx);
-    float2 v[8];
+  for (int l0 = 0; l0 < L; l0 += NB) {
+    NfPair pairs[NB][4];
+    float fr[NB][3];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = nsr_ld_table(table, idx[c]);
-    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < NB; ++j) {
+      const LevelInfo li = nsr_level(g, l0 + j);
+      uint32_t cx, cy, cz;
+      nsr_pos_fract(x, li.scale, cx, fr[j][0]);
+      nsr_pos_fract(y, li.scale, cy, fr[j][1]);
+      nsr_pos_fract(z, li.scale, cz, fr[j][2]);
+      if (li.dense) {
+        const uint32_t r = li.res, r2 = li.res * li.res;
+        const uint32_t b = cx + cy * r + cz * r2;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float w = nsr_corner_weight(c, fx, fy, fz);
-      a0 = fmaf(w, v[c].x, a0);
-      a1 = fmaf(w, v[c].y, a1);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t i = b + (q & 1) * r + (q >> 1) * r2;
+          nf_issue_pair(tu, nf_dense_mod(i, li.size) + li.offset, nf_dense_mod(i + 1u, li.size) + li.offset, pairs[j][q]);
+        }
+      } else {
+        const uint32_t m = li.size - 1u;
+        const uint32_t hy0 = cy * NSR_PRIME_Y, hy1 = (cy + 1u) * NSR_PRIME_Y;
+        const uint32_t hz0 = cz * NSR_PRIME_Z, hz1 = (cz + 1u) * NSR_PRIME_Z;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t A = ((q & 1) ? hy1 : hy0) ^ ((q >> 1) ? hz1 : hz0);
+          nf_issue_pair(tu, ((cx ^ A) & m) + li.offset, (((cx + 1u) ^ A) & m) + li.offset, pairs[j][q]);
+        }
+      }
     }
-    f[l] = nsr_pack_h2(a0, a1);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float fx = fr[j][0], fy = fr[j][1], fz = fr[j][2];
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 v0, v1;
+        nf_pair_values(pairs[j][q], v0, v1);
+        const float wyz = ((q & 1) ? fy : 1.f - fy) * ((q >> 1) ? fz : 1.f - fz);
+        const float w0 = (1.f - fx) * wyz, w1 = fx * wyz;
+        a0 = fmaf(w0, v0.x, a0);
+        a1 = fmaf(w0, v0.y, a1);
+        a0 = fmaf(w1, v1.x, a0);
+        a1 = fmaf(w1, v1.y, a1);
+      }
+      f[l0 + j] = nsr_pack_h2(a0, a1);
+    }
   }
 }
 

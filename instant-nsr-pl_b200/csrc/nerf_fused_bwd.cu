@@ -1,19 +1,20 @@
 // Fused NeRF backward through both networks and the hash grid (autograd of VolumeRadiance + VolumeDensity +
 // HashGrid, models/texture.py:23-30, models/geometry.py:122-130), one launch.
 //
-// Per 128-sample CTA tile (8 warps x 16 rows): reload the 64 B/sample encoded features saved by the forward,
+// Per 64-sample CTA tile (4 warps x 16 rows, two CTAs per SM): reload the 64 B/sample encoded features saved by the forward,
 // recompute every activation on tensor cores (cheaper than storing 416 B/sample of hidden state), run the dgrad
 // chain in registers, scatter dL/d(table) straight from the mma accumulator layout (each thread owns 2 samples x 4
 // levels) with 8-byte vector REDs into the fp32 gradient table, then split the five weight-gradient GEMMs
-// (dW = dPre^T * Act, K = 128 samples) over the 8 warps with register accumulators that persist for the whole
+// (dW = dPre^T * Act, K = 64 samples) over the 4 warps with register accumulators that persist for the whole
 // kernel; one atomicAdd per weight per CTA at the end (tcnn: split-K CUTLASS GEMMs over K = batch + reduction).
 #include "nerf_fused.cuh"
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRows = kWarps * 16;  // 128
+constexpr int kRows = kWarps * 16;  // 64-row CTA tile: ~96 KB of smem => 2 CTAs / SM whose phases (MMA / scatter / wgrad) overlap
+constexpr int kCtasPerSm = 2;
 
 // smem tile offsets (halves) after the weights
 constexpr int T_X0 = 0;                         // [128][40]  encoded features
@@ -29,7 +30,7 @@ constexpr int T_DH1 = T_DO + kRows * 24;        // [128][72]
 constexpr int T_TOTAL = T_DH1 + kRows * NSR_LD64;
 constexpr size_t kSmemBytes = (size_t)(NF_W_TOTAL + T_TOTAL) * sizeof(__half);
 
-constexpr int kSlots = 5;  // 40 wgrad pair-tiles / 8 warps
+constexpr int kSlots = 40 / kWarps;  // 40 wgrad pair-tiles split over the warps
 
 struct WgradTile {
   int dy_off, ldy, x_off, ldx, m0, n0;  // smem tiles
@@ -68,7 +69,7 @@ __device__ __forceinline__ void relu_mask_pack(const float (&acc)[1][8][4], cons
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) nerf_bwd_kernel(const __grid_constant__ nsr_nerf_t P, const float* __restrict__ rays,
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __grid_constant__ nsr_nerf_t P, const float* __restrict__ rays,
                                                                const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                                                                const float* __restrict__ t_ends, const __half* __restrict__ enc_save,
                                                                const __half* __restrict__ dparams, const __half* __restrict__ cparams,
@@ -283,8 +284,8 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
     attr_set = true;
   }
   const int64_t tiles = (k + kRows - 1) / kRows;
-  int grid = (int)min((int64_t)nsr_sm_count(), tiles);
-  if (k_dev != nullptr) grid = nsr_sm_count();
+  int grid = (int)min((int64_t)nsr_sm_count() * kCtasPerSm, tiles);
+  if (k_dev != nullptr) grid = nsr_sm_count() * kCtasPerSm;
   nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
                                                                         (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
                                                                         grad_dparams, grad_cparams, loss_scale, amax, k, k_dev);

@@ -8,6 +8,8 @@ step from Python: the reference's per-step host cost dominates once the kernels 
 The captured region is ``out = model.forward_(rays, static=True); loss = loss_fn(out, batch); loss.backward()``:
 march, visibility pre-pass, compaction, fused forward, loss, fused backward -- no host synchronisation inside
 (sample counts live on the device).  loss_fn must be capturable (no .item(), no boolean-mask indexing).
+Build it BEFORE running eager steps on the same parameters, or drop every reference to earlier outputs / losses first:
+autograd AccumulateGrad nodes kept alive by an old graph are bound to the default stream, which invalidates capture.
 """
 import torch
 

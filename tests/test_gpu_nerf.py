@@ -156,13 +156,16 @@ def test_graphed_step_matches_eager():
     for p in model.parameters():
         p.grad = None
     le.backward()
-    ge = [p.grad.clone() for p in model.parameters()]
+    plist = [p for p in model.parameters() if p.numel() > 0]
+    ge = [p.grad.clone() for p in plist]
     k_eager = int(out['num_samples'])
+    le_val = le.item()
+    del out, le  # drop the eager autograd graph: its AccumulateGrad nodes are bound to the default stream (see GraphedStep docs)
     gs = GraphedStep(model, loss_fn, 512, batch_spec={'rgb': (3,)})
     lg = gs(r, rgb=tgt, background_color=bg.to(D))
-    assert abs(lg.item() - le.item()) <= 1e-5 * max(1.0, abs(le.item()))
+    assert abs(lg.item() - le_val) <= 1e-5 * max(1.0, abs(le_val))
     assert gs.counts()[1] == k_eager and gs.launches_per_replay >= 10
-    for p, g in zip(model.parameters(), ge):
+    for p, g in zip(plist, ge):
         assert cos(p.grad, g) >= 0.9999
     # new inputs -> new result, no recapture
     r2 = torch.from_numpy(__import__('nsr_b200').synthetic.sample_rays(512, seed=77)).to(D)
