@@ -174,6 +174,11 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
                        float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
                        void* stream);
 
+/* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
+int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
+                   void* stream);
+int nsr_dbg_scatter(const nsr_grid_t* g, const float* pos, const void* denc_h, float* grad, int64_t n, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,12 +72,11 @@ __device__ __forceinline__ void nf_pair_values(const NfPair& p, float2& v0, floa
   v1 = __half22float2(*reinterpret_cast<const __half2*>(&b));
 }
 
-// all levels of one sample; features packed as half2 per level (fp16 = what tcnn's encoding emits).
-// Levels are processed in batches of NB: all loads of a batch are issued before any is consumed
-// (memory-level parallelism: ~6*NB requests in flight per thread instead of 8).
-template <int L, int NB = 4>
-__device__ __forceinline__ void nf_gather(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z,
-                                          uint32_t (&f)[L]) {
+// paired + batched variant kept for tools/gather_bench.py (measured: no faster than the plain loop below -- every
+// variant converges to the same ~82 us / 446 k samples once occupancy is not the limit, see DESIGN.md "Gather").
+template <int L, int NB>
+__device__ __forceinline__ void nf_gather_paired(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z,
+                                                 uint32_t (&f)[L]) {
   static_assert(L % NB == 0, "level count must be a multiple of the batch");
   const uint32_t* tu = reinterpret_cast<const uint32_t*>(table);
 #pragma unroll
@@ -127,6 +126,33 @@ __device__ __forceinline__ void nf_gather(const nsr_grid_t& g, const __half2* __
       }
       f[l0 + j] = nsr_pack_h2(a0, a1);
     }
+  }
+}
+
+// all levels of one sample; features packed as half2 per level (fp16 = what tcnn's encoding emits)
+template <int L>
+__device__ __forceinline__ void nf_gather(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z,
+                                          uint32_t (&f)[L]) {
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const LevelInfo li = nsr_level(g, l);
+    uint32_t cx, cy, cz, idx[8];
+    float fx, fy, fz;
+    nsr_pos_fract(x, li.scale, cx, fx);
+    nsr_pos_fract(y, li.scale, cy, fy);
+    nsr_pos_fract(z, li.scale, cz, fz);
+    nsr_corner_indices(li, cx, cy, cz, idx);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = nsr_ld_table(table, idx[c]);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float w = nsr_corner_weight(c, fx, fy, fz);
+      a0 = fmaf(w, v[c].x, a0);
+      a1 = fmaf(w, v[c].y, a1);
+    }
+    f[l] = nsr_pack_h2(a0, a1);
   }
 }
 
