@@ -202,6 +202,10 @@ def gpu_arm(args):
         raise SystemExit('bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # stdout carries exactly ONE JSON line: anything libraries print there meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     model = build_model(dev)
@@ -220,15 +224,14 @@ def gpu_arm(args):
         return masked_smooth_l1(out['comp_rgb'], batch['rgb'], out['rays_valid'])
 
     # the public fast path: whole step (march .. backward) as one CUDA graph, no host sync inside
-    gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3)
+    # N > 1: the NCCL all-reduce (mean) of the parameter gradients is captured into the same graph, right behind the backward
     sync = GradSync(params, world) if world > 1 else None
+    gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
+                        post_backward=(sync.all_reduce_mean if sync is not None else None))
 
     def step(rays, target, do_sync=True):
         bg = torch.rand(3, device=dev)                      # systems/nerf.py:71 (random background per step)
-        loss = gstep(rays, rgb=target, background_color=bg)
-        if sync is not None and do_sync:
-            sync.all_reduce_mean()
-        return loss
+        return gstep(rays, rgb=target, background_color=bg)
 
     def eager_step(rays, target):
         """the same step through the eager public API (NeRFModel.forward), exact-size outputs, ~40 launches from Python"""
@@ -284,17 +287,22 @@ def gpu_arm(args):
     ms_e2e = timed(args.steps, e2e=True)
     barrier()
     clocks = None
+    # keep the GPUs under the same load until the clock sampler has seen it (short timed regions); every rank replays
+    # the same number of steps because the captured graph contains the collective
+    n_soak = int(max(0.0, 1.5 - (ms + ms_e2e) / 1e3) / max(ms / args.steps * 1e-3, 1e-4)) if world == 1 else int(1.5 / max(ms / args.steps * 1e-3, 1e-4))
+    if world > 1:
+        t = torch.tensor([n_soak], device=dev)
+        dist.broadcast(t, 0)
+        n_soak = int(t.item())
+    for _ in range(n_soak):
+        step(rays_dev[0], tgt_dev[0])
+    torch.cuda.synchronize()
     if rank == 0:
-        # keep the GPU under the same load until the clock sampler has seen it (short timed regions)
-        t_end = time.time() + max(0.0, 1.5 - (ms + ms_e2e) / 1e3)
-        while time.time() < t_end:
-            step(rays_dev[0], tgt_dev[0], do_sync=False)
-        torch.cuda.synchronize()
         clocks = sampler.stop()
     # ---- sample counts of the workload (one replay per pool batch, read back)
     kept = marched = 0.0
     for j in range(POOL):
-        step(rays_dev[j], tgt_dev[j], do_sync=False)
+        step(rays_dev[j], tgt_dev[j])
         mm, kk = gstep.counts()
         marched += mm / POOL
         kept += kk / POOL
@@ -355,6 +363,8 @@ def gpu_arm(args):
         line['cpu_baseline'] = {'value': cpu['rays_per_s'], 'unit': 'rays/s', 'cores': cpu['cores'], 'kind': 'port',
                                 'sample': f"2 steps x {cpu['n_rays']} rays of the C2 workload (kept {cpu['kept']:.0f} samples/step), fwd+bwd, "
                                           f"fp32 CPU oracle, {cpu['cores']} threads"}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -139,6 +139,17 @@ int nsr_accumulate(const float* weights, const float* values, const int64_t* off
  * holds the true count and n is the buffer capacity -- no host sync, so a whole step can be captured in a CUDA
  * graph.  n_dev == NULL: n is the count. */
 
+/* marching for the fused path (AABB, cone_angle 0; same sample sets as nsr_ray_aabb + nsr_march_count/_write):
+ * one kernel does ray-box intersection (+ per-ray jitter * step when jitter != NULL), tests the step lattice
+ * against the bitfield (coarse_bits: optional (res/4)^3 "any bit in the 4^3 block" field used to skip empty space),
+ * stores the per-ray occupancy masks [n_rays, words] and t_min, and its last CTA writes the exclusive scan of the
+ * counts into offsets[n_rays+1] (done_counter: device uint32, zero before the first call, resets itself).
+ * nsr_march_rays_expand turns the masks into packed samples. */
+int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
+                        uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts, int64_t* offsets, uint32_t* done_counter,
+                        int64_t n_rays, void* stream);
+int nsr_march_rays_expand(const nsr_march_t* p, const uint32_t* masks, int32_t words, const float* t_min, const int64_t* offsets,
+                          int32_t* ray_indices, float* t_starts, float* t_ends, int64_t n_rays, void* stream);
 /* density at world positions (occ_eval_fn of models/nerf.py:49-52; VolumeDensity.forward density-only).
  * positions f32 [n,3]; dparams fp16 flat [3072 MLP | table]; density f32 [n]. */
 int nsr_nerf_density(const nsr_nerf_t* f, const float* positions, const void* dparams_h, float* density, int64_t n, void* stream);

@@ -174,6 +174,182 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
   if (tid == 1023) offsets[n] = warp_sums[31];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused-path marcher (AABB, cone_angle == 0): ray -> (t_min, t_max) -> lattice occupancy masks in ONE kernel,
+// with a coarse "any bit set in this 4^3 block" bitfield staged in shared memory so that empty space costs no
+// global load, and the exclusive scan of the per-ray counts done by the last CTA to finish.  The write pass only
+// expands the stored masks (no second round of occupancy tests).  Same arithmetic as ray_aabb_kernel +
+// march_lattice_kernel above => identical sample sets.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_scan_counts(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets, int64_t n,
+                                                  int64_t* warp_sums /* smem [32] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int64_t per = (n + nthreads - 1) / nthreads;
+  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
+  int64_t s = 0;
+  for (int64_t i = b; i < e; ++i) s += counts[i];
+  int64_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < nwarps ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int64_t i = b; i < e; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (tid == nthreads - 1) offsets[n] = warp_sums[nwarps - 1];
+}
+
+__global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_march_t p, const float* __restrict__ rays,
+                                                                           const float* __restrict__ jitter,
+                                                                           const uint32_t* __restrict__ bits,
+                                                                           const uint32_t* __restrict__ coarse, uint32_t* __restrict__ masks,
+                                                                           int words, float* __restrict__ t_min_out,
+                                                                           int32_t* __restrict__ counts, int64_t* __restrict__ offsets,
+                                                                           uint32_t* __restrict__ done_counter, int64_t n_rays) {
+  __shared__ uint32_t s_coarse[1024];  // (R/4)^3 bits, R <= 128
+  __shared__ int64_t s_warp_sums[32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Rc = p.res >> 2;
+  const bool use_coarse = coarse != nullptr;
+  if (use_coarse) {
+    const int nw = (Rc * Rc * Rc + 31) >> 5;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) s_coarse[i] = __ldg(coarse + i);
+    __syncthreads();
+  }
+  const int64_t ray = blockIdx.x * (int64_t)kMarchWarps + warp;
+  if (ray < n_rays) {
+    const float* rr = rays + ray * 6;
+    const float ox = rr[0], oy = rr[1], oz = rr[2], dx = rr[3], dy = rr[4], dz = rr[5];
+    // ray_aabb_kernel, verbatim
+    float near = -INFINITY, far = INFINITY;
+    {
+      const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float t1 = (p.roi[a] - o3[a]) / d3[a], t2 = (p.roi[3 + a] - o3[a]) / d3[a];
+        near = fmaxf(near, fminf(t1, t2));
+        far = fminf(far, fmaxf(t1, t2));
+      }
+    }
+    const float near0 = fmaxf(near, 0.f);
+    const bool hit = far > near0;
+    float tmin = hit ? near0 : 1e10f;
+    const float tmax = hit ? far : 1e10f;
+    const float step = p.step;
+    if (jitter != nullptr) tmin = tmin + jitter[ray] * step;  // stratified: one draw per ray (unfused mul, add)
+    const float lx = p.roi[0], ly = p.roi[1], lz = p.roi[2], hx = p.roi[3], hy = p.roi[4], hz = p.roi[5];
+    const int R = p.res;
+    const float fR = (float)R;
+    int cnt = 0;
+    uint32_t* mrow = masks + ray * words;
+    int w = 0;
+    for (; w < words; ++w) {
+      const float k = (float)(w * 32 + lane);
+      const float t0 = __fmaf_rn(k, step, tmin);
+      const float t1 = __fmaf_rn(k + 1.f, step, tmin);
+      const float tm = (t0 + t1) * 0.5f;
+      const bool valid = tm < tmax;
+      bool occ = false;
+      if (valid) {
+        const float px = __fmaf_rn(tm, dx, ox), py = __fmaf_rn(tm, dy, oy), pz = __fmaf_rn(tm, dz, oz);
+        if (px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz) {
+          const float ux = (px - lx) / (hx - lx), uy = (py - ly) / (hy - ly), uz = (pz - lz) / (hz - lz);
+          int cx = (int)(ux * fR), cy = (int)(uy * fR), cz = (int)(uz * fR);
+          cx = min(max(cx, 0), R - 1);
+          cy = min(max(cy, 0), R - 1);
+          cz = min(max(cz, 0), R - 1);
+          bool maybe = true;
+          if (use_coarse) {
+            const uint32_t ci = (uint32_t)(cx >> 2) * Rc * Rc + (uint32_t)(cy >> 2) * Rc + (uint32_t)(cz >> 2);
+            maybe = (s_coarse[ci >> 5] >> (ci & 31u)) & 1u;
+          }
+          if (maybe) {
+            const uint32_t idx = (uint32_t)cx * R * R + (uint32_t)cy * R + (uint32_t)cz;
+            occ = (__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u;
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, occ);
+      if (lane == 0) mrow[w] = m;
+      cnt += __popc(m);
+      if (!__shfl_sync(0xffffffffu, (int)valid, 31)) {
+        ++w;
+        break;
+      }
+    }
+    for (int z = w + lane; z < words; z += 32) mrow[z] = 0u;
+    if (lane == 0) {
+      counts[ray] = cnt;
+      t_min_out[ray] = tmin;
+    }
+  }
+  // ---- last CTA to finish scans the counts (saves a launch); the ticket counter resets itself
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t ticket = atomicAdd(done_counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    block_scan_counts(counts, offsets, n_rays, s_warp_sums);
+    if (threadIdx.x == 0) *done_counter = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kMarchWarps * 32) march_rays_expand_kernel(nsr_march_t p, const uint32_t* __restrict__ masks, int words,
+                                                                             const float* __restrict__ t_min,
+                                                                             const int64_t* __restrict__ offsets,
+                                                                             int32_t* __restrict__ ray_indices, float* __restrict__ t_starts,
+                                                                             float* __restrict__ t_ends, int64_t n_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int64_t beg = offsets[ray];
+  if (offsets[ray + 1] == beg) return;
+  const float tmin = t_min[ray], step = p.step;
+  int64_t base = beg;
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t m = w < words ? masks[ray * words + w] : 0u;
+    const int c = __popc(m);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int64_t pos = base + incl - c;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1u;
+      const float k = (float)(w * 32 + b);
+      ray_indices[pos] = (int32_t)ray;
+      t_starts[pos] = __fmaf_rn(k, step, tmin);
+      t_ends[pos] = __fmaf_rn(k + 1.f, step, tmin);
+      ++pos;
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
 template <bool WRITE>
 int launch_march(const nsr_march_t* p, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
                  const uint32_t* bits, int32_t* counts, const int64_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
@@ -221,5 +397,30 @@ extern "C" int nsr_march_write(const nsr_march_t* p, const float* rays_o, const 
 extern "C" int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, void* stream) {
   scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, offsets, n);
   NSR_CHECK_LAUNCH("nsr_scan_counts");
+  return 0;
+}
+
+extern "C" int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits,
+                                   const uint32_t* coarse_bits, uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts,
+                                   int64_t* offsets, uint32_t* done_counter, int64_t n_rays, void* stream) {
+  NSR_REQUIRE(p != nullptr && p->contraction == 0 && p->cone_angle == 0.f, "nsr_march_rays_mask: AABB / cone_angle 0 only");
+  NSR_REQUIRE(p->step > 0.f && p->res >= 1 && p->res <= 1024, "nsr_march_rays_mask: bad step / resolution");
+  NSR_REQUIRE(coarse_bits == nullptr || (p->res % 4 == 0 && p->res <= 128), "nsr_march_rays_mask: coarse bits need res %% 4 == 0, res <= 128");
+  NSR_REQUIRE(words >= 1 && done_counter != nullptr, "nsr_march_rays_mask: words >= 1 and a ticket counter are required");
+  const int64_t blocks = n_rays > 0 ? (n_rays + kMarchWarps - 1) / kMarchWarps : 1;
+  march_rays_mask_kernel<<<(int)blocks, kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, rays, jitter, bits, coarse_bits, masks, words,
+                                                                                     t_min_out, counts, offsets, done_counter, n_rays);
+  NSR_CHECK_LAUNCH("nsr_march_rays_mask");
+  return 0;
+}
+
+extern "C" int nsr_march_rays_expand(const nsr_march_t* p, const uint32_t* masks, int32_t words, const float* t_min, const int64_t* offsets,
+                                     int32_t* ray_indices, float* t_starts, float* t_ends, int64_t n_rays, void* stream) {
+  NSR_REQUIRE(p != nullptr, "nsr_march_rays_expand: descriptor is NULL");
+  if (n_rays == 0) return 0;
+  march_rays_expand_kernel<<<nsr_blocks(n_rays, kMarchWarps), kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, masks, words, t_min, offsets,
+                                                                                                           ray_indices, t_starts, t_ends,
+                                                                                                           n_rays);
+  NSR_CHECK_LAUNCH("nsr_march_rays_expand");
   return 0;
 }

@@ -90,6 +90,7 @@ class NerfFused:
         self.loss_scale = 0.0  # <= 0: chosen on the device from the incoming gradient magnitude
         self.early_stop_eps, self.alpha_thre = 1e-4, 0.0
         self.last_stats = {}
+        self._ticket = None
 
     @staticmethod
     def try_build(model):
@@ -142,20 +143,22 @@ class NerfFused:
         n = rays.shape[0]
         cap = n * self.cap_per_ray
         mref = ctypes.byref(self.march)
-        rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
-        t_min, t_max = ops.ray_aabb_intersect(rays_o, rays_d, m.scene_aabb)
+        u = None
         if m.randomized:
-            u = torch.rand(n, device=dev) if jitter is None else jitter.to(dev, torch.float32)
-            t_min = t_min + u * m.render_step_size
-        bits = m.occupancy_grid.bits()
+            u = torch.rand(n, device=dev) if jitter is None else contig(jitter.to(dev), torch.float32)
+        grid = m.occupancy_grid
+        bits, coarse = grid.bits(), grid.coarse_bits()
         i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
         f32 = lambda k: torch.empty(k, dtype=torch.float32, device=dev)
+        words = (self.cap_per_ray + 31) // 32
+        masks, t_min = i32(n * words), f32(n)
         counts, offsets_m = i32(n), torch.empty(n + 1, dtype=torch.int64, device=dev)
-        lib.call('nsr_march_count', mref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(counts), n, stream())
-        lib.call('nsr_scan_counts', ptr(counts), ptr(offsets_m), n, stream())
+        if self._ticket is None or self._ticket.device != dev:
+            self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts),
+                 ptr(offsets_m), ptr(self._ticket), n, stream())
         ri_m, ts_m, te_m = i32(cap), f32(cap), f32(cap)
-        lib.call('nsr_march_write', mref, ptr(rays_o), ptr(rays_d), ptr(t_min), ptr(t_max), ptr(bits), ptr(offsets_m), ptr(ri_m), ptr(ts_m),
-                 ptr(te_m), n, stream())
+        lib.call('nsr_march_rays_expand', mref, ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(ri_m), ptr(ts_m), ptr(te_m), n, stream())
         alphas = f32(cap)
         lib.call('nsr_nerf_prepass', self.ref(), ptr(rays), ptr(ri_m), ptr(ts_m), ptr(te_m), ptr(self.dparams_half()), ptr(alphas), cap,
                  ptr(offsets_m[n:]), stream())

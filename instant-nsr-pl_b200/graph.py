@@ -17,8 +17,9 @@ from .lib import lib
 
 
 class GraphedStep:
-    def __init__(self, model, loss_fn, n_rays, batch_spec=None, device=None, warmup=3, refresh_half_params=False):
+    def __init__(self, model, loss_fn, n_rays, batch_spec=None, device=None, warmup=3, refresh_half_params=False, post_backward=None):
         self.model, self.loss_fn = model, loss_fn
+        self.post_backward = post_backward  # e.g. the NCCL gradient all-reduce: captured into the same graph
         dev = device or next(model.parameters()).device
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.rays = torch.zeros(n_rays, 6, device=dev)
@@ -41,6 +42,8 @@ class GraphedStep:
         out = m.forward_(self.rays, static=True)
         loss = self.loss_fn(out, self.batch)
         loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
         return out, loss
 
     def _capture(self, warmup):

@@ -67,6 +67,8 @@ _SIGNATURES = {
     'nsr_accumulate': [P, P, P, P, I32, I64, P],
     'nsr_dbg_gather': [P, P, P, P, I64, I32, I32, P],
     'nsr_dbg_scatter': [P, P, P, P, I64, I32, P],
+    'nsr_march_rays_mask': [P, P, P, P, P, P, I32, P, P, P, P, I64, P],
+    'nsr_march_rays_expand': [P, P, I32, P, P, P, P, P, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],
     'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P, P],
     'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],

@@ -69,6 +69,7 @@ class OccupancyGrid(nn.Module):
         self.register_buffer('occs', torch.zeros(self.num_cells))
         self.register_buffer('_binary', torch.zeros([self._res] * 3, dtype=torch.bool))
         self._bits = None
+        self._coarse = None
         self._bits_key = None
 
     # nerfacc checkpoints also carry grid_coords / grid_indices (derivable index tables): drop them on load
@@ -93,8 +94,16 @@ class OccupancyGrid(nn.Module):
         key = (self._binary._version, self._binary.data_ptr())
         if self._bits_key != key:
             self._bits = pack_binary(self._binary)
+            R = self._res
+            self._coarse = None
+            if R % 4 == 0 and R <= 128:  # "any bit in the 4^3 block": lets the marcher skip empty space without a global load
+                self._coarse = pack_binary(self._binary.view(R // 4, 4, R // 4, 4, R // 4, 4).any(dim=5).any(dim=3).any(dim=1))
             self._bits_key = key
         return self._bits
+
+    def coarse_bits(self):
+        self.bits()
+        return self._coarse
 
     def set_binary(self, binary):
         self._binary = binary.to(device=self._binary.device, dtype=torch.bool).view_as(self._binary).clone()
