@@ -214,29 +214,63 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     nsr_zero_acc(accE);
     nsr_gemm_wt<1, 4, 4>(accE, a_d, smem + NF_OFF_DW1, NF_LD32);
 
-    // ---- hash-table scatter straight from the accumulator layout: this thread owns samples (g, g+8) x levels (c, 4+c, 8+c, 12+c)
+    // ---- hash-table scatter straight from the accumulator layout: this thread owns samples (g, g+8) x levels (c, 4+c, 8+c, 12+c).
+    // Levels 0..7 (nt < 2): consecutive samples of a ray stay in one cell for several steps, so the 8 lanes that hold the
+    // same level for 8 consecutive samples first merge runs of equal cells with a segmented shuffle scan and only the
+    // last lane of each run issues the 8 REDs (-40 % REDs overall, far less same-address contention in L2).
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int64_t i = hh ? ib : ia;
-      if (i < n) {
-        float x, y, z, dx, dy, dz;
-        nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
+      const bool ok = i < n;
+      float x = 0.f, y = 0.f, z = 0.f, dx, dy, dz;
+      if (ok) nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const float d0 = accE[0][nt][hh * 2] * inv_scale, d1 = accE[0][nt][hh * 2 + 1] * inv_scale;
-          if (d0 != 0.f || d1 != 0.f) {
-            const LevelInfo li = nsr_level(P.grid, nt * 4 + c);
-            uint32_t cx, cy, cz, idx[8];
-            float fx, fy, fz;
-            nsr_pos_fract(x, li.scale, cx, fx);
-            nsr_pos_fract(y, li.scale, cy, fy);
-            nsr_pos_fract(z, li.scale, cz, fz);
+      for (int nt = 0; nt < 4; ++nt) {
+        const float d0 = ok ? accE[0][nt][hh * 2] * inv_scale : 0.f, d1 = ok ? accE[0][nt][hh * 2 + 1] * inv_scale : 0.f;
+        const LevelInfo li = nsr_level(P.grid, nt * 4 + c);
+        uint32_t cx, cy, cz, idx[8];
+        float fx, fy, fz;
+        nsr_pos_fract(x, li.scale, cx, fx);
+        nsr_pos_fract(y, li.scale, cy, fy);
+        nsr_pos_fract(z, li.scale, cz, fz);
+        if (nt < 2) {
+          // segmented inclusive scan over g (lanes c, c+4, ..., c+28) keyed by the cell
+          const uint32_t key = ok ? (cx + li.res * (cy + li.res * cz)) : (0xFFFFFFF0u + g);
+          const uint32_t key_prev = __shfl_up_sync(0xffffffffu, key, 4);
+          const bool head = (g == 0) || (key_prev != key);
+          const int next_head = __shfl_down_sync(0xffffffffu, (int)head, 4);
+          const bool tail = (g == 7) || next_head;
+          float v[16];
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const float w = nsr_corner_weight(cc, fx, fy, fz);
+            v[2 * cc] = w * d0;
+            v[2 * cc + 1] = w * d1;
+          }
+          bool flag = head;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            const int f_up = __shfl_up_sync(0xffffffffu, (int)flag, 4 * o);
+            const bool take = (g >= o) && !flag;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float u = __shfl_up_sync(0xffffffffu, v[e], 4 * o);
+              if (take) v[e] += u;
+            }
+            if (take) flag = f_up;
+          }
+          if (ok && tail) {
             nsr_corner_indices(li, cx, cy, cz, idx);
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-              const float w = nsr_corner_weight(cc, fx, fy, fz);
-              nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], w * d0, w * d1);
-            }
+            for (int cc = 0; cc < 8; ++cc)
+              if (v[2 * cc] != 0.f || v[2 * cc + 1] != 0.f) nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], v[2 * cc], v[2 * cc + 1]);
+          }
+        } else if (ok && (d0 != 0.f || d1 != 0.f)) {
+          nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const float w = nsr_corner_weight(cc, fx, fy, fz);
+            nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], w * d0, w * d1);
           }
         }
       }
