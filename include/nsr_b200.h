@@ -185,6 +185,30 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
                        float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
                        void* stream);
 
+/* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
+ * nsr_nerf_rays_fwd: masks (nsr_march_rays_mask) -> per-ray colour in ONE kernel: a warp owns a ray (atomic ticket queue),
+ * walks its samples 32 at a time (gather, density MLP, transmittance scan with the carry in a register, visibility test
+ * T >= early_stop_eps, SH4 + colour MLP, weights, per-ray sums) and stops at the first chunk after which T < eps.  Kept
+ * samples of ray r land at offsets_m[r] + j, j < kept[r] ("loose" layout).  The last CTA writes offsets_k = exclusive
+ * scan of kept.  ticket: device uint32[2], zero on entry, reset on exit.  Replaces sigma_fn pre-pass + render_visibility
+ * + mask compaction + main pass of models/nerf.py:82-109. */
+int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* masks, int32_t words, const float* t_min,
+                      const int64_t* offsets_m, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
+                      void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx, float* acc_rgb,
+                      float* opacity, float* depth, int32_t* kept, int64_t* offsets_k, uint32_t* ticket, int64_t n_rays, void* stream);
+/* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
+int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
+                  const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k, int64_t n_rays,
+                  void* stream);
+/* nsr_nerf_rays_bwd: compositing backward + both MLPs + hash scatter in ONE kernel (a warp walks its ray's kept samples 16 at
+ * a time from the last chunk to the first carrying the suffix sum).  g_weights is in the loose layout.  amax: device float,
+ * zeroed; ticket: device uint32, zeroed; loss_scale <= 0 selects the fp16 dgrad scale on the device from the per-ray
+ * gradient bound (t_bound = largest ray parameter, for the depth term). */
+int nsr_nerf_rays_bwd(const nsr_nerf_t* f, const float* rays, const float* t_min, const int64_t* offsets_m, const int32_t* kept, float step,
+                      const void* enc_save_h, const float* sigmas, const float* rgbs, const float* weights, const float* trans,
+                      const int32_t* kidx, const void* dparams_h, const void* cparams_h, const float* g_rgb, const float* g_opacity,
+                      const float* g_depth, const float* g_weights, float* grad_dparams, float* grad_cparams, float loss_scale, float* amax,
+                      float t_bound, uint32_t* ticket, int64_t n_rays, void* stream);
 /* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
 int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
                    void* stream);

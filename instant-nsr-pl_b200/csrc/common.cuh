@@ -162,3 +162,36 @@ __device__ __forceinline__ void nsr_sh4(float x, float y, float z, float (&s)[16
   s[14] = 1.4453057213202769f * z * (x2 - y2);
   s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
+
+// exclusive scan of int32 counts into int64 offsets[n+1] by ONE CTA (used by the "last CTA to finish" epilogues)
+__device__ __forceinline__ void nsr_block_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, int64_t* warp_sums /* smem [32] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int64_t per = (n + nthreads - 1) / nthreads;
+  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
+  int64_t s = 0;
+  for (int64_t i = b; i < e; ++i) s += __ldcg(counts + i);
+  int64_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < nwarps ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int64_t i = b; i < e; ++i) {
+    offsets[i] = run;
+    run += __ldcg(counts + i);
+  }
+  if (tid == nthreads - 1) offsets[n] = warp_sums[nwarps - 1];
+}

@@ -181,39 +181,6 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
 // expands the stored masks (no second round of occupancy tests).  Same arithmetic as ray_aabb_kernel +
 // march_lattice_kernel above => identical sample sets.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_scan_counts(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets, int64_t n,
-                                                  int64_t* warp_sums /* smem [32] */) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int64_t per = (n + nthreads - 1) / nthreads;
-  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
-  int64_t s = 0;
-  for (int64_t i = b; i < e; ++i) s += counts[i];
-  int64_t incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int64_t w = lane < nwarps ? warp_sums[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
-    }
-    warp_sums[lane] = w;
-  }
-  __syncthreads();
-  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
-  for (int64_t i = b; i < e; ++i) {
-    offsets[i] = run;
-    run += counts[i];
-  }
-  if (tid == nthreads - 1) offsets[n] = warp_sums[nwarps - 1];
-}
-
 __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_march_t p, const float* __restrict__ rays,
                                                                            const float* __restrict__ jitter,
                                                                            const uint32_t* __restrict__ bits,
@@ -309,7 +276,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
   __syncthreads();
   if (s_last) {
     __threadfence();
-    block_scan_counts(counts, offsets, n_rays, s_warp_sums);
+    nsr_block_scan_counts(counts, offsets, n_rays, s_warp_sums);
     if (threadIdx.x == 0) *done_counter = 0u;
   }
 }
