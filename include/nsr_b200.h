@@ -147,7 +147,7 @@ int nsr_accumulate(const float* weights, const float* values, const int64_t* off
  * nsr_march_rays_expand turns the masks into packed samples. */
 int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
                         uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts, int64_t* offsets, uint32_t* done_counter,
-                        int64_t n_rays, void* stream);
+                        int32_t* order /* [n_rays] longest-rays-first processing order, may be NULL */, int64_t n_rays, void* stream);
 int nsr_march_rays_expand(const nsr_march_t* p, const uint32_t* masks, int32_t words, const float* t_min, const int64_t* offsets,
                           int32_t* ray_indices, float* t_starts, float* t_ends, int64_t n_rays, void* stream);
 /* density at world positions (occ_eval_fn of models/nerf.py:49-52; VolumeDensity.forward density-only).
@@ -183,6 +183,7 @@ int nsr_nerf_ray_bwd(const int64_t* offsets_k, const float* t_starts, const floa
 int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
                        const void* enc_save_h, const void* dparams_h, const void* cparams_h, const float* d_sraw, const float* d_rgb,
                        float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
+                       const int64_t* row_pos /* optional: row j of enc_save / d_sraw / d_rgb lives at row_pos[j] (loose layout) */,
                        void* stream);
 
 /* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
@@ -193,13 +194,19 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
  * scan of kept.  ticket: device uint32[2], zero on entry, reset on exit.  Replaces sigma_fn pre-pass + render_visibility
  * + mask compaction + main pass of models/nerf.py:82-109. */
 int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* masks, int32_t words, const float* t_min,
-                      const int64_t* offsets_m, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
+                      const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h,
+                      const void* cparams_h,
                       void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx, float* acc_rgb,
                       float* opacity, float* depth, int32_t* kept, int64_t* offsets_k, uint32_t* ticket, int64_t n_rays, void* stream);
 /* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
 int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
-                  const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k, int64_t n_rays,
-                  void* stream);
+                  const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k /* may be NULL */,
+                  int64_t* loose_pos /* packed row -> loose position, may be NULL */, int64_t n_rays, void* stream);
+/* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min). */
+int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx, const float* trans,
+                           const float* weights, const float* sigmas, const float* rgbs, const float* g_rgb, const float* g_opacity,
+                           const float* g_depth, const float* g_weights, float* d_sraw, float* d_rgb, float* amax, int64_t n_rays,
+                           void* stream);
 /* nsr_nerf_rays_bwd: compositing backward + both MLPs + hash scatter in ONE kernel (a warp walks its ray's kept samples 16 at
  * a time from the last chunk to the first carrying the suffix sum).  g_weights is in the loose layout.  amax: device float,
  * zeroed; ticket: device uint32, zeroed; loss_scale <= 0 selects the fp16 dgrad scale on the device from the per-ray

@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
                                                                            const uint32_t* __restrict__ coarse, uint32_t* __restrict__ masks,
                                                                            int words, float* __restrict__ t_min_out,
                                                                            int32_t* __restrict__ counts, int64_t* __restrict__ offsets,
-                                                                           uint32_t* __restrict__ done_counter, int64_t n_rays) {
+                                                                           uint32_t* __restrict__ done_counter, int32_t* __restrict__ order,
+                                                                           int64_t n_rays) {
   __shared__ uint32_t s_coarse[1024];  // (R/4)^3 bits, R <= 128
   __shared__ int64_t s_warp_sums[32];
   __shared__ bool s_last;
@@ -277,6 +278,28 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
   if (s_last) {
     __threadfence();
     nsr_block_scan_counts(counts, offsets, n_rays, s_warp_sums);
+    if (order != nullptr) {
+      // longest rays first: bucket the rays by their number of 32-sample chunks (>=9, 5-8, 3-4, 2, 1, 0) so that the
+      // per-ray forward kernel starts its longest serial chains at t = 0 (order inside a bucket is irrelevant)
+      __shared__ int s_bin[6], s_cursor[6];
+      if (threadIdx.x < 6) s_bin[threadIdx.x] = 0;
+      __syncthreads();
+      auto bin_of = [](int cnt) {
+        const int ch = (cnt + 31) >> 5;
+        return ch >= 9 ? 0 : (ch >= 5 ? 1 : (ch >= 3 ? 2 : (ch == 2 ? 3 : (ch == 1 ? 4 : 5))));
+      };
+      for (int64_t i = threadIdx.x; i < n_rays; i += blockDim.x) atomicAdd(&s_bin[bin_of(__ldcg(counts + i))], 1);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < 6; ++b) {
+          s_cursor[b] = run;
+          run += s_bin[b];
+        }
+      }
+      __syncthreads();
+      for (int64_t i = threadIdx.x; i < n_rays; i += blockDim.x) order[atomicAdd(&s_cursor[bin_of(__ldcg(counts + i))], 1)] = (int32_t)i;
+    }
     if (threadIdx.x == 0) *done_counter = 0u;
   }
 }
@@ -369,14 +392,14 @@ extern "C" int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t 
 
 extern "C" int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits,
                                    const uint32_t* coarse_bits, uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts,
-                                   int64_t* offsets, uint32_t* done_counter, int64_t n_rays, void* stream) {
+                                   int64_t* offsets, uint32_t* done_counter, int32_t* order, int64_t n_rays, void* stream) {
   NSR_REQUIRE(p != nullptr && p->contraction == 0 && p->cone_angle == 0.f, "nsr_march_rays_mask: AABB / cone_angle 0 only");
   NSR_REQUIRE(p->step > 0.f && p->res >= 1 && p->res <= 1024, "nsr_march_rays_mask: bad step / resolution");
   NSR_REQUIRE(coarse_bits == nullptr || (p->res % 4 == 0 && p->res <= 128), "nsr_march_rays_mask: coarse bits need res %% 4 == 0, res <= 128");
   NSR_REQUIRE(words >= 1 && done_counter != nullptr, "nsr_march_rays_mask: words >= 1 and a ticket counter are required");
   const int64_t blocks = n_rays > 0 ? (n_rays + kMarchWarps - 1) / kMarchWarps : 1;
   march_rays_mask_kernel<<<(int)blocks, kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, rays, jitter, bits, coarse_bits, masks, words,
-                                                                                     t_min_out, counts, offsets, done_counter, n_rays);
+                                                                                     t_min_out, counts, offsets, done_counter, order, n_rays);
   NSR_CHECK_LAUNCH("nsr_march_rays_mask");
   return 0;
 }

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
                                                                const __half* __restrict__ dparams, const __half* __restrict__ cparams,
                                                                const float* __restrict__ d_sraw, const float* __restrict__ d_rgb,
                                                                float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
-                                                               float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev) {
+                                                               float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev,
+                                                               const int64_t* __restrict__ row_pos) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + NF_W_TOTAL;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       const int r = v >> 2, q = v & 3;
       const int64_t i = row0 + r0 + r;
       uint4 val = make_uint4(0, 0, 0, 0);
-      if (i < n) val = __ldg(reinterpret_cast<const uint4*>(enc_save + i * 32) + q);
+      if (i < n) val = __ldg(reinterpret_cast<const uint4*>(enc_save + (row_pos ? row_pos[i] : i) * 32) + q);
       *reinterpret_cast<uint4*>(T + T_X0 + (r0 + r) * NF_LD32 + q * 8) = val;
     }
     if (lane < 16) {
@@ -161,13 +162,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     }
     // ---- d(rgb pre-activation) = d_rgb * s (1 - s), s = sigmoid(fp16(raw)); columns 0..2 only
     const int64_t ia = row0 + r0 + g, ib = ia + 8;
+    // rows of the per-sample gradient buffers (identity for the packed layout, loose positions for the per-ray forward)
+    const int64_t pa = (row_pos && ia < n) ? row_pos[ia] : ia, pb = (row_pos && ib < n) ? row_pos[ib] : ib;
     uint32_t a_dc3[1][1][4];
     {
       float dp[4] = {0.f, 0.f, 0.f, 0.f};  // (row g: col c*2, c*2+1), (row g+8: col c*2, c*2+1)
       if (c < 2) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int64_t i = hh ? ib : ia;
+          const int64_t i = hh ? ib : ia, pi = hh ? pb : pa;
           if (i < n) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
               if (col < 3) {
                 const float raw = __half2float(__float2half_rn(acc16[0][0][hh * 2 + e]));
                 const float s = 1.f / (1.f + expf(-raw));
-                dp[hh * 2 + e] = d_rgb[i * 3 + col] * s * (1.f - s) * loss_scale;
+                dp[hh * 2 + e] = d_rgb[pi * 3 + col] * s * (1.f - s) * loss_scale;
               }
             }
           }
@@ -200,8 +203,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     nsr_zero_acc(acc16);
     nsr_gemm_wt<1, 4, 2>(acc16, a_d, smem + NF_OFF_CW1, NF_LD32);  // first 16 input columns = the geometry features
     if (c == 0) {  // density path: d(out0) += d sigma / d raw (trunc_exp backward folded in by nsr_nerf_ray_bwd)
-      if (ia < n) acc16[0][0][0] += d_sraw[ia] * loss_scale;
-      if (ib < n) acc16[0][0][2] += d_sraw[ib] * loss_scale;
+      if (ia < n) acc16[0][0][0] += d_sraw[pa] * loss_scale;
+      if (ib < n) acc16[0][0][2] += d_sraw[pb] * loss_scale;
     }
     uint32_t a_do[1][1][4];
     nsr_acc_to_afrag<1, 2>(acc16, a_do, NSR_ACT_NONE);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
 extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
                                   const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
                                   const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
-                                  const float* amax, int64_t k, const int64_t* k_dev, void* stream) {
+                                  const float* amax, int64_t k, const int64_t* k_dev, const int64_t* row_pos, void* stream) {
   NSR_REQUIRE(f != nullptr, "nsr_nerf_field_bwd: field descriptor is NULL");
   NSR_REQUIRE(f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 && f->color_hidden == 2,
               "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
@@ -322,7 +325,7 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
   if (k_dev != nullptr) grid = nsr_sm_count() * kCtasPerSm;
   nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
                                                                         (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev);
+                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
   return 0;
 }

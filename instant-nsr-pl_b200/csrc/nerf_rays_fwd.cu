@@ -27,6 +27,7 @@ struct RaysFwdArgs {
   const uint32_t* masks;       // [n_rays, words]
   const float* t_min;          // [n_rays]
   const int64_t* offsets_m;    // [n_rays+1] marched offsets (loose layout base of every ray)
+  const int32_t* order;        // [n_rays] processing order (longest rays first) or NULL
   const __half* dparams;
   const __half* cparams;
   __half* enc_save;            // [cap,32] or NULL
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid
     if (lane == 0) ray = atomicAdd(a.ticket, 1u);
     ray = __shfl_sync(0xffffffffu, ray, 0);
     if (ray >= a.n_rays) break;
+    if (a.order != nullptr) ray = __ldg(a.order + ray);
     // ---- the ray's occupancy mask: lane w holds words w and w+32
     const uint32_t mw0 = lane < a.words ? __ldg(a.masks + ray * a.words + lane) : 0u;
     const uint32_t mw1 = lane + 32 < a.words ? __ldg(a.masks + ray * a.words + lane + 32) : 0u;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
                                                         const float* __restrict__ t_min, float step, const int32_t* __restrict__ kidx,
                                                         const float* __restrict__ weights, int32_t* __restrict__ ri_k,
                                                         float* __restrict__ ts_k, float* __restrict__ te_k, float* __restrict__ w_k,
-                                                        int64_t n_rays) {
+                                                        int64_t* __restrict__ loose_pos, int64_t n_rays) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
@@ -285,14 +287,72 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
     ri_k[dst + j] = (int32_t)ray;
     ts_k[dst + j] = __fmaf_rn(k, step, tmin);
     te_k[dst + j] = __fmaf_rn(k + 1.f, step, tmin);
-    w_k[dst + j] = weights[src + j];
+    if (w_k) w_k[dst + j] = weights[src + j];
+    if (loose_pos) loose_pos[dst + j] = src + j;
+  }
+}
+
+// compositing backward on the loose layout (one warp per ray, reverse chunks, suffix carry): d_sraw, d_rgb (loose), amax
+__global__ void __launch_bounds__(256) ray_bwd_loose_kernel(const int64_t* __restrict__ off_m, const int32_t* __restrict__ kept,
+                                                            const float* __restrict__ t_min, float step, const int32_t* __restrict__ kidx,
+                                                            const float* __restrict__ trans, const float* __restrict__ weights,
+                                                            const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                            const float* __restrict__ g_rgb, const float* __restrict__ g_opacity,
+                                                            const float* __restrict__ g_depth, const float* __restrict__ g_weights,
+                                                            float* __restrict__ d_sraw, float* __restrict__ d_rgb, float* __restrict__ amax,
+                                                            int64_t n_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int64_t beg = off_m[ray];
+  const int n = kept[ray];
+  if (n <= 0) return;
+  const float tmin = t_min[ray];
+  const float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f, gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f, gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+  const float go = g_opacity ? g_opacity[ray] : 0.f, gd = g_depth ? g_depth[ray] : 0.f;
+  float carry = 0.f, vmax = 0.f;
+  for (int cb = ((n - 1) / 32) * 32; cb >= 0; cb -= 32) {
+    const int j = cb + lane;
+    const bool ok = j < n;
+    const int64_t i = beg + j;
+    float w = 0.f, gi = 0.f, delta = 0.f;
+    if (ok) {
+      w = weights[i];
+      const float kf = (float)kidx[i];
+      const float t0 = __fmaf_rn(kf, step, tmin), t1 = __fmaf_rn(kf + 1.f, step, tmin);
+      delta = t1 - t0;
+      gi = gr * rgbs[i * 3 + 0] + gg * rgbs[i * 3 + 1] + gb * rgbs[i * 3 + 2] + go + gd * ((t0 + t1) * 0.5f) + (g_weights ? g_weights[i] : 0.f);
+      d_rgb[i * 3 + 0] = w * gr;
+      d_rgb[i * 3 + 1] = w * gg;
+      d_rgb[i * 3 + 2] = w * gb;
+      vmax = fmaxf(vmax, 0.25f * w * fmaxf(fabsf(gr), fmaxf(fabsf(gg), fabsf(gb))));
+    }
+    const float gw = gi * w;
+    float suf = gw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    if (ok) {
+      const float ds = delta * (gi * (trans[i] - w) - (carry + suf - gw));
+      const float dr = ds * fminf(sigmas[i], 3269017.37f);
+      d_sraw[i] = dr;
+      vmax = fmaxf(vmax, fabsf(dr));
+    }
+    carry += __shfl_sync(0xffffffffu, suf, 0);
+  }
+  if (amax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f && isfinite(vmax)) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(vmax));
   }
 }
 
 }  // namespace
 
 extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* masks, int32_t words, const float* t_min,
-                                 const int64_t* offsets_m, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
+                                 const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
                                  void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx,
                                  float* acc_rgb, float* opacity, float* depth, int32_t* kept, int64_t* offsets_k, uint32_t* ticket,
                                  int64_t n_rays, void* stream) {
@@ -311,7 +371,7 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
     attr_set = true;
   }
   RaysFwdArgs a;
-  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m;
+  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order;
   a.dparams = (const __half*)dparams_h; a.cparams = (const __half*)cparams_h; a.enc_save = (__half*)enc_save_h;
   a.sigmas = sigmas; a.rgbs = rgbs; a.weights = weights; a.trans = trans; a.kidx_out = kidx;
   a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.offsets_k = offsets_k; a.ticket = ticket;
@@ -325,10 +385,21 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
 
 extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                              const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k,
-                             int64_t n_rays, void* stream) {
+                             int64_t* loose_pos, int64_t n_rays, void* stream) {
   if (n_rays == 0) return 0;
   pack_kept_kernel<<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, t_min, step, kidx, weights, ray_indices_k,
-                                                                            t_starts_k, t_ends_k, weights_k, n_rays);
+                                                                            t_starts_k, t_ends_k, weights_k, loose_pos, n_rays);
   NSR_CHECK_LAUNCH("nsr_pack_kept");
+  return 0;
+}
+
+extern "C" int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx,
+                                      const float* trans, const float* weights, const float* sigmas, const float* rgbs, const float* g_rgb,
+                                      const float* g_opacity, const float* g_depth, const float* g_weights, float* d_sraw, float* d_rgb,
+                                      float* amax, int64_t n_rays, void* stream) {
+  if (n_rays == 0) return 0;
+  ray_bwd_loose_kernel<<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, kept, t_min, step, kidx, trans, weights, sigmas, rgbs,
+                                                                                g_rgb, g_opacity, g_depth, g_weights, d_sraw, d_rgb, amax, n_rays);
+  NSR_CHECK_LAUNCH("nsr_nerf_ray_bwd_loose");
   return 0;
 }

@@ -63,13 +63,16 @@ class _NerfRender(torch.autograd.Function):
             lib.call('nsr_nerf_ray_bwd', ptr(offsets_k), ptr(ts), ptr(te), ptr(trans), ptr(weights), ptr(sig), ptr(rgbs), ptr(f32(g_rgb)),
                      ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n_rays, stream())
             lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc), ptr(dh), ptr(ch), ptr(d_sraw),
-                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n_rays:]), stream())
+                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n_rays:]), None, stream())
         return gd, gc, None, None, None
 
 
 class _NerfRenderRays(torch.autograd.Function):
-    """Per-ray persistent kernels (default): mask march -> ONE forward kernel; ONE backward kernel.
-    Per-sample tensors are in the loose layout: ray r's kept samples at offsets_m[r] + j, j < kept[r]."""
+    """Default fused path.  Forward: mask march (+ longest-rays-first order) -> ONE persistent per-ray kernel (gather, both
+    MLPs, compositing with early ray termination) -> index pack.  Backward: per-ray compositing backward + the
+    load-balanced sample-tile field backward, reading the per-ray ("loose") buffers through the packed->loose index.
+    Loose layout: ray r's kept samples at offsets_m[r] + j, j < kept[r].
+    fused.bwd_kernel = 'rays' swaps in the single per-ray backward kernel (nsr_nerf_rays_bwd; measured slower)."""
 
     @staticmethod
     def forward(ctx, dparams, cparams, fused, rays, jitter):
@@ -85,43 +88,59 @@ class _NerfRenderRays(torch.autograd.Function):
         bits, coarse = grid.bits(), grid.coarse_bits()
         i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
         f32 = lambda *k: torch.empty(*k, dtype=torch.float32, device=dev)
+        i64 = lambda k: torch.empty(k, dtype=torch.int64, device=dev)
         words = (fused.cap_per_ray + 31) // 32
-        masks, t_min, counts = i32(n * words), f32(n), i32(n)
-        offsets_m = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        masks, t_min, counts, order = i32(n * words), f32(n), i32(n), i32(n)
+        offsets_m = i64(n + 1)
         lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts),
-                 ptr(offsets_m), ptr(fused.ticket(dev)), n, stream())
+                 ptr(offsets_m), ptr(fused.ticket(dev)), ptr(order), n, stream())
         need_grad = dparams.requires_grad or cparams.requires_grad
         enc = torch.empty(cap, 32, dtype=torch.float16, device=dev) if need_grad else None
         sig, rgbs, weights, trans, kidx = f32(cap), f32(cap, 3), f32(cap), f32(cap), i32(cap)
         acc_rgb, opacity, depth, kept = f32(n, 3), f32(n, 1), f32(n, 1), i32(n)
-        offsets_k = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        offsets_k = i64(n + 1)
         dh, ch = fused.dparams_half(), fused.cparams_half()
         tick = torch.zeros(2, dtype=torch.int32, device=dev)
-        lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), float(m.render_step_size),
+        step = float(m.render_step_size)
+        lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
                  ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(offsets_k), ptr(tick), n, stream())
-        ctx.fused, ctx.n_rays = fused, n
+        # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
+        ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
+        lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
+                 ptr(pos), n, stream())
+        ctx.fused, ctx.n_rays, ctx.cap = fused, n, cap
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(rays, t_min, offsets_m, kept, enc, sig, rgbs, weights, trans, kidx, dh, ch)
+        ctx.save_for_backward(rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch)
         counts_mk = torch.cat([offsets_m[n:], offsets_k[n:]])  # [M, K] on the device
-        ctx.mark_non_differentiable(t_min, kidx, offsets_m, offsets_k, counts_mk)
-        return acc_rgb, opacity, depth, weights, t_min, kidx, offsets_m, offsets_k, counts_mk
+        ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k, counts_mk)
+        return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, counts_mk
 
     @staticmethod
     def backward(ctx, g_rgb, g_op, g_depth, g_w, *_):
         fused = ctx.fused
-        rays, t_min, offsets_m, kept, enc, sig, rgbs, weights, trans, kidx, dh, ch = ctx.saved_tensors
+        rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch = ctx.saved_tensors
         dev = rays.device
+        n, cap = ctx.n_rays, ctx.cap
+        step = float(fused.model.render_step_size)
         gd = torch.zeros(fused.n_dparams, device=dev)
         gc = torch.zeros(fused.n_cparams, device=dev)
-        if enc is not None and ctx.n_rays > 0:
+        if enc is not None and n > 0:
             f32 = lambda t: None if t is None else contig(t, torch.float32)
             amax = torch.zeros(1, device=dev)
-            tick = torch.zeros(1, dtype=torch.int32, device=dev)
-            lib.call('nsr_nerf_rays_bwd', fused.ref(), ptr(rays), ptr(t_min), ptr(offsets_m), ptr(kept), float(fused.model.render_step_size),
-                     ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx), ptr(dh), ptr(ch), ptr(f32(g_rgb)), ptr(f32(g_op)),
-                     ptr(f32(g_depth)), ptr(f32(g_w)), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), float(fused.t_bound),
-                     ptr(tick), ctx.n_rays, stream())
+            if fused.bwd_kernel == 'rays':
+                tick = torch.zeros(1, dtype=torch.int32, device=dev)
+                lib.call('nsr_nerf_rays_bwd', fused.ref(), ptr(rays), ptr(t_min), ptr(offsets_m), ptr(kept), step, ptr(enc), ptr(sig), ptr(rgbs),
+                         ptr(weights), ptr(trans), ptr(kidx), ptr(dh), ptr(ch), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)),
+                         ptr(f32(g_w)), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), float(fused.t_bound), ptr(tick), n, stream())
+            else:
+                d_sraw = torch.empty(cap, device=dev)
+                d_rgb = torch.empty(cap, 3, device=dev)
+                lib.call('nsr_nerf_ray_bwd_loose', ptr(offsets_m), ptr(kept), ptr(t_min), step, ptr(kidx), ptr(trans), ptr(weights), ptr(sig),
+                         ptr(rgbs), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n,
+                         stream())
+                lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc), ptr(dh), ptr(ch), ptr(d_sraw),
+                         ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(pos), stream())
         return gd, gc, None, None, None
 
 
@@ -149,7 +168,8 @@ class NerfFused:
         self.early_stop_eps, self.alpha_thre = 1e-4, 0.0
         self.last_stats = {}
         self._ticket = None
-        self.mode = 'per_ray'   # 'per_ray' (persistent per-ray kernels) | 'two_pass' (pre-pass / compaction / sample-tile kernels)
+        self.mode = 'per_ray'   # 'per_ray' (persistent per-ray forward kernel) | 'two_pass' (pre-pass / compaction / sample-tile kernels)
+        self.bwd_kernel = 'tiles'  # 'tiles' (sample-tile backward through the packed->loose index) | 'rays' (single per-ray backward kernel)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 
     @staticmethod
@@ -219,7 +239,7 @@ class NerfFused:
         masks, t_min = i32(n * words), f32(n)
         counts, offsets_m = i32(n), torch.empty(n + 1, dtype=torch.int64, device=dev)
         lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts),
-                 ptr(offsets_m), ptr(self.ticket(dev)), n, stream())
+                 ptr(offsets_m), ptr(self.ticket(dev)), None, n, stream())
         ri_m, ts_m, te_m = i32(cap), f32(cap), f32(cap)
         lib.call('nsr_march_rays_expand', mref, ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(ri_m), ptr(ts_m), ptr(te_m), n, stream())
         alphas = f32(cap)
@@ -246,30 +266,26 @@ class NerfFused:
         rays = contig(rays, torch.float32)
         if self.mode == 'two_pass':
             return self._render_two_pass(rays, jitter, static)
-        n = rays.shape[0]
-        acc_rgb, opacity, depth, weights, t_min, kidx, offsets_m, offsets_k, counts = _NerfRenderRays.apply(
+        acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, counts = _NerfRenderRays.apply(
             self.net.params, self.cnet.params, self, rays, jitter)
         comp_rgb = acc_rgb + m.background_color * (1.0 - opacity)
         out = {'comp_rgb': comp_rgb, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
                'num_samples': counts[1:].to(torch.int32)}
         if static:
             self.last_stats = {'counts_dev': counts}
-            if m.training:  # loose layout: ray r's kept samples at offsets_m[r] + j, j < offsets_k[r+1] - offsets_k[r]
-                out.update({'weights': weights, 'lattice_index': kidx, 't_min': t_min, 'offsets_loose': offsets_m, 'offsets_packed': offsets_k})
+            if m.training:
+                # capacity-length buffers, first num_samples entries valid: packed t_starts / t_ends / ray_indices; `weights` is in the
+                # loose layout (ray r's kept samples at offsets_loose[r] + j); packed row j lives at loose position loose_pos[j]
+                out.update({'weights': weights, 't_starts': ts, 't_ends': te, 'ray_indices': ri, 'loose_pos': pos,
+                            'offsets_loose': offsets_m, 'offsets_packed': offsets_k})
             return out
         n_marched, k = counts.tolist()
         self.last_stats = {'n_marched': n_marched, 'n_kept': k}
         if m.training:
-            dev = rays.device
-            ri = torch.empty(k, dtype=torch.int32, device=dev)
-            ts, te, wk = torch.empty(k, device=dev), torch.empty(k, device=dev), torch.empty(k, device=dev)
-            lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), float(m.render_step_size), ptr(kidx), ptr(weights.detach()),
-                     ptr(ri), ptr(ts), ptr(te), ptr(wk), n, stream())
-            ril = ri.long()
-            if weights.requires_grad:  # keep `weights` differentiable (distortion loss): gather from the loose buffer
-                pos = offsets_m[ril] + (torch.arange(k, device=dev) - offsets_k[ril])
-                wk = weights.index_select(0, pos)
-            out.update({'weights': wk.view(-1), 'points': ((ts + te) / 2.).view(-1), 'intervals': (te - ts).view(-1), 'ray_indices': ril.view(-1)})
+            ts_, te_ = ts[:k], te[:k]
+            wk = weights.index_select(0, pos[:k])  # packed view; keeps `weights` differentiable (distortion-loss consumers)
+            out.update({'weights': wk.view(-1), 'points': ((ts_ + te_) / 2.).view(-1), 'intervals': (te_ - ts_).view(-1),
+                        'ray_indices': ri[:k].long().view(-1)})
         return out
 
     def _render_two_pass(self, rays, jitter, static):

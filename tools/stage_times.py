@@ -10,6 +10,9 @@ from nsr_b200.graph import GraphedStep
 dev = torch.device('cuda:0')
 n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.N_RAYS
 model = bench.build_model(dev)
+if len(sys.argv) > 2:
+    model._fused.mode = 'two_pass' if sys.argv[2] == 'two_pass' else 'per_ray'
+    model._fused.bwd_kernel = 'rays' if sys.argv[2] == 'per_ray_bwd' else 'tiles'
 rays = [torch.from_numpy(synthetic.sample_rays(n, seed=i)).to(dev) for i in range(4)]
 target = torch.rand(n, 3, device=dev)
 params = [p for p in model.parameters() if p.numel() > 0]
