@@ -163,35 +163,79 @@ __device__ __forceinline__ void nsr_sh4(float x, float y, float z, float (&s)[16
   s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-// exclusive scan of int32 counts into int64 offsets[n+1] by ONE CTA (used by the "last CTA to finish" epilogues)
-__device__ __forceinline__ void nsr_block_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, int64_t* warp_sums /* smem [32] */) {
+// exclusive scan of int32 counts into int64 offsets[n+1] by ONE CTA (the "last CTA to finish" epilogues).
+// Row-wise: thread t handles elements base + t (coalesced), 8 rows are loaded before any is consumed so that the
+// L2 latency of the loads overlaps.  Optionally also emits `order`: the element indices bucketed by their number of
+// 32-sample chunks (>=9, 5-8, 3-4, 2, 1, 0), i.e. a longest-processing-time-first schedule for per-ray kernels.
+__device__ __forceinline__ int nsr_chunk_bin(int cnt) {
+  const int ch = (cnt + 31) >> 5;
+  return ch >= 9 ? 0 : (ch >= 5 ? 1 : (ch >= 3 ? 2 : (ch == 2 ? 3 : (ch == 1 ? 4 : 5))));
+}
+
+__device__ __forceinline__ void nsr_block_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, int64_t* warp_sums /* smem [32] */,
+                                                      int32_t* order = nullptr) {
+  __shared__ int s_bin[6], s_cursor[6];
+  constexpr int RB = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int64_t per = (n + nthreads - 1) / nthreads;
-  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
-  int64_t s = 0;
-  for (int64_t i = b; i < e; ++i) s += __ldcg(counts + i);
-  int64_t incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
+  if (tid < 6) s_bin[tid] = 0;
   __syncthreads();
-  if (warp == 0) {
-    int64_t w = lane < nwarps ? warp_sums[lane] : 0;
+  int64_t carry = 0;
+  for (int64_t base = 0; base < n; base += (int64_t)RB * nthreads) {
+    int v[RB];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
+    for (int j = 0; j < RB; ++j) {
+      const int64_t i = base + (int64_t)j * nthreads + tid;
+      v[j] = i < n ? __ldcg(counts + i) : 0;
     }
-    warp_sums[lane] = w;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int64_t i = base + (int64_t)j * nthreads + tid;
+      if (base + (int64_t)j * nthreads >= n) break;
+      int incl = v[j];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (lane == 31) warp_sums[warp] = incl;
+      __syncthreads();
+      int64_t wbase = 0, row_total = 0;
+      for (int w = 0; w < nwarps; ++w) {
+        const int64_t t = warp_sums[w];
+        if (w < warp) wbase += t;
+        row_total += t;
+      }
+      if (i < n) {
+        offsets[i] = carry + wbase + incl - v[j];
+        if (order != nullptr) atomicAdd(&s_bin[nsr_chunk_bin(v[j])], 1);
+      }
+      carry += row_total;
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
-  for (int64_t i = b; i < e; ++i) {
-    offsets[i] = run;
-    run += __ldcg(counts + i);
+  if (tid == 0) offsets[n] = carry;
+  if (order != nullptr) {
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int b = 0; b < 6; ++b) {
+        s_cursor[b] = run;
+        run += s_bin[b];
+      }
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += (int64_t)RB * nthreads) {
+      int v[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int64_t i = base + (int64_t)j * nthreads + tid;
+        v[j] = i < n ? __ldcg(counts + i) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int64_t i = base + (int64_t)j * nthreads + tid;
+        if (i < n) order[atomicAdd(&s_cursor[nsr_chunk_bin(v[j])], 1)] = (int32_t)i;
+      }
+    }
   }
-  if (tid == nthreads - 1) offsets[n] = warp_sums[nwarps - 1];
 }

@@ -16,7 +16,8 @@ namespace {
 
 __device__ __forceinline__ bool occupied(const nsr_march_t& p, const uint32_t* __restrict__ bits, float px, float py, float pz) {
   const float lx = p.roi[0], ly = p.roi[1], lz = p.roi[2], hx = p.roi[3], hy = p.roi[4], hz = p.roi[5];
-  float ux = (px - lx) / (hx - lx), uy = (py - ly) / (hy - ly), uz = (pz - lz) / (hz - lz);
+  // unit-cube coordinate = (p - lo) * (1 / (hi - lo)) with the reciprocal rounded to fp32 once (oracle/march.py does the same)
+  float ux = (px - lx) * (1.f / (hx - lx)), uy = (py - ly) * (1.f / (hy - ly)), uz = (pz - lz) * (1.f / (hz - lz));
   if (p.contraction == 0) {
     if (!(px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz)) return false;
   } else {
@@ -143,35 +144,7 @@ __global__ void march_seq_kernel(nsr_march_t p, const float* __restrict__ rays_o
 // exclusive scan of int32 counts into int64 offsets[n+1]; one CTA (n is a ray count: small)
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets, int64_t n) {
   __shared__ int64_t warp_sums[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t b = (int64_t)tid * per, e = min(n, b + per);
-  int64_t s = 0;
-  for (int64_t i = b; i < e; ++i) s += counts[i];
-  int64_t incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int64_t w = warp_sums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
-    }
-    warp_sums[lane] = w;
-  }
-  __syncthreads();
-  int64_t run = incl - s + (warp > 0 ? warp_sums[warp - 1] : 0);
-  for (int64_t i = b; i < e; ++i) {
-    offsets[i] = run;
-    run += counts[i];
-  }
-  if (tid == 1023) offsets[n] = warp_sums[31];
+  nsr_block_scan_counts(counts, offsets, n, warp_sums);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -224,6 +197,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
     const float lx = p.roi[0], ly = p.roi[1], lz = p.roi[2], hx = p.roi[3], hy = p.roi[4], hz = p.roi[5];
     const int R = p.res;
     const float fR = (float)R;
+    const float ix = 1.f / (hx - lx), iy = 1.f / (hy - ly), iz = 1.f / (hz - lz);
     int cnt = 0;
     uint32_t* mrow = masks + ray * words;
     int w = 0;
@@ -237,7 +211,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
       if (valid) {
         const float px = __fmaf_rn(tm, dx, ox), py = __fmaf_rn(tm, dy, oy), pz = __fmaf_rn(tm, dz, oz);
         if (px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz) {
-          const float ux = (px - lx) / (hx - lx), uy = (py - ly) / (hy - ly), uz = (pz - lz) / (hz - lz);
+          const float ux = (px - lx) * ix, uy = (py - ly) * iy, uz = (pz - lz) * iz;
           int cx = (int)(ux * fR), cy = (int)(uy * fR), cz = (int)(uz * fR);
           cx = min(max(cx, 0), R - 1);
           cy = min(max(cy, 0), R - 1);
@@ -277,29 +251,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
   __syncthreads();
   if (s_last) {
     __threadfence();
-    nsr_block_scan_counts(counts, offsets, n_rays, s_warp_sums);
-    if (order != nullptr) {
-      // longest rays first: bucket the rays by their number of 32-sample chunks (>=9, 5-8, 3-4, 2, 1, 0) so that the
-      // per-ray forward kernel starts its longest serial chains at t = 0 (order inside a bucket is irrelevant)
-      __shared__ int s_bin[6], s_cursor[6];
-      if (threadIdx.x < 6) s_bin[threadIdx.x] = 0;
-      __syncthreads();
-      auto bin_of = [](int cnt) {
-        const int ch = (cnt + 31) >> 5;
-        return ch >= 9 ? 0 : (ch >= 5 ? 1 : (ch >= 3 ? 2 : (ch == 2 ? 3 : (ch == 1 ? 4 : 5))));
-      };
-      for (int64_t i = threadIdx.x; i < n_rays; i += blockDim.x) atomicAdd(&s_bin[bin_of(__ldcg(counts + i))], 1);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int run = 0;
-        for (int b = 0; b < 6; ++b) {
-          s_cursor[b] = run;
-          run += s_bin[b];
-        }
-      }
-      __syncthreads();
-      for (int64_t i = threadIdx.x; i < n_rays; i += blockDim.x) order[atomicAdd(&s_cursor[bin_of(__ldcg(counts + i))], 1)] = (int32_t)i;
-    }
+    nsr_block_scan_counts(counts, offsets, n_rays, s_warp_sums, order);  // + longest-rays-first order for the per-ray kernel
     if (threadIdx.x == 0) *done_counter = 0u;
   }
 }

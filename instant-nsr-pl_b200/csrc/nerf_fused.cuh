@@ -156,6 +156,44 @@ __device__ __forceinline__ void nf_gather(const nsr_grid_t& g, const __half2* __
   }
 }
 
+// latency-oriented variant: all loads of NB levels are issued before any is consumed (8*NB requests in flight per thread).
+// Used by the per-ray forward kernel, whose run time is set by the serial chunk chain of the longest rays; the
+// throughput-bound sample-tile kernels keep the plain loop (tools/gather_bench.py: no difference at full occupancy).
+template <int L, int NB>
+__device__ __forceinline__ void nf_gather_batched(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z,
+                                                  uint32_t (&f)[L]) {
+  static_assert(L % NB == 0, "level count must be a multiple of the batch");
+  const uint32_t* tu = reinterpret_cast<const uint32_t*>(table);
+#pragma unroll
+  for (int l0 = 0; l0 < L; l0 += NB) {
+    uint32_t raw[NB][8];
+    float fr[NB][3];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const LevelInfo li = nsr_level(g, l0 + j);
+      uint32_t cx, cy, cz, idx[8];
+      nsr_pos_fract(x, li.scale, cx, fr[j][0]);
+      nsr_pos_fract(y, li.scale, cy, fr[j][1]);
+      nsr_pos_fract(z, li.scale, cz, fr[j][2]);
+      nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) raw[j][c] = __ldg(tu + idx[c]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float w = nsr_corner_weight(c, fr[j][0], fr[j][1], fr[j][2]);
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&raw[j][c]));
+        a0 = fmaf(w, v.x, a0);
+        a1 = fmaf(w, v.y, a1);
+      }
+      f[l0 + j] = nsr_pack_h2(a0, a1);
+    }
+  }
+}
+
 // write one 32-feature row (16 packed half2) of a [rows][NF_LD32] smem tile
 __device__ __forceinline__ void nf_store_row32(__half* tile, int row, const uint32_t (&f)[16]) {
   uint4* p = reinterpret_cast<uint4*>(tile + row * NF_LD32);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid
         if (valid) {
           const float x = (fmaf(dx, mid, ox) + P.radius) * inv, y = (fmaf(dy, mid, oy) + P.radius) * inv,
                       z = (fmaf(dz, mid, oz) + P.radius) * inv;
-          nf_gather<16>(P.grid, table, x, y, z, f);
+          nf_gather_batched<16, 4>(P.grid, table, x, y, z, f);
         } else {
 #pragma unroll
           for (int l = 0; l < 16; ++l) f[l] = 0u;

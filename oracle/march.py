@@ -67,7 +67,10 @@ def occupied(p, roi, binary, contraction):
     """p [..,3] float32 world points -> bool.  binary: bool [R,R,R] (flat ix*R*R + iy*R + iz)."""
     R = binary.shape[0]
     lo, hi = roi[0:3].astype(F32), roi[3:6].astype(F32)
-    unit = ((p - lo) / (hi - lo)).astype(F32)
+    # (p - lo) * fp32(1 / (hi - lo)): one fp32 reciprocal of the extent, then a multiply (what the kernels do; nerfacc divides --
+    # the two differ only for points within one ulp of a cell face)
+    inv = (F32(1) / (hi - lo)).astype(F32)
+    unit = ((p - lo).astype(F32) * inv).astype(F32)
     if contraction == AABB:
         inside = np.all((p >= lo) & (p <= hi), axis=-1)
     else:
