@@ -142,12 +142,12 @@ int nsr_accumulate(const float* weights, const float* values, const int64_t* off
 /* marching for the fused path (AABB, cone_angle 0; same sample sets as nsr_ray_aabb + nsr_march_count/_write):
  * one kernel does ray-box intersection (+ per-ray jitter * step when jitter != NULL), tests the step lattice
  * against the bitfield (coarse_bits: optional (res/4)^3 "any bit in the 4^3 block" field used to skip empty space),
- * stores the per-ray occupancy masks [n_rays, words] and t_min, and its last CTA writes the exclusive scan of the
- * counts into offsets[n_rays+1] (done_counter: device uint32, zero before the first call, resets itself).
- * nsr_march_rays_expand turns the masks into packed samples. */
+ * stores the per-ray occupancy masks [n_rays, words], t_min and the per-ray sample counts.
+ * nsr_scan_counts_order: exclusive scan of the counts + a longest-rays-first processing order (rays bucketed by their
+ * number of 32-sample chunks) for the per-ray kernel.  nsr_march_rays_expand turns the masks into packed samples. */
 int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
-                        uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts, int64_t* offsets, uint32_t* done_counter,
-                        int32_t* order /* [n_rays] longest-rays-first processing order, may be NULL */, int64_t n_rays, void* stream);
+                        uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts, int64_t n_rays, void* stream);
+int nsr_scan_counts_order(const int32_t* counts, int64_t* offsets, int32_t* order, int64_t n, void* stream);
 int nsr_march_rays_expand(const nsr_march_t* p, const uint32_t* masks, int32_t words, const float* t_min, const int64_t* offsets,
                           int32_t* ray_indices, float* t_starts, float* t_ends, int64_t n_rays, void* stream);
 /* density at world positions (occ_eval_fn of models/nerf.py:49-52; VolumeDensity.forward density-only).
@@ -190,14 +190,13 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
  * nsr_nerf_rays_fwd: masks (nsr_march_rays_mask) -> per-ray colour in ONE kernel: a warp owns a ray (atomic ticket queue),
  * walks its samples 32 at a time (gather, density MLP, transmittance scan with the carry in a register, visibility test
  * T >= early_stop_eps, SH4 + colour MLP, weights, per-ray sums) and stops at the first chunk after which T < eps.  Kept
- * samples of ray r land at offsets_m[r] + j, j < kept[r] ("loose" layout).  The last CTA writes offsets_k = exclusive
- * scan of kept.  ticket: device uint32[2], zero on entry, reset on exit.  Replaces sigma_fn pre-pass + render_visibility
+ * samples of ray r land at offsets_m[r] + j, j < kept[r] ("loose" layout).  ticket: device uint32, zero on entry.  Replaces sigma_fn pre-pass + render_visibility
  * + mask compaction + main pass of models/nerf.py:82-109. */
 int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* masks, int32_t words, const float* t_min,
                       const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h,
                       const void* cparams_h,
                       void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx, float* acc_rgb,
-                      float* opacity, float* depth, int32_t* kept, int64_t* offsets_k, uint32_t* ticket, int64_t n_rays, void* stream);
+                      float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays, void* stream);
 /* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
 int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                   const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k /* may be NULL */,

@@ -163,79 +163,144 @@ __device__ __forceinline__ void nsr_sh4(float x, float y, float z, float (&s)[16
   s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-// exclusive scan of int32 counts into int64 offsets[n+1] by ONE CTA (the "last CTA to finish" epilogues).
-// Row-wise: thread t handles elements base + t (coalesced), 8 rows are loaded before any is consumed so that the
-// L2 latency of the loads overlaps.  Optionally also emits `order`: the element indices bucketed by their number of
-// 32-sample chunks (>=9, 5-8, 3-4, 2, 1, 0), i.e. a longest-processing-time-first schedule for per-ray kernels.
+// exclusive scan of int32 counts into int64 offsets[n+1] by ONE CTA (the "last CTA to finish" epilogues), optionally with
+// `order`: the element indices bucketed by their number of 32-sample chunks, longest first (a longest-processing-time-first
+// schedule for the per-ray kernel; order inside a bucket = index order, so the result is deterministic).
+// Fast path (n <= 32 * blockDim.x): every thread holds 32 strided elements in registers, the scan is shuffles + two
+// barriers, the bucketing is ballots + one barrier -- no shared-memory atomics, no per-row barriers.
+constexpr int NSR_ORDER_BINS = 8;
 __device__ __forceinline__ int nsr_chunk_bin(int cnt) {
-  const int ch = (cnt + 31) >> 5;
-  return ch >= 9 ? 0 : (ch >= 5 ? 1 : (ch >= 3 ? 2 : (ch == 2 ? 3 : (ch == 1 ? 4 : 5))));
+  const int ch = (cnt + 31) >> 5;  // 32-sample chunks the per-ray kernel would walk
+  return ch >= 17 ? 0 : (ch >= 13 ? 1 : (ch >= 9 ? 2 : (ch >= 5 ? 3 : (ch >= 3 ? 4 : (ch == 2 ? 5 : (ch == 1 ? 6 : 7))))));
 }
 
+template <int ROWS>
 __device__ __forceinline__ void nsr_block_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, int64_t* warp_sums /* smem [32] */,
                                                       int32_t* order = nullptr) {
-  __shared__ int s_bin[6], s_cursor[6];
-  constexpr int RB = 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  if (tid < 6) s_bin[tid] = 0;
-  __syncthreads();
-  int64_t carry = 0;
-  for (int64_t base = 0; base < n; base += (int64_t)RB * nthreads) {
-    int v[RB];
+  static_assert(ROWS <= 32, "at most 32 rows");
+  __shared__ int s_rw[32][33];                       // [row][warp] inclusive warp totals
+  __shared__ int64_t s_rowbase[33];
+  __shared__ int s_wb[32][NSR_ORDER_BINS];           // [warp][bin] counts, then bases
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, W = T >> 5;
+  if (n <= (int64_t)ROWS * T) {
+    int v[ROWS], incl[ROWS];
 #pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int64_t i = base + (int64_t)j * nthreads + tid;
+    for (int j = 0; j < ROWS; ++j) {
+      const int64_t i = (int64_t)j * T + tid;
       v[j] = i < n ? __ldcg(counts + i) : 0;
     }
 #pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int64_t i = base + (int64_t)j * nthreads + tid;
-      if (base + (int64_t)j * nthreads >= n) break;
-      int incl = v[j];
+    for (int j = 0; j < ROWS; ++j) {
+      int x = v[j];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
+        const int u = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += u;
       }
-      if (lane == 31) warp_sums[warp] = incl;
-      __syncthreads();
-      int64_t wbase = 0, row_total = 0;
-      for (int w = 0; w < nwarps; ++w) {
-        const int64_t t = warp_sums[w];
-        if (w < warp) wbase += t;
-        row_total += t;
+      incl[j] = x;
+      if (lane == 31) s_rw[j][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {  // lane j: total of row j, then exclusive scan over the rows
+      int64_t tot = 0;
+      if (lane < ROWS)
+        for (int w = 0; w < W; ++w) tot += s_rw[lane][w];
+      int64_t x = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t u = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += u;
       }
+      s_rowbase[lane] = x - tot;
+      if (lane == 31) s_rowbase[32] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int64_t i = (int64_t)j * T + tid;
       if (i < n) {
-        offsets[i] = carry + wbase + incl - v[j];
-        if (order != nullptr) atomicAdd(&s_bin[nsr_chunk_bin(v[j])], 1);
+        int64_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_rw[j][w];
+        offsets[i] = s_rowbase[j] + wbase + incl[j] - v[j];
       }
-      carry += row_total;
+    }
+    if (tid == 0) offsets[n] = s_rowbase[32];
+    if (order != nullptr) {
+      int run[NSR_ORDER_BINS];
+#pragma unroll
+      for (int b = 0; b < NSR_ORDER_BINS; ++b) run[b] = 0;
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const bool ok = (int64_t)j * T + tid < n;
+        const int bin = nsr_chunk_bin(v[j]);
+#pragma unroll
+        for (int b = 0; b < NSR_ORDER_BINS; ++b) run[b] += __popc(__ballot_sync(0xffffffffu, ok && bin == b));
+      }
+      if (lane < NSR_ORDER_BINS) {
+        int mine = 0;
+#pragma unroll
+        for (int b = 0; b < NSR_ORDER_BINS; ++b)
+          if (lane == b) mine = run[b];
+        s_wb[warp][lane] = mine;
+      }
       __syncthreads();
-    }
-  }
-  if (tid == 0) offsets[n] = carry;
-  if (order != nullptr) {
-    __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int b = 0; b < 6; ++b) {
-        s_cursor[b] = run;
-        run += s_bin[b];
+      if (tid == 0) {  // bases, bin-major: all of bin 0 (warp 0, 1, ...), then bin 1, ...; rows inside a warp keep their order
+        int acc = 0;
+        for (int b = 0; b < NSR_ORDER_BINS; ++b)
+          for (int w = 0; w < W; ++w) {
+            const int c = s_wb[w][b];
+            s_wb[w][b] = acc;
+            acc += c;
+          }
       }
-    }
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += (int64_t)RB * nthreads) {
-      int v[RB];
+      __syncthreads();
 #pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        const int64_t i = base + (int64_t)j * nthreads + tid;
-        v[j] = i < n ? __ldcg(counts + i) : 0;
-      }
+      for (int b = 0; b < NSR_ORDER_BINS; ++b) run[b] = s_wb[warp][b];
 #pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        const int64_t i = base + (int64_t)j * nthreads + tid;
-        if (i < n) order[atomicAdd(&s_cursor[nsr_chunk_bin(v[j])], 1)] = (int32_t)i;
+      for (int j = 0; j < ROWS; ++j) {
+        const int64_t i = (int64_t)j * T + tid;
+        const bool ok = i < n;
+        const int bin = nsr_chunk_bin(v[j]);
+        int pos = 0;
+#pragma unroll
+        for (int b = 0; b < NSR_ORDER_BINS; ++b) {
+          const uint32_t m = __ballot_sync(0xffffffffu, ok && bin == b);
+          if (bin == b) pos = run[b] + __popc(m & ((1u << lane) - 1u));
+          run[b] += __popc(m);
+        }
+        if (ok) order[pos] = (int32_t)i;
       }
     }
+    return;
   }
+  // ---- generic path (large n): contiguous chunk per thread; order = identity
+  const int64_t per = (n + T - 1) / T;
+  const int64_t b0 = (int64_t)tid * per, e0 = min(n, b0 + per);
+  int64_t s0 = 0;
+  for (int64_t i = b0; i < e0; ++i) s0 += __ldcg(counts + i);
+  int64_t inc = s0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < W ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int64_t run = inc - s0 + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int64_t i = b0; i < e0; ++i) {
+    offsets[i] = run;
+    run += __ldcg(counts + i);
+    if (order != nullptr) order[i] = (int32_t)i;
+  }
+  if (tid == T - 1) offsets[n] = warp_sums[W - 1];
 }

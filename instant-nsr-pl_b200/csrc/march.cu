@@ -142,9 +142,11 @@ __global__ void march_seq_kernel(nsr_march_t p, const float* __restrict__ rays_o
 }
 
 // exclusive scan of int32 counts into int64 offsets[n+1]; one CTA (n is a ray count: small)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets, int64_t n) {
+template <int ROWS>
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ offsets,
+                                                           int32_t* __restrict__ order, int64_t n) {
   __shared__ int64_t warp_sums[32];
-  nsr_block_scan_counts(counts, offsets, n, warp_sums);
+  nsr_block_scan_counts<ROWS>(counts, offsets, n, warp_sums, order);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,12 +161,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
                                                                            const uint32_t* __restrict__ bits,
                                                                            const uint32_t* __restrict__ coarse, uint32_t* __restrict__ masks,
                                                                            int words, float* __restrict__ t_min_out,
-                                                                           int32_t* __restrict__ counts, int64_t* __restrict__ offsets,
-                                                                           uint32_t* __restrict__ done_counter, int32_t* __restrict__ order,
-                                                                           int64_t n_rays) {
+                                                                           int32_t* __restrict__ counts, int64_t n_rays) {
   __shared__ uint32_t s_coarse[1024];  // (R/4)^3 bits, R <= 128
-  __shared__ int64_t s_warp_sums[32];
-  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Rc = p.res >> 2;
   const bool use_coarse = coarse != nullptr;
@@ -240,19 +238,6 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
       counts[ray] = cnt;
       t_min_out[ray] = tmin;
     }
-  }
-  // ---- last CTA to finish scans the counts (saves a launch); the ticket counter resets itself
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t ticket = atomicAdd(done_counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    nsr_block_scan_counts(counts, offsets, n_rays, s_warp_sums, order);  // + longest-rays-first order for the per-ray kernel
-    if (threadIdx.x == 0) *done_counter = 0u;
   }
 }
 
@@ -336,22 +321,35 @@ extern "C" int nsr_march_write(const nsr_march_t* p, const float* rays_o, const 
                             (cudaStream_t)stream, "nsr_march_write");
 }
 
-extern "C" int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, void* stream) {
-  scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, offsets, n);
-  NSR_CHECK_LAUNCH("nsr_scan_counts");
+static int launch_scan(const int32_t* counts, int64_t* offsets, int32_t* order, int64_t n, cudaStream_t st, const char* name) {
+  if (n <= 8 * 1024)
+    scan_counts_kernel<8><<<1, 1024, 0, st>>>(counts, offsets, order, n);
+  else
+    scan_counts_kernel<32><<<1, 1024, 0, st>>>(counts, offsets, order, n);
+  NSR_CHECK_LAUNCH(name);
   return 0;
+}
+
+extern "C" int nsr_scan_counts(const int32_t* counts, int64_t* offsets, int64_t n, void* stream) {
+  return launch_scan(counts, offsets, nullptr, n, (cudaStream_t)stream, "nsr_scan_counts");
+}
+
+extern "C" int nsr_scan_counts_order(const int32_t* counts, int64_t* offsets, int32_t* order, int64_t n, void* stream) {
+  NSR_REQUIRE(order != nullptr, "nsr_scan_counts_order: order is NULL");
+  return launch_scan(counts, offsets, order, n, (cudaStream_t)stream, "nsr_scan_counts_order");
 }
 
 extern "C" int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits,
                                    const uint32_t* coarse_bits, uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts,
-                                   int64_t* offsets, uint32_t* done_counter, int32_t* order, int64_t n_rays, void* stream) {
+                                   int64_t n_rays, void* stream) {
   NSR_REQUIRE(p != nullptr && p->contraction == 0 && p->cone_angle == 0.f, "nsr_march_rays_mask: AABB / cone_angle 0 only");
   NSR_REQUIRE(p->step > 0.f && p->res >= 1 && p->res <= 1024, "nsr_march_rays_mask: bad step / resolution");
   NSR_REQUIRE(coarse_bits == nullptr || (p->res % 4 == 0 && p->res <= 128), "nsr_march_rays_mask: coarse bits need res %% 4 == 0, res <= 128");
-  NSR_REQUIRE(words >= 1 && done_counter != nullptr, "nsr_march_rays_mask: words >= 1 and a ticket counter are required");
-  const int64_t blocks = n_rays > 0 ? (n_rays + kMarchWarps - 1) / kMarchWarps : 1;
+  NSR_REQUIRE(words >= 1, "nsr_march_rays_mask: words >= 1 is required");
+  if (n_rays == 0) return 0;
+  const int64_t blocks = (n_rays + kMarchWarps - 1) / kMarchWarps;
   march_rays_mask_kernel<<<(int)blocks, kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, rays, jitter, bits, coarse_bits, masks, words,
-                                                                                     t_min_out, counts, offsets, done_counter, order, n_rays);
+                                                                                     t_min_out, counts, n_rays);
   NSR_CHECK_LAUNCH("nsr_march_rays_mask");
   return 0;
 }

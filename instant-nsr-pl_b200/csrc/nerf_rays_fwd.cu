@@ -40,8 +40,7 @@ struct RaysFwdArgs {
   float* opacity;              // [n_rays]
   float* depth;                // [n_rays]
   int32_t* kept;               // [n_rays]
-  int64_t* offsets_k;          // [n_rays+1] written by the last CTA (exclusive scan of kept)
-  uint32_t* ticket;            // [2]: ray queue head, finished-CTA counter (both zero on entry, reset on exit)
+  uint32_t* ticket;            // ray queue head (zero on entry)
   float step, early_stop_eps;
   int words;
   int64_t n_rays;
@@ -63,8 +62,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid_constant__ nsr_nerf_t P, const RaysFwdArgs a) {
   extern __shared__ __align__(16) __half smem[];
-  __shared__ int64_t s_scan[32];
-  __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   __half* At = smem + NF_W_TOTAL + warp * kWarpHalves;
   __half* St = At + 32 * NF_LD32;
@@ -256,19 +253,6 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid
     }
     __syncwarp();
   }
-  // ---- last CTA to finish: exclusive scan of the kept counts (-> num_samples, packed offsets) and ticket reset
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    nsr_block_scan_counts(a.kept, a.offsets_k, a.n_rays, s_scan);
-    if (threadIdx.x == 0) {
-      a.ticket[0] = 0u;
-      a.ticket[1] = 0u;
-    }
-  }
 }
 
 // kept prefix of every ray: loose (offsets_m) -> packed (offsets_k), for the exact-size per-sample outputs
@@ -354,13 +338,14 @@ __global__ void __launch_bounds__(256) ray_bwd_loose_kernel(const int64_t* __res
 extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* masks, int32_t words, const float* t_min,
                                  const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
                                  void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx,
-                                 float* acc_rgb, float* opacity, float* depth, int32_t* kept, int64_t* offsets_k, uint32_t* ticket,
-                                 int64_t n_rays, void* stream) {
+                                 float* acc_rgb, float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays,
+                                 void* stream) {
   NSR_REQUIRE(f != nullptr && f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 &&
                   f->color_hidden == 2,
               "nsr_nerf_rays_fwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
   NSR_REQUIRE(words >= 1 && words <= kMaxWords, "nsr_nerf_rays_fwd: words must be in [1,%d]", kMaxWords);
-  NSR_REQUIRE(ticket != nullptr && kept != nullptr && offsets_k != nullptr, "nsr_nerf_rays_fwd: ticket / kept / offsets_k are required");
+  NSR_REQUIRE(ticket != nullptr && kept != nullptr, "nsr_nerf_rays_fwd: ticket / kept are required");
+  if (n_rays == 0) return 0;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nerf_rays_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
@@ -374,7 +359,7 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
   a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order;
   a.dparams = (const __half*)dparams_h; a.cparams = (const __half*)cparams_h; a.enc_save = (__half*)enc_save_h;
   a.sigmas = sigmas; a.rgbs = rgbs; a.weights = weights; a.trans = trans; a.kidx_out = kidx;
-  a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.offsets_k = offsets_k; a.ticket = ticket;
+  a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.ticket = ticket;
   a.step = step; a.early_stop_eps = early_stop_eps; a.words = words; a.n_rays = n_rays;
   const int64_t want = (n_rays + kWarps - 1) / kWarps;
   int grid = (int)min((int64_t)nsr_sm_count() * 2, want > 0 ? want : (int64_t)1);

@@ -92,19 +92,20 @@ class _NerfRenderRays(torch.autograd.Function):
         words = (fused.cap_per_ray + 31) // 32
         masks, t_min, counts, order = i32(n * words), f32(n), i32(n), i32(n)
         offsets_m = i64(n + 1)
-        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts),
-                 ptr(offsets_m), ptr(fused.ticket(dev)), ptr(order), n, stream())
+        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), n, stream())
+        lib.call('nsr_scan_counts_order', ptr(counts), ptr(offsets_m), ptr(order), n, stream())
         need_grad = dparams.requires_grad or cparams.requires_grad
         enc = torch.empty(cap, 32, dtype=torch.float16, device=dev) if need_grad else None
         sig, rgbs, weights, trans, kidx = f32(cap), f32(cap, 3), f32(cap), f32(cap), i32(cap)
         acc_rgb, opacity, depth, kept = f32(n, 3), f32(n, 1), f32(n, 1), i32(n)
         offsets_k = i64(n + 1)
         dh, ch = fused.dparams_half(), fused.cparams_half()
-        tick = torch.zeros(2, dtype=torch.int32, device=dev)
+        tick = torch.zeros(1, dtype=torch.int32, device=dev)
         step = float(m.render_step_size)
         lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
-                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(offsets_k), ptr(tick), n, stream())
+                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, stream())
+        lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
         ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
         lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
@@ -238,8 +239,8 @@ class NerfFused:
         words = (self.cap_per_ray + 31) // 32
         masks, t_min = i32(n * words), f32(n)
         counts, offsets_m = i32(n), torch.empty(n + 1, dtype=torch.int64, device=dev)
-        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts),
-                 ptr(offsets_m), ptr(self.ticket(dev)), None, n, stream())
+        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), n, stream())
+        lib.call('nsr_scan_counts', ptr(counts), ptr(offsets_m), n, stream())
         ri_m, ts_m, te_m = i32(cap), f32(cap), f32(cap)
         lib.call('nsr_march_rays_expand', mref, ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(ri_m), ptr(ts_m), ptr(te_m), n, stream())
         alphas = f32(cap)
