@@ -220,8 +220,11 @@ def gpu_arm(args):
     tgt_pin = [t.pin_memory() for t in tgt_np]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
+    from nsr_b200.losses import nerf_rgb_loss
+
     def loss_fn(out, batch):
-        return masked_smooth_l1(out['comp_rgb'], batch['rgb'], out['rays_valid'])
+        # systems/nerf.py:68-97 (background blend + masked smooth-L1) as the fused CUDA op of the package
+        return nerf_rgb_loss(out['acc_rgb'], out['opacity'], model.background_color, batch['rgb'])[0]
 
     # the public fast path: whole step (march .. backward) as one CUDA graph, no host sync inside
     # N > 1: the NCCL all-reduce (mean) of the parameter gradients is captured into the same graph, right behind the backward

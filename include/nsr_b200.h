@@ -215,6 +215,14 @@ int nsr_nerf_rays_bwd(const nsr_nerf_t* f, const float* rays, const float* t_min
                       const int32_t* kidx, const void* dparams_h, const void* cparams_h, const float* g_rgb, const float* g_opacity,
                       const float* g_depth, const float* g_weights, float* grad_dparams, float* grad_cparams, float loss_scale, float* amax,
                       float t_bound, uint32_t* ticket, int64_t n_rays, void* stream);
+/* ---- training-step back end (systems/nerf.py:68-97) ---------------------------------------------------
+ * background blend + masked smooth-L1 over the valid rays: comp = acc_rgb + bg (1 - opacity), valid = opacity > 0,
+ * loss = sum smooth_l1(comp - target) / max(3 n_valid, 1).  accum2: device float[2] (loss sum, n_valid), zeroed by the
+ * caller; comp_rgb [n,3] optional output.  The backward writes dL/d acc_rgb and dL/d opacity. */
+int nsr_nerf_loss_fwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, float* comp_rgb, float* accum2,
+                      int64_t n_rays, void* stream);
+int nsr_nerf_loss_bwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, const float* accum2,
+                      const float* g_loss, float* g_acc_rgb, float* g_opacity, int64_t n_rays, void* stream);
 /* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
 int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
                    void* stream);

@@ -274,6 +274,7 @@ class NerfFused:
                'num_samples': counts[1:].to(torch.int32)}
         if static:
             self.last_stats = {'counts_dev': counts}
+            out['acc_rgb'] = acc_rgb  # pre-blend per-ray colour sum (input of nsr_b200.losses.nerf_rgb_loss)
             if m.training:
                 # capacity-length buffers, first num_samples entries valid: packed t_starts / t_ends / ray_indices; `weights` is in the
                 # loose layout (ray r's kept samples at offsets_loose[r] + j); packed row j lives at loose position loose_pos[j]

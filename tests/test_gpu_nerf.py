@@ -191,3 +191,33 @@ def test_graphed_step_matches_eager():
     # static outputs: capacity-length per-sample buffers + device-side count
     assert gs.out['weights'].shape[0] == 512 * model._fused.cap_per_ray and gs.out['num_samples'].dtype == torch.int32
     assert {'offsets_loose', 'offsets_packed', 'loose_pos', 't_starts'} <= set(gs.out)
+
+
+def test_fused_rgb_loss_matches_torch():
+    """nsr_b200.losses.nerf_rgb_loss == background blend + masked smooth-L1 of systems/nerf.py:68-97, values and gradients."""
+    import torch.nn.functional as F
+    from nsr_b200.losses import nerf_rgb_loss
+    D = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(0)
+    n = 5000
+    acc = (torch.rand(n, 3, generator=g) * 1.5).to(D).requires_grad_(True)
+    op = torch.rand(n, 1, generator=g)
+    op[::3] = 0.0
+    op = op.to(D).requires_grad_(True)
+    bg, tgt = torch.rand(3, generator=g).to(D), (torch.rand(n, 3, generator=g) * 3 - 1).to(D)
+    loss, comp = nerf_rgb_loss(acc, op, bg, tgt)
+    (loss * 2.5).backward()
+    acc_r, op_r = acc.detach().clone().requires_grad_(True), op.detach().clone().requires_grad_(True)
+    comp_r = acc_r + bg * (1.0 - op_r)
+    valid = op_r[:, 0] > 0
+    loss_r = F.smooth_l1_loss(comp_r[valid], tgt[valid])
+    (loss_r * 2.5).backward()
+    assert abs(loss.item() - loss_r.item()) <= 1e-5 * abs(loss_r.item())
+    assert (comp - comp_r.detach()).abs().max().item() <= 1e-6
+    assert (acc.grad - acc_r.grad).abs().max().item() <= 1e-9 + 1e-5 * acc_r.grad.abs().max().item()
+    assert (op.grad - op_r.grad).abs().max().item() <= 1e-9 + 1e-5 * op_r.grad.abs().max().item()
+    # no valid ray: zero loss, zero gradients
+    z = torch.zeros(16, 1, device=D, requires_grad=True)
+    l0, _ = nerf_rgb_loss(acc[:16].detach().requires_grad_(True), z, bg, tgt[:16])
+    l0.backward()
+    assert l0.item() == 0.0 and float(z.grad.abs().sum()) == 0.0

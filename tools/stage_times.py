@@ -19,7 +19,13 @@ params = [p for p in model.parameters() if p.numel() > 0]
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 
 
+from nsr_b200.losses import nerf_rgb_loss
+FUSED_LOSS = os.environ.get('NSR_TORCH_LOSS', '0') != '1'
+
+
 def loss_fn(out, batch):
+    if FUSED_LOSS and 'acc_rgb' in out:
+        return nerf_rgb_loss(out['acc_rgb'], out['opacity'], model.background_color, batch['rgb'])[0]
     return bench.masked_smooth_l1(out['comp_rgb'], batch['rgb'], out['rays_valid'])
 
 
