@@ -356,7 +356,7 @@ def gpu_arm(args):
                    'rays_per_gpu': N_RAYS, 'marched_samples_per_step': marched, 'kept_samples_per_step': kept,
                    'samples_per_s': kept * args.steps / (ms * 1e-3), 'l2': 'flushed (256 MB write) before every timed step',
                    'parallelism': f'dp{world}' if world > 1 else 'single',
-                   'step': 'march+prepass+fwd+smooth_l1+bwd as one CUDA graph (nsr_b200.graph.GraphedStep)' + (' + NCCL all-reduce of grads' if world > 1 else ''),
+                   'step': 'mask march + per-ray forward (early termination) + fused smooth-L1 loss + backward, one CUDA graph (nsr_b200.graph.GraphedStep)' + (' + NCCL all-reduce of grads' if world > 1 else ''),
                    'eager_api_ms_per_step': ms_eager},
         'e2e': {'value': N_RAYS * world * args.steps / (ms_e2e * 1e-3), 'unit': 'rays/s',
                 'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4},
