@@ -317,9 +317,12 @@ def gpu_arm(args):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         kept, marched = cnt.tolist()
         dist.barrier()
+        torch.cuda.synchronize()
         if rank != 0:
-            dist.destroy_process_group()
-            return
+            # hard exit: tearing down an NCCL communicator that is referenced by a live CUDA graph can block forever
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
     # ---- rank 0: eager-API timing and per-kernel durations (CUDA events around every C-ABI call; same workload)
     nprof = min(args.steps, 20)
@@ -370,7 +373,9 @@ def gpu_arm(args):
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)  # see above: skip the NCCL teardown
 
 
 def main():
