@@ -102,6 +102,11 @@ int nsr_mlp_fwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, void*
 int nsr_mlp_bwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, const void* y_h, const void* dy_h,
                 float* grad_params, void* dx_h, float loss_scale, int64_t n, void* stream);
 
+/* tcgen05 / TMEM version of nsr_mlp_fwd (same tensors): 128-row CTA tiles, operands in the canonical K-major smem layout,
+ * accumulators in tensor memory, tcgen05.ld epilogue.  variant bit 0 = swap LBO/SBO in the smem descriptors (bring-up switch);
+ * status: device int (may be NULL), set to 1 if an mbarrier wait timed out. */
+int nsr_mlp_fwd_tc(const nsr_mlp_t* m, const void* x_h, const void* params_h, void* out_h, int64_t n, int variant, int* status, void* stream);
+
 /* ---- marching / compositing (nerfacc 0.3.3 surface) ----------------------------------------- */
 
 /* nerfacc.intersection.ray_aabb_intersect (models/neus.py:153). */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     'nsr_sh4_fwd': [P, P, I64, P],
     'nsr_mlp_fwd': [P, P, P, P, I64, P],
     'nsr_mlp_bwd': [P, P, P, P, P, P, P, F32, I64, P],
+    'nsr_mlp_fwd_tc': [P, P, P, P, I64, I32, P, P],
     'nsr_ray_aabb': [P, P, P, P, P, I64, P],
     'nsr_march_count': [P, P, P, P, P, P, P, I64, P],
     'nsr_scan_counts': [P, P, I64, P],

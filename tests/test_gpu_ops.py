@@ -384,3 +384,27 @@ def test_occupancy_grid_update(nsr):
     g2 = nerfacc.OccupancyGrid(aabb, 32).to(D)
     g2.load_state_dict(sd)
     assert torch.equal(g2.binary, grid.binary)
+
+
+@pytest.mark.parametrize('n_in,n_out,nh,oact', [(32, 16, 1, 'None'), (32, 3, 2, 'Sigmoid'), (64, 4, 2, 'None'), (16, 1, 3, 'None')])
+def test_mlp_fwd_tcgen05_matches_mma_sync(nsr, n_in, n_out, nh, oact):
+    """nsr_mlp_fwd_tc (tcgen05.mma + TMEM) computes the same network as nsr_mlp_fwd (mma.sync) and as the oracle."""
+    nsr_b200, ops, tcnn, _ = nsr
+    from nsr_b200.lib import lib, ptr, stream
+    D = dev()
+    cfg = dict(otype='FullyFusedMLP', activation='ReLU', output_activation=oact, n_neurons=64, n_hidden_layers=nh)
+    net = tcnn.Network(n_in, n_out, cfg).to(D)
+    g = torch.Generator().manual_seed(3)
+    n = 1000
+    x = torch.randn(n, n_in, generator=g).half().to(D).contiguous()
+    ref = net(x.float()).float()
+    ph = net._params_half()
+    out = torch.zeros(n, 16, dtype=torch.float16, device=D)
+    status = torch.zeros(1, dtype=torch.int32, device=D)
+    lib.call('nsr_mlp_fwd_tc', net.mlp.ref(), ptr(x), ptr(ph), ptr(out), n, 0, ptr(status), stream())
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    got = out[:, :n_out].float()
+    assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    yr = omlp.ffmlp_fwd(x.float().cpu(), net.params.detach().cpu(), n_in, n_out, 64, nh, 'ReLU', oact, emulate_fp16=True)
+    assert (got.cpu() - yr).abs().max().item() <= 2e-2 * yr.abs().max().item() + 2e-3

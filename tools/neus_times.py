@@ -1,0 +1,61 @@
+"""Timing of the drop-in 'neus' model (configs C3 neus-blender 8192 rays, C4 neus-dtu 4096 rays + learned background) on the
+per-op CUDA surface: forward + reference losses (systems/neus.py:98-113) + backward.  Development / profiles aid."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.nn.functional as F
+from nsr_b200 import models, configs, synthetic
+
+D = torch.device('cuda:0')
+
+
+def build(cfg_fn, n_rays):
+    cfg = cfg_fn()
+    torch.manual_seed(0)
+    m = models.make('neus', cfg).to(D)
+    r = cfg['radius']
+    g = (np.arange(128) + 0.5) / 128 * 2 * r - r
+    X, Y, Z = np.meshgrid(g, g, g, indexing='ij')
+    d = np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+    m.occupancy_grid.set_binary(torch.from_numpy((d > 0.42 * r / 1.5 * 1.5 * 0.8) & (d < 0.58 * r / 1.5 * 1.5 * 0.8 + 0.1)))  # shell around the sphere-init surface
+    if cfg['learned_background']:
+        m.occupancy_grid_bg.set_binary(torch.from_numpy(np.random.default_rng(0).random((256, 256, 256)) < 0.15))
+    rays = synthetic.sample_rays(n_rays, seed=0)
+    if r != 1.5:
+        rays[:, :3] *= r / 1.5 * 0.6
+    m.background_color = torch.rand(3, device=D)
+    m.train()
+    m.update_step(0, 5001)
+    return m, torch.from_numpy(rays).to(D)
+
+
+def step(m, rays, target, mask):
+    out = m(rays)
+    v = out['rays_valid_full'][..., 0].float()[:, None]
+    l_rgb = ((out['comp_rgb_full'] - target) ** 2 * v).sum() / (v.sum() * 3).clamp(min=1)
+    l_eik = ((torch.linalg.norm(out['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+    op = torch.clamp(out['opacity'].squeeze(-1), 1e-3, 1 - 1e-3)
+    l_mask = F.binary_cross_entropy(op, mask)
+    loss = 10. * l_rgb + 0.1 * l_eik + 0.1 * l_mask
+    for p in m.parameters():
+        p.grad = None
+    loss.backward()
+    return int(out['num_samples_full'].sum())
+
+
+res = {}
+for name, fn, n in (('C3 neus-blender', configs.neus_blender, 8192), ('C4 neus-dtu', configs.neus_dtu, 4096)):
+    m, rays = build(fn, n)
+    target, mask = torch.rand(n, 3, device=D), (torch.rand(n, device=D) > 0.5).float()
+    for _ in range(3):
+        k = step(m, rays, target, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        k = step(m, rays, target, mask)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    res[name] = {'rays': n, 'samples': k, 'ms_per_step': round(ms, 3), 'rays_per_s': round(n / ms * 1e3), 'samples_per_s': round(k / ms * 1e3)}
+    del m
+    torch.cuda.empty_cache()
+print(json.dumps(res))
