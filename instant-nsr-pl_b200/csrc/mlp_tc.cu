@@ -230,7 +230,8 @@ extern "C" int nsr_mlp_fwd_tc(const nsr_mlp_t* m, const void* x_h, const void* p
   const int in_pad = (m->n_in + 15) / 16 * 16, kt = in_pad / 16;
   const size_t smem = (size_t)kRows * in_pad * 2 + kRows * 64 * 2 + 64 * in_pad * 2 + (size_t)(m->n_hidden - 1) * 64 * 64 * 2 + 16 * 64 * 2 + 128;
   const int64_t tiles = (n + kRows - 1) / kRows;
-  const int grid = (int)min((int64_t)nsr_sm_count() * 2, tiles);
+  // ~40 KB smem and 128 TMEM columns per CTA: 4 CTAs per SM overlap each other's load / MMA / epilogue phases
+  const int grid = (int)min((int64_t)nsr_sm_count() * 4, tiles);
 #define NSR_LAUNCH_TC(KT)                                                                                                  \
   case KT: {                                                                                                               \
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \

@@ -5,6 +5,7 @@ libnsr_b200.so.  Mirrors what tiny-cuda-nn's torch binding / nerfacc's python wr
 their CUDA kernels.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -82,6 +83,8 @@ class MlpSpec:
         if otype not in ('FullyFusedMLP', 'CutlassMLP'):
             raise NotImplementedError(f'network otype={otype!r} not implemented')
         self.n_in, self.n_out = int(n_in), int(n_out)
+        # 'mma_sync' (warp-level tensor cores, default) | 'tcgen05' (5th-gen tensor cores + TMEM; forward only, our extension key)
+        self.backend = str(cfg.get('backend', os.environ.get('NSR_MLP_BACKEND', 'mma_sync')))
         self.n_neurons = int(cfg.get('n_neurons', 64))
         self.n_hidden = int(cfg.get('n_hidden_layers', 1))
         if self.n_neurons != 64:
@@ -206,7 +209,10 @@ class _MlpFn(torch.autograd.Function):
     def forward(ctx, spec, x_h, params_f32, params_h):
         n = x_h.shape[0]
         out = torch.empty(n, 16, dtype=torch.float16, device=x_h.device)
-        lib.call('nsr_mlp_fwd', spec.ref(), ptr(x_h), ptr(params_h), ptr(out), n, stream())
+        if getattr(spec, 'backend', 'mma_sync') == 'tcgen05':   # tcgen05.mma + TMEM forward (bit-identical results)
+            lib.call('nsr_mlp_fwd_tc', spec.ref(), ptr(x_h), ptr(params_h), ptr(out), n, 0, None, stream())
+        else:
+            lib.call('nsr_mlp_fwd', spec.ref(), ptr(x_h), ptr(params_h), ptr(out), n, stream())
         ctx.spec = spec
         ctx.save_for_backward(x_h, params_h, out)
         return out

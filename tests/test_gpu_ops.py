@@ -408,3 +408,12 @@ def test_mlp_fwd_tcgen05_matches_mma_sync(nsr, n_in, n_out, nh, oact):
     assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
     yr = omlp.ffmlp_fwd(x.float().cpu(), net.params.detach().cpu(), n_in, n_out, 64, nh, 'ReLU', oact, emulate_fp16=True)
     assert (got.cpu() - yr).abs().max().item() <= 2e-2 * yr.abs().max().item() + 2e-3
+    # the module-level switch: tcnn.Network(..., {'backend': 'tcgen05'}) routes the forward through the same kernel, autograd intact
+    net_tc = tcnn.Network(n_in, n_out, dict(cfg, backend='tcgen05')).to(D)
+    with torch.no_grad():
+        net_tc.params.copy_(net.params)
+    xg = x.float().requires_grad_(True)
+    y_tc = net_tc(xg)
+    assert torch.equal(y_tc, net(x.float()))
+    y_tc.float().sum().backward()
+    assert net_tc.params.grad is not None and xg.grad is not None
