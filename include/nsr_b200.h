@@ -220,6 +220,18 @@ int nsr_nerf_rays_bwd(const nsr_nerf_t* f, const float* rays, const float* t_min
                       const int32_t* kidx, const void* dparams_h, const void* cparams_h, const float* g_rgb, const float* g_opacity,
                       const float* g_depth, const float* g_weights, float* grad_dparams, float* grad_cparams, float loss_scale, float* amax,
                       float t_bound, uint32_t* ticket, int64_t n_rays, void* stream);
+/* ---- fused NeuS SDF field (VolumeSDF.forward, grad_type 'analytic': models/geometry.py:158-180) -----------------------------
+ * points f32 [n,3] world (AABB contraction (x + r) / (2 r)); table fp16 (16 levels, F=2); fp32 VanillaMLP weights of the reference's
+ * layout: W1 [64,35] (inputs = [2 x01 - 1 | hash]), b1 [64], W2 [n_out,64], b2 [n_out] (weight-norm already applied), Softplus(beta=100).
+ * fwd: sdf [n], grad [n,3] = d sdf / d x_world (analytic), feature [n,n_out] (= the raw network output, sdf in column 0).
+ * bwd: upstream g_out [n,n_out] and g_grad [n,3] -> grad_table f32 (+=, first AND second order terms, one 8-byte RED per corner),
+ * dW1, db1, dW2, db2 (+=).  amax: device float, bound on |g_out|, |g_grad| (fp16 scale of the weight-gradient tiles). */
+int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
+                       const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature, int64_t n, void* stream);
+int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
+                       const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_grad, const float* amax,
+                       float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n, void* stream);
+
 /* ---- training-step back end (systems/nerf.py:68-97) ---------------------------------------------------
  * background blend + masked smooth-L1 over the valid rays: comp = acc_rgb + bg (1 - opacity), valid = opacity > 0,
  * loss = sum smooth_l1(comp - target) / max(3 n_valid, 1).  accum2: device float[2] (loss sum, n_valid), zeroed by the

@@ -1,0 +1,388 @@
+// Fused NeuS SDF field: VolumeSDF.forward with grad_type='analytic' (models/geometry.py:158-180) -- hash-grid encoding with
+// include_xyz (network_utils.py:68-79), fp32 VanillaMLP 35 -> 64 (Softplus beta=100) -> n_out (network_utils.py:95-139), and
+// the analytic normal d sdf / d x -- as ONE forward kernel, and its first- AND second-order backward (what torch reaches through
+// autograd.grad(create_graph=True) + the eikonal loss, systems/neus.py:106) as ONE backward kernel.  The math is the hand
+// derivation checked against autograd in oracle/neus_field.py:
+//   e = [2 x01 - 1 | hash(x01)];  z = W1 e + b1;  h = softplus(z);  s = sigmoid(beta z);  out = W2 h + b2;  u = s * W2[0]
+//   q = W1^T u;  grad_world = (2 q_xyz + J^T q_hash) / (2 r)
+//   backward(g_out, g_grad): gx = g_grad / (2r);  qb = [2 gx | J gx];  ub = W1 qb;  zb = (W2^T g_out) s + ub W2[0] beta s (1 - s)
+//     eb = W1^T zb;  dW1 = u qb^T + zb e^T;  db1 = zb;  dW2 = g_out h^T (+ row 0: ub s);  db2 = g_out
+//     dtable[c] += w_c eb_l + q_l scale_l (dw_c/dx . gx)        (ONE 8-byte RED per corner carries both orders)
+// The SDF branch stays fp32 on the CUDA cores (the reference runs it under autocast(False): the NeuS alpha multiplies sdf by
+// inv_s up to 1e3+), weights broadcast from shared memory; only the weight-gradient outer products go through tensor cores.
+#include "mlp_warp.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int NIN = 35;     // 3 + 16 * 2
+constexpr int NINP = 36;    // padded row length (float4 loads)
+constexpr int NH = 64;
+constexpr int NOUTP = 16;   // padded output width
+
+struct NeusW {  // shared-memory weights (floats)
+  float W1[NH][NINP];       // [k][j]
+  float W2T[NH][NOUTP];     // [k][i] = W2[i][k]
+  float b1[NH];
+  float b2[NOUTP];
+};
+
+__device__ __forceinline__ void stage_neus_weights(NeusW& w, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                   const float* __restrict__ W2, const float* __restrict__ b2, int n_out) {
+  for (int i = threadIdx.x; i < NH * NINP; i += blockDim.x) {
+    const int k = i / NINP, j = i % NINP;
+    w.W1[k][j] = j < NIN ? W1[k * NIN + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < NH * NOUTP; i += blockDim.x) {
+    const int k = i / NOUTP, o = i % NOUTP;
+    w.W2T[k][o] = o < n_out ? W2[o * NH + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < NH; i += blockDim.x) w.b1[i] = b1[i];
+  for (int i = threadIdx.x; i < NOUTP; i += blockDim.x) w.b2[i] = i < n_out ? b2[i] : 0.f;
+}
+
+__device__ __forceinline__ float softplus100(float z, float& s) {
+  const float bz = 100.f * z;
+  s = 1.f / (1.f + __expf(-bz));
+  return bz > 20.f ? z : log1pf(__expf(bz)) * 0.01f;  // torch.nn.Softplus(beta=100, threshold=20)
+}
+
+// gather: e[3..34] (features) and optionally qb[3..34] = J gx (directional derivative of every feature along gx)
+template <bool WITH_QB>
+__device__ __forceinline__ void gather_enc(const nsr_grid_t& g, const __half2* __restrict__ table, float x, float y, float z, float gx0,
+                                           float gx1, float gx2, float (&e)[NINP], float (&qb)[NINP]) {
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    const LevelInfo li = nsr_level(g, l);
+    uint32_t cx, cy, cz, idx[8];
+    float fx, fy, fz;
+    nsr_pos_fract(x, li.scale, cx, fx);
+    nsr_pos_fract(y, li.scale, cy, fy);
+    nsr_pos_fract(z, li.scale, cz, fz);
+    nsr_corner_indices(li, cx, cy, cz, idx);
+    float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 v = nsr_ld_table(table, idx[c]);
+      const float w = nsr_corner_weight(c, fx, fy, fz);
+      a0 = fmaf(w, v.x, a0);
+      a1 = fmaf(w, v.y, a1);
+      if (WITH_QB) {
+        const float dw = gx0 * nsr_corner_dweight(c, 0, fx, fy, fz) + gx1 * nsr_corner_dweight(c, 1, fx, fy, fz) +
+                         gx2 * nsr_corner_dweight(c, 2, fx, fy, fz);
+        d0 = fmaf(dw, v.x, d0);
+        d1 = fmaf(dw, v.y, d1);
+      }
+    }
+    e[3 + 2 * l] = a0;
+    e[4 + 2 * l] = a1;
+    if (WITH_QB) {
+      qb[3 + 2 * l] = d0 * li.scale;
+      qb[4 + 2 * l] = d1 * li.scale;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
+                                                                  const __half2* __restrict__ table, const float* __restrict__ W1,
+                                                                  const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                  const float* __restrict__ b2, float radius, int n_out,
+                                                                  float* __restrict__ sdf, float* __restrict__ grad,
+                                                                  float* __restrict__ feat, int64_t n) {
+  __shared__ NeusW w;
+  stage_neus_weights(w, W1, b1, W2, b2, n_out);
+  __syncthreads();
+  const float inv2r = 1.f / (2.f * radius);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const float x = (points[i * 3 + 0] + radius) * inv2r, y = (points[i * 3 + 1] + radius) * inv2r, z = (points[i * 3 + 2] + radius) * inv2r;
+    float e[NINP], q[NINP], dummy[NINP];
+    e[0] = 2.f * x - 1.f;
+    e[1] = 2.f * y - 1.f;
+    e[2] = 2.f * z - 1.f;
+    e[NIN] = 0.f;
+    gather_enc<false>(g, table, x, y, z, 0.f, 0.f, 0.f, e, dummy);
+    float out[NOUTP];
+#pragma unroll
+    for (int o = 0; o < NOUTP; ++o) out[o] = w.b2[o];
+#pragma unroll
+    for (int j = 0; j < NINP; ++j) q[j] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < NH; ++k) {
+      float row[NINP];
+#pragma unroll
+      for (int v = 0; v < NINP / 4; ++v) *reinterpret_cast<float4*>(&row[4 * v]) = *reinterpret_cast<const float4*>(&w.W1[k][4 * v]);
+      float zk = w.b1[k];
+#pragma unroll
+      for (int j = 0; j < NINP; ++j) zk = fmaf(row[j], e[j], zk);
+      float s;
+      const float h = softplus100(zk, s);
+      float w2[NOUTP];
+#pragma unroll
+      for (int v = 0; v < NOUTP / 4; ++v) *reinterpret_cast<float4*>(&w2[4 * v]) = *reinterpret_cast<const float4*>(&w.W2T[k][4 * v]);
+#pragma unroll
+      for (int o = 0; o < NOUTP; ++o) out[o] = fmaf(w2[o], h, out[o]);
+      const float u = s * w2[0];
+#pragma unroll
+      for (int j = 0; j < NINP; ++j) q[j] = fmaf(row[j], u, q[j]);
+    }
+    // analytic normal: second gather, features weighted by q
+    float gx = 2.f * q[0], gy = 2.f * q[1], gz = 2.f * q[2];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      const LevelInfo li = nsr_level(g, l);
+      uint32_t cx, cy, cz, idx[8];
+      float fx, fy, fz;
+      nsr_pos_fract(x, li.scale, cx, fx);
+      nsr_pos_fract(y, li.scale, cy, fy);
+      nsr_pos_fract(z, li.scale, cz, fz);
+      nsr_corner_indices(li, cx, cy, cz, idx);
+      float lx = 0.f, ly = 0.f, lz = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 v = nsr_ld_table(table, idx[c]);
+        const float sv = v.x * q[3 + 2 * l] + v.y * q[4 + 2 * l];
+        lx = fmaf(nsr_corner_dweight(c, 0, fx, fy, fz), sv, lx);
+        ly = fmaf(nsr_corner_dweight(c, 1, fx, fy, fz), sv, ly);
+        lz = fmaf(nsr_corner_dweight(c, 2, fx, fy, fz), sv, lz);
+      }
+      gx = fmaf(li.scale, lx, gx);
+      gy = fmaf(li.scale, ly, gy);
+      gz = fmaf(li.scale, lz, gz);
+    }
+    sdf[i] = out[0];
+    grad[i * 3 + 0] = gx * inv2r;
+    grad[i * 3 + 1] = gy * inv2r;
+    grad[i * 3 + 2] = gz * inv2r;
+#pragma unroll
+    for (int o = 0; o < NOUTP; ++o)
+      if (o < n_out) feat[i * n_out + o] = out[o];
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+// transposed fp16 tiles [feature][sample] (ld = 128 + 8): thread `row` writes consecutive halves => conflict-free
+constexpr int LDT = kThreads + 8;  // 136
+constexpr int TT_U = 0;                       // [64] u          (unscaled)
+constexpr int TT_ZB = TT_U + NH * LDT;        // [64] zb         (scaled)
+constexpr int TT_H = TT_ZB + NH * LDT;        // [64] h          (unscaled)
+constexpr int TT_US = TT_H + NH * LDT;        // [64] ub * s     (scaled)
+constexpr int TT_QB = TT_US + NH * LDT;       // [48] qb         (scaled)
+constexpr int TT_E = TT_QB + 48 * LDT;        // [48] e          (unscaled)
+constexpr int TT_GO = TT_E + 48 * LDT;        // [16] g_out      (scaled)
+constexpr int TT_ONE = TT_GO + 16 * LDT;      // [16] row 0 = 1  (unscaled)
+constexpr int TT_TOTAL = TT_ONE + 16 * LDT;
+constexpr size_t kBwdSmem = sizeof(NeusW) + (size_t)TT_TOTAL * sizeof(__half);
+
+// acc[1][2] (16 x 16 output block) += A^T-tile rows m0..m0+15 (x 128 samples) * B-tile rows n0..n0+15
+__device__ __forceinline__ void wgrad_block(float (&acc)[1][2][4], const __half* At, int m0, const __half* Bt, int n0) {
+  uint32_t a[1][8][4];
+  nsr_load_afrag<1, 8>(a, At, LDT, m0);
+  nsr_gemm_w<1, 8, 2>(acc, a, Bt + (size_t)n0 * LDT, LDT);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
+                                                                     const __half2* __restrict__ table, const float* __restrict__ W1,
+                                                                     const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                     const float* __restrict__ b2, float radius, int n_out,
+                                                                     const float* __restrict__ g_out, const float* __restrict__ g_grad,
+                                                                     const float* __restrict__ amax_ptr, float* __restrict__ grad_table,
+                                                                     float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                                                     float* __restrict__ db2, int64_t n) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  NeusW& w = *reinterpret_cast<NeusW*>(smem_raw);
+  __half* T = reinterpret_cast<__half*>(smem_raw + sizeof(NeusW));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, cq = lane & 3;
+  stage_neus_weights(w, W1, b1, W2, b2, n_out);
+  for (int i = tid; i < 16 * LDT; i += kThreads) T[TT_ONE + i] = __float2half(i < kThreads ? 1.f : 0.f);  // row 0 = ones
+  const float amax = fmaxf(amax_ptr ? __ldg(amax_ptr) : 1.f, 1e-30f);
+  const float scale = exp2f(fminf(fmaxf(floorf(log2f(4.f / amax)), -24.f), 40.f));
+  const float inv_scale = 1.f / scale, inv2r = 1.f / (2.f * radius);
+  __syncthreads();
+
+  // weight-gradient accumulators: dW1 [64 x 48] = 12 blocks, dW2 [16 x 64] = 4, db1 [64 x 16] = 4, db2 [16 x 16] = 1  => 21 / 4 warps
+  constexpr int kBlocks = 21, kSlots = 6;
+  float wacc[kSlots][1][2][4];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wacc[s][0][j][i] = 0.f;
+
+  const int64_t n_tiles = (n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + tid;
+    const bool ok = i < n;
+    __syncthreads();  // previous tile's wgrad is done with the tiles
+    float e[NINP], qb[NINP], eb[NINP], q[NINP], go[NOUTP];
+    float x = 0.f, y = 0.f, z = 0.f, gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NINP; ++j) e[j] = qb[j] = eb[j] = q[j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NOUTP; ++o) go[o] = 0.f;
+    if (ok) {
+      x = (points[i * 3 + 0] + radius) * inv2r;
+      y = (points[i * 3 + 1] + radius) * inv2r;
+      z = (points[i * 3 + 2] + radius) * inv2r;
+      gx0 = g_grad[i * 3 + 0] * inv2r;
+      gx1 = g_grad[i * 3 + 1] * inv2r;
+      gx2 = g_grad[i * 3 + 2] * inv2r;
+#pragma unroll
+      for (int o = 0; o < NOUTP; ++o)
+        if (o < n_out) go[o] = g_out[i * n_out + o];
+      e[0] = 2.f * x - 1.f;
+      e[1] = 2.f * y - 1.f;
+      e[2] = 2.f * z - 1.f;
+      qb[0] = 2.f * gx0;
+      qb[1] = 2.f * gx1;
+      qb[2] = 2.f * gx2;
+      gather_enc<true>(g, table, x, y, z, gx0, gx1, gx2, e, qb);
+    }
+#pragma unroll 2
+    for (int k = 0; k < NH; ++k) {
+      float row[NINP];
+#pragma unroll
+      for (int v = 0; v < NINP / 4; ++v) *reinterpret_cast<float4*>(&row[4 * v]) = *reinterpret_cast<const float4*>(&w.W1[k][4 * v]);
+      float zk = w.b1[k], ubk = 0.f;
+#pragma unroll
+      for (int j = 0; j < NINP; ++j) {
+        zk = fmaf(row[j], e[j], zk);
+        ubk = fmaf(row[j], qb[j], ubk);
+      }
+      float s;
+      const float h = softplus100(zk, s);
+      float w2[NOUTP];
+#pragma unroll
+      for (int v = 0; v < NOUTP / 4; ++v) *reinterpret_cast<float4*>(&w2[4 * v]) = *reinterpret_cast<const float4*>(&w.W2T[k][4 * v]);
+      float tk = 0.f;
+#pragma unroll
+      for (int o = 0; o < NOUTP; ++o) tk = fmaf(w2[o], go[o], tk);
+      const float u = s * w2[0];
+      const float zbk = tk * s + ubk * w2[0] * (100.f * s * (1.f - s));
+#pragma unroll
+      for (int j = 0; j < NINP; ++j) {
+        eb[j] = fmaf(row[j], zbk, eb[j]);
+        q[j] = fmaf(row[j], u, q[j]);
+      }
+      T[TT_U + k * LDT + tid] = __float2half(ok ? u : 0.f);
+      T[TT_ZB + k * LDT + tid] = __float2half(ok ? zbk * scale : 0.f);
+      T[TT_H + k * LDT + tid] = __float2half(ok ? h : 0.f);
+      T[TT_US + k * LDT + tid] = __float2half(ok ? ubk * s * scale : 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 48; ++j) {
+      T[TT_QB + j * LDT + tid] = __float2half(j < NIN ? qb[j < NINP ? j : 0] * scale : 0.f);
+      T[TT_E + j * LDT + tid] = __float2half(j < NIN ? e[j < NINP ? j : 0] : 0.f);
+    }
+#pragma unroll
+    for (int o = 0; o < NOUTP; ++o) T[TT_GO + o * LDT + tid] = __float2half(go[o] * scale);
+    // ---- table gradient: first- and second-order terms in one RED per corner
+    if (ok) {
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const float eb0 = eb[3 + 2 * l], eb1 = eb[4 + 2 * l], q0 = q[3 + 2 * l], q1 = q[4 + 2 * l];
+        const LevelInfo li = nsr_level(g, l);
+        uint32_t cx, cy, cz, idx[8];
+        float fx, fy, fz;
+        nsr_pos_fract(x, li.scale, cx, fx);
+        nsr_pos_fract(y, li.scale, cy, fy);
+        nsr_pos_fract(z, li.scale, cz, fz);
+        nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float wc = nsr_corner_weight(c, fx, fy, fz);
+          const float coef = li.scale * (gx0 * nsr_corner_dweight(c, 0, fx, fy, fz) + gx1 * nsr_corner_dweight(c, 1, fx, fy, fz) +
+                                         gx2 * nsr_corner_dweight(c, 2, fx, fy, fz));
+          const float v0 = wc * eb0 + coef * q0, v1 = wc * eb1 + coef * q1;
+          if (v0 != 0.f || v1 != 0.f) nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[c], v0, v1);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- weight gradients on tensor cores over the 128 samples of the tile
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int t = warp + s * 4;
+      if (t < 12) {            // dW1 block (m, n): u qb^T + zb e^T
+        const int m0 = (t / 3) * 16, n0 = (t % 3) * 16;
+        wgrad_block(wacc[s], T + TT_U, m0, T + TT_QB, n0);
+        wgrad_block(wacc[s], T + TT_ZB, m0, T + TT_E, n0);
+      } else if (t < 16) {     // dW2 block: g_out h^T (+ row 0: ones (ub s)^T)
+        const int n0 = (t - 12) * 16;
+        wgrad_block(wacc[s], T + TT_GO, 0, T + TT_H, n0);
+        wgrad_block(wacc[s], T + TT_ONE, 0, T + TT_US, n0);
+      } else if (t < 20) {     // db1 = zb . ones  (column 0)
+        wgrad_block(wacc[s], T + TT_ZB, (t - 16) * 16, T + TT_ONE, 0);
+      } else if (t < kBlocks) {  // db2 = g_out . ones
+        wgrad_block(wacc[s], T + TT_GO, 0, T + TT_ONE, 0);
+      }
+    }
+  }
+  // ---- flush
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int t = warp + s * 4;
+    if (t >= kBlocks) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = gq + ((i >> 1) << 3), cidx = j * 8 + cq * 2 + (i & 1);
+        const float val = wacc[s][0][j][i] * inv_scale;
+        if (val == 0.f) continue;
+        if (t < 12) {
+          const int m = (t / 3) * 16 + r, nn = (t % 3) * 16 + cidx;
+          if (nn < NIN) atomicAdd(dW1 + m * NIN + nn, val);
+        } else if (t < 16) {
+          const int nn = (t - 12) * 16 + cidx;
+          if (r < n_out) atomicAdd(dW2 + r * NH + nn, val);
+        } else if (t < 20) {
+          if (cidx == 0) atomicAdd(db1 + (t - 16) * 16 + r, val);
+        } else {
+          if (cidx == 0 && r < n_out) atomicAdd(db2 + r, val);
+        }
+      }
+  }
+}
+
+int check(const nsr_grid_t* g, int n_out, const char* name) {
+  NSR_REQUIRE(g != nullptr && g->n_levels == 16 && g->n_features == 2, "%s: needs a 16-level F=2 hash grid", name);
+  NSR_REQUIRE(n_out >= 1 && n_out <= 16, "%s: n_out must be in [1,16]", name);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1,
+                                  const float* W2, const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature,
+                                  int64_t n, void* stream) {
+  if (int e = check(g, n_out, "nsr_neus_field_fwd")) return e;
+  if (n == 0) return 0;
+  const int grid = (int)min((int64_t)nsr_sm_count() * 8, (n + kThreads - 1) / kThreads);
+  neus_field_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out, sdf,
+                                                                     grad, feature, n);
+  NSR_CHECK_LAUNCH("nsr_neus_field_fwd");
+  return 0;
+}
+
+extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1,
+                                  const float* W2, const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_grad,
+                                  const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n,
+                                  void* stream) {
+  if (int e = check(g, n_out, "nsr_neus_field_bwd")) return e;
+  if (n == 0) return 0;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(neus_field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) {
+      nsr_set_error("nsr_neus_field_bwd: cannot reserve %zu B shared memory: %s", kBwdSmem, cudaGetErrorString(e));
+      return 2;
+    }
+    attr_set = true;
+  }
+  const int grid = (int)min((int64_t)nsr_sm_count(), (n + kThreads - 1) / kThreads);
+  neus_field_bwd_kernel<<<grid, kThreads, kBwdSmem, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out,
+                                                                            g_out, g_grad, amax, grad_table, dW1, db1, dW2, db2, n);
+  NSR_CHECK_LAUNCH("nsr_neus_field_bwd");
+  return 0;
+}

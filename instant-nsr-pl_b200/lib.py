@@ -75,6 +75,8 @@ _SIGNATURES = {
     'nsr_pack_kept': [P, P, P, F32, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_ray_bwd_loose': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P, F32, P, I64, P],
+    'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P],
+    'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_loss_fwd': [P, P, P, P, P, P, I64, P],
     'nsr_nerf_loss_bwd': [P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],

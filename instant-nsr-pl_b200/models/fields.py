@@ -76,6 +76,48 @@ class VolumeSDF(BaseImplicitGeometry):
         self.grad_type = self.config.grad_type
         self.finite_difference_eps = self.config.get('finite_difference_eps', 1e-3)
         self._finite_difference_eps = None  # value in use; updated per step when "progressive"
+        self._fused = self.config.get('fused', True) and self._fusable()
+
+    def _fusable(self):
+        """the neus-blender / neus-dtu geometry shape (configs/neus-blender.yaml:36-63): include_xyz HashGrid(L=16, F=2) + VanillaMLP
+        35 -> 64 (Softplus 100) -> n_out <= 16 with analytic normals => one fused forward and one fused backward kernel"""
+        from .. import tcnn
+        from .networks import VanillaMLP
+        enc, net = self.encoding, self.network
+        try:
+            return (self.grad_type == 'analytic' and enc.include_xyz and isinstance(enc.encoding, tcnn.Encoding)
+                    and enc.encoding.grid is not None and enc.encoding.grid.n_levels == 16 and enc.encoding.grid.n_features == 2
+                    and isinstance(net, VanillaMLP) and net.n_hidden_layers == 1 and net.n_neurons == 64 and net.sphere_init
+                    and self.config.mlp_network_config.get('output_activation', 'none') in (None, 'none') and self.n_output_dims <= 16
+                    and 'sdf_activation' not in self.config and 'feature_activation' not in self.config)
+        except AttributeError:
+            return False
+
+    def _effective_weights(self):
+        ws = []
+        for lin in (self.network.layers[0], self.network.layers[2]):
+            if hasattr(lin, 'weight_g'):
+                ws.append(torch._weight_norm(lin.weight_v, lin.weight_g, 0))
+            else:
+                ws.append(lin.weight)
+            ws.append(lin.bias)
+        return ws
+
+    def _forward_fused(self, points, with_grad, with_feature):
+        from .. import ops
+        from ..nerfacc import ContractionType
+        enc = self.encoding.encoding
+        shape = points.shape[:-1]
+        W1, b1, W2, b2 = self._effective_weights()
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            sdf, grad, feat = ops.neus_sdf(enc.grid, self.radius, points.reshape(-1, 3), enc.params, enc._params_half(), W1, b1, W2, b2)
+        rv = [sdf.reshape(shape)]
+        if with_grad:
+            rv.append(grad.reshape(*shape, 3))
+        if with_feature:
+            rv.append(feat.reshape(*shape, self.n_output_dims))
+        rv = [v if self.training else v.detach() for v in rv]
+        return rv[0] if len(rv) == 1 else rv
 
     def _query(self, unit_points):
         return self.network(self.encoding(unit_points.reshape(-1, 3)))
@@ -86,6 +128,9 @@ class VolumeSDF(BaseImplicitGeometry):
         return out0
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
+        from ..nerfacc import ContractionType as _CT
+        if self._fused and not with_laplace and points.is_cuda and self.contraction_type == _CT.AABB:
+            return self._forward_fused(points, with_grad, with_feature)
         analytic = with_grad and self.grad_type == 'analytic'
         with torch.inference_mode(torch.is_inference_mode_enabled() and not analytic):
             with torch.set_grad_enabled(self.training or analytic):

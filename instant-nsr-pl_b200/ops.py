@@ -371,3 +371,47 @@ def accumulate(weights, values, offsets, ray_indices):
     w = contig(weights.reshape(-1, 1), torch.float32)
     v = None if values is None else contig(values.reshape(w.shape[0], -1), torch.float32)
     return _Accumulate.apply(w, v, offsets, ray_indices)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused NeuS SDF field (hash grid + fp32 MLP + analytic normal; first and second order backward in one kernel)
+# --------------------------------------------------------------------------------------------------
+class _NeusSDF(torch.autograd.Function):
+    """(sdf, grad, feature) = VolumeSDF.forward(points) (models/geometry.py:158-180).  torch sees a first-order Function:
+    the second-order terms the eikonal / normal-dependent losses need are inside nsr_neus_field_bwd."""
+
+    @staticmethod
+    def forward(ctx, spec, radius, n_out, points, table_f32, table_h, W1, b1, W2, b2):
+        n = points.shape[0]
+        dev = points.device
+        sdf = torch.empty(n, device=dev)
+        grad = torch.empty(n, 3, device=dev)
+        feat = torch.empty(n, n_out, device=dev)
+        lib.call('nsr_neus_field_fwd', spec.ref(), ptr(points), ptr(table_h), ptr(W1), ptr(b1), ptr(W2), ptr(b2), float(radius), int(n_out),
+                 ptr(sdf), ptr(grad), ptr(feat), n, stream())
+        ctx.spec, ctx.radius, ctx.n_out = spec, radius, n_out
+        ctx.save_for_backward(points, table_h, W1, b1, W2, b2)
+        return sdf, grad, feat
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad, g_feat):
+        points, table_h, W1, b1, W2, b2 = ctx.saved_tensors
+        n, dev, n_out = points.shape[0], points.device, ctx.n_out
+        g_out = torch.zeros(n, n_out, device=dev) if g_feat is None else contig(g_feat, torch.float32).clone()
+        if g_sdf is not None:
+            g_out[:, 0] += g_sdf.float()
+        g_grad = torch.zeros(n, 3, device=dev) if g_grad is None else contig(g_grad, torch.float32)
+        amax = torch.maximum(g_out.abs().max(), g_grad.abs().max()).reshape(1) if n > 0 else torch.ones(1, device=dev)
+        dtable = torch.zeros(ctx.spec.n_params, device=dev)
+        dW1, db1, dW2, db2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
+        lib.call('nsr_neus_field_bwd', ctx.spec.ref(), ptr(points), ptr(table_h), ptr(W1), ptr(b1), ptr(W2), ptr(b2), float(ctx.radius),
+                 int(n_out), ptr(g_out), ptr(g_grad), ptr(amax), ptr(dtable), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), n, stream())
+        return None, None, None, None, dtable, None, dW1, db1, dW2, db2
+
+
+def neus_sdf(spec, radius, points, table_f32, table_h, W1, b1, W2, b2):
+    """points [N,3] world (AABB scene of half-extent `radius`); W1 [64,35], b1 [64], W2 [n_out,64], b2 [n_out] fp32 (effective weights)."""
+    check_cuda(points, table_h, W1, W2, what='VolumeSDF (fused)')
+    n_out = W2.shape[0]
+    return _NeusSDF.apply(spec, float(radius), int(n_out), contig(points.detach(), torch.float32), table_f32, table_h,
+                          contig(W1, torch.float32), contig(b1, torch.float32), contig(W2, torch.float32), contig(b2, torch.float32))

@@ -241,3 +241,35 @@ def test_occgrid_update_rule_and_bit_packing():
     flat = b1.view(-1).numpy()
     for idx in (0, 1, 37, 255, 300, 511):
         assert bool((bits[idx >> 5] >> (idx & 31)) & 1) == bool(flat[idx])
+
+
+def test_neus_field_manual_formulas_match_autograd():
+    """oracle/neus_field.py (the hand-derived first + second order backward the fused NeuS kernels implement) == torch autograd of
+    VolumeSDF's analytic-normal construction (models/geometry.py:158-180), in float64."""
+    from oracle import neus_field
+    cfg = dict(n_levels=5, n_features_per_level=2, log2_hashmap_size=9, base_resolution=4, per_level_scale=1.6)
+    lt = hashgrid.level_table(cfg)
+    g = torch.Generator().manual_seed(0)
+    n, n_in, n_out, r = 40, 3 + 2 * 5, 13, 1.5
+    table = (torch.randn(lt['n_params'], generator=g, dtype=torch.float64) * 0.3).requires_grad_(True)
+    W1 = (torch.randn(64, n_in, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    b1 = (torch.randn(64, generator=g, dtype=torch.float64) * 0.01).requires_grad_(True)
+    W2 = (torch.randn(n_out, 64, generator=g, dtype=torch.float64) * 0.2).requires_grad_(True)
+    b2 = (torch.randn(n_out, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    pts = ((torch.rand(n, 3, generator=g, dtype=torch.float64) * 2 - 1) * 1.2).requires_grad_(True)
+    # autograd path, as the reference builds it
+    x01 = (pts + r) / (2 * r)
+    enc = torch.cat([x01 * 2 - 1, hashgrid.hashgrid_fwd(x01, table.view(-1, 2), lt)], -1)
+    out = torch.nn.functional.softplus(enc @ W1.t() + b1, beta=100) @ W2.t() + b2
+    sdf = out[:, 0]
+    grad, = torch.autograd.grad(sdf, pts, torch.ones_like(sdf), create_graph=True)
+    g_out = torch.randn(n, n_out, generator=g, dtype=torch.float64)
+    g_grad = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    ((out * g_out).sum() + (grad * g_grad).sum()).backward()
+    # manual path
+    sdf_m, grad_m, out_m, cache = neus_field.forward(pts.detach(), table.detach(), lt, W1.detach(), b1.detach(), W2.detach(), b2.detach(), r)
+    np.testing.assert_allclose(out_m.numpy(), out.detach().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(grad_m.numpy(), grad.detach().numpy(), rtol=1e-8, atol=1e-10)
+    gm = neus_field.backward(cache, table.detach(), lt, W1.detach(), b1.detach(), W2.detach(), b2.detach(), r, g_out, g_grad)
+    for name, ref in (('W1', W1.grad), ('b1', b1.grad), ('W2', W2.grad), ('b2', b2.grad), ('table', table.grad)):
+        np.testing.assert_allclose(gm[name].numpy(), ref.numpy(), rtol=1e-7, atol=1e-9, err_msg=name)
