@@ -228,7 +228,8 @@ def gpu_arm(args):
 
     # the public fast path: whole step (march .. backward) as one CUDA graph, no host sync inside
     # N > 1: the NCCL all-reduce (mean) of the parameter gradients is captured into the same graph, right behind the backward
-    sync = GradSync(params, world) if world > 1 else None
+    comm = os.environ.get('NSR_GRAD_COMM_DTYPE', 'fp32')  # 'bf16': opt-in wire compression of the table gradient
+    sync = GradSync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None)) if world > 1 else None
     gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
                         post_backward=(sync.all_reduce_mean if sync is not None else None))
 
@@ -359,7 +360,7 @@ def gpu_arm(args):
                    'rays_per_gpu': N_RAYS, 'marched_samples_per_step': marched, 'kept_samples_per_step': kept,
                    'samples_per_s': kept * args.steps / (ms * 1e-3), 'l2': 'flushed (256 MB write) before every timed step',
                    'parallelism': f'dp{world}' if world > 1 else 'single',
-                   'step': 'mask march + per-ray forward (early termination) + fused smooth-L1 loss + backward, one CUDA graph (nsr_b200.graph.GraphedStep)' + (' + NCCL all-reduce of grads' if world > 1 else ''),
+                   'step': 'mask march + per-ray forward (early termination) + fused smooth-L1 loss + backward, one CUDA graph (nsr_b200.graph.GraphedStep)' + (f' + NCCL all-reduce of grads ({comm})' if world > 1 else ''),
                    'eager_api_ms_per_step': ms_eager},
         'e2e': {'value': N_RAYS * world * args.steps / (ms_e2e * 1e-3), 'unit': 'rays/s',
                 'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4},

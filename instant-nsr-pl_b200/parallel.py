@@ -7,10 +7,16 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, params, world_size=None, group=None):
+    """comm_dtype=None: all-reduce the fp32 gradients as they are (what the reference's DDP does).
+    comm_dtype=torch.bfloat16: large gradients (the hash table) travel as bf16 -- half the bytes on the wire, 8-bit mantissa;
+    an opt-in wire-compression hook, not the default."""
+
+    def __init__(self, params, world_size=None, group=None, comm_dtype=None, compress_min_numel=1 << 20):
         self.params = list(params)
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.comm_dtype = comm_dtype
+        self.compress_min_numel = compress_min_numel
 
     def all_reduce_mean(self):
         """in-place mean of every .grad over the ranks (largest tensor first so NCCL starts on the 50 MB
@@ -19,10 +25,19 @@ class GradSync:
             return
         grads = [p.grad for p in self.params if p.grad is not None]
         grads.sort(key=lambda g: -g.numel())
-        works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for g in grads]
+        inv = 1.0 / self.world
+        works, packed = [], []
+        for g in grads:
+            if self.comm_dtype is not None and g.numel() >= self.compress_min_numel:
+                buf = g.to(self.comm_dtype)
+                packed.append((g, buf))
+                works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         for w in works:
             w.wait()
-        inv = 1.0 / self.world
+        for g, buf in packed:
+            g.copy_(buf)
         for g in grads:
             g.mul_(inv)
 

