@@ -351,6 +351,31 @@ def gpu_arm(args):
                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom], 'kernel_ms': kern[dom]['ms'],
                     'whole_step': {'algorithmic_bytes': step_bytes, 'achieved': step_bytes / (ms_step * 1e-3) / 1e9,
                                    'frac': step_bytes / (ms_step * 1e-3) / 1e9 / peak}}
+    # ---- adjacent row 8f-2 (not part of `value`): the fused AdamW pass over all parameters, timed alone with CUDA events, L2 flushed
+    adamw = None
+    if world == 1:
+        from nsr_b200.optim import FusedAdamW
+        opt = FusedAdamW.for_model(model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15)   # nerf-blender.yaml:74-79
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        for _ in range(3):
+            opt.step()
+        evs = []
+        for i in range(20):
+            flush.fill_(float(i))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            opt.step()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        opt_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        n_par = sum(p.numel() for p in params)
+        opt_bytes = 30.0 * n_par   # p, g, m, v read (16 B) + p, m, v written (12 B) + fp16 copy written (2 B)
+        adamw = {'kernel': 'adamw_kernel (nsr_adamw_step)', 'params': n_par, 'ms': opt_ms, 'algorithmic_bytes': opt_bytes,
+                 'achieved_GBps': opt_bytes / (opt_ms * 1e-3) / 1e9, 'frac_of_hbm_peak': opt_bytes / (opt_ms * 1e-3) / 1e9 / peak,
+                 'train_step_ms_with_optimizer': ms_step + opt_ms}
     cpu = time_cpu(2, 1, n_rays=512) if world == 1 else None
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
@@ -366,6 +391,8 @@ def gpu_arm(args):
                 'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels_ms': {k: round(v['ms'], 5) for k, v in kern.items()},
     }
+    if adamw is not None:
+        line['optimizer'] = adamw
     if cpu is not None:
         line['cpu_baseline'] = {'value': cpu['rays_per_s'], 'unit': 'rays/s', 'cores': cpu['cores'], 'kind': 'port',
                                 'sample': f"2 steps x {cpu['n_rays']} rays of the C2 workload (kept {cpu['kept']:.0f} samples/step), fwd+bwd, "

@@ -70,6 +70,26 @@ typedef struct {
   int32_t color_hidden;    /* must be 2 */
 } nsr_nerf_t;
 
+/* VolumeRadiance fused kernel (models/texture.py:23-30): input = cat[feature (n_feat) | SH degree 4 of the ray direction (16) |
+ * extra (n_extra, NeuS: the unit normal)], which must be 32 wide; FullyFused 64-wide MLP with two hidden ReLU layers, 3 outputs.
+ * act_mode 0: raw network output; 1: Sigmoid as the network's output activation (nerf-blender.yaml:66, result rounded to fp16);
+ * 2: no network activation, fp32 sigmoid afterwards (neus-blender.yaml `color_activation: sigmoid`). */
+typedef struct {
+  int32_t n_feat;
+  int32_t n_extra;
+  int32_t act_mode;
+} nsr_radiance_t;
+
+/* torch.optim.AdamW hyper-parameters (systems/utils.py:314-325; nerf-blender.yaml:74-79: lr 1e-2, betas (0.9, 0.99), eps 1e-15,
+ * weight_decay = torch's default 1e-2).  step: 1-based number of THIS update; inv_grad_scale: gradients are multiplied by it
+ * first (1 / GradScaler scale; 1 for none). */
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+  float inv_grad_scale;
+} nsr_adamw_t;
+
+
 const char* nsr_last_error(void);
 int nsr_version(void);
 int nsr_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -224,13 +244,55 @@ int nsr_nerf_rays_bwd(const nsr_nerf_t* f, const float* rays, const float* t_min
  * points f32 [n,3] world (AABB contraction (x + r) / (2 r)); table fp16 (16 levels, F=2); fp32 VanillaMLP weights of the reference's
  * layout: W1 [64,35] (inputs = [2 x01 - 1 | hash]), b1 [64], W2 [n_out,64], b2 [n_out] (weight-norm already applied), Softplus(beta=100).
  * fwd: sdf [n], grad [n,3] = d sdf / d x_world (analytic), feature [n,n_out] (= the raw network output, sdf in column 0).
- * bwd: upstream g_out [n,n_out] and g_grad [n,3] -> grad_table f32 (+=, first AND second order terms, one 8-byte RED per corner),
+ * bwd: upstream g_out [n,n_out], g_sdf [n] (added to column 0) and g_grad [n,3] (each may be NULL) -> grad_table f32 (+=, first AND second order terms, one 8-byte RED per corner),
  * dW1, db1, dW2, db2 (+=).  amax: device float, bound on |g_out|, |g_grad| (fp16 scale of the weight-gradient tiles). */
 int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
                        const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature, int64_t n, void* stream);
 int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
-                       const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_grad, const float* amax,
-                       float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n, void* stream);
+                       const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_sdf, const float* g_grad,
+                       const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n, void* stream);
+/* out[0] = max(|a|, |b|, |c|) over up to three fp32 arrays (NULL / 0 skipped): the bound nsr_neus_field_bwd's amax wants. */
+int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, void* stream);
+
+/* sample -> world position / view direction / interval length (models/nerf.py:96-99, models/neus.py:222-225): rays f32 [N,6],
+ * positions [K,3] = o + d * (t0 + t1) / 2 (mul then add, no fma), dirs [K,3] and dists [K] = t1 - t0 may be NULL. */
+int nsr_sample_points(const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends, float* positions,
+                      float* dirs, float* dists, int64_t n, void* stream);
+
+/* ---- NeuS shading pieces (models/neus.py:117-139, 225, 237-243) --------------------------------------------------------------
+ * nsr_neus_alpha_fwd: normal = normalize(sdf_grad) and alpha = get_alpha(sdf, normal, dirs, dists) with the cos-anneal ratio;
+ * dirs f32 [K,3] per-sample view directions, dists f32 [K] = t_ends - t_starts, inv_s: DEVICE scalar (already clipped to [1e-6, 1e6]).
+ * nsr_neus_alpha_bwd: d_alpha [K], d_normal [K,3] (may be NULL) -> d_sdf [K], d_sdf_grad [K,3], d_inv_s (+=, device scalar). */
+int nsr_neus_alpha_fwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, float* alpha, float* normal, int64_t n,
+                       void* stream);
+int nsr_neus_alpha_bwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, const float* d_alpha, const float* d_normal,
+                       float* d_sdf, float* d_sdf_grad, float* d_inv_s, int64_t n, void* stream);
+/* render_weight_from_alpha + accumulate_along_rays x4 (opacity, depth at the sample midpoints, rgb, normal) in one pass per
+ * direction.  offsets int64 [n_rays+1]; comp_normal is the un-normalised weighted sum.  Backward: any of the g_* may be NULL. */
+int nsr_neus_composite_fwd(const float* alphas, const float* rgbs, const float* normals, const float* t_starts, const float* t_ends,
+                           const int64_t* offsets, float* weights, float* trans, float* opacity, float* depth, float* comp_rgb,
+                           float* comp_normal, int64_t n_rays, void* stream);
+int nsr_neus_composite_bwd(const float* alphas, const float* rgbs, const float* normals, const float* t_starts, const float* t_ends,
+                           const float* weights, const float* trans, const int64_t* offsets, const float* g_weights,
+                           const float* g_opacity, const float* g_depth, const float* g_rgb, const float* g_normal, float* d_alphas,
+                           float* d_rgbs, float* d_normals, int64_t n_rays, void* stream);
+/* VolumeRadiance (see nsr_radiance_t): feat f32 [n,n_feat], dirs f32 [n,3] (unit view directions, per sample), extra f32 [n,n_extra] (or NULL), params fp16 [7168] in tcnn order,
+ * rgb f32 [n,3].  Backward: d_rgb [n,3] -> d_feat, d_extra (either may be NULL), grad_params f32 [7168] (+=);
+ * loss_scale <= 0: choose the fp16 dgrad scale from *amax (device float: max |d_rgb|). */
+int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra,
+                     const void* params_h, float* rgb, int64_t n, void* stream);
+int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra,
+                     const void* params_h, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
+                     float* grad_params, int64_t n, void* stream);
+
+/* ---- optimizer (systems/utils.py:314-325) ------------------------------------------------------------------------
+ * One fused pass of torch.optim.AdamW over a flat fp32 vector: un-scale, skip on *found_inf != 0, decoupled weight decay, moments,
+ * update, and (params_half != NULL) the fp16 copy the kernels read.  dev_lr_step (device float[2] = {lr, step}, or NULL)
+ * overrides h->lr / h->step for CUDA-graph capture.  All buffers 16-byte aligned. */
+int nsr_adamw_step(const nsr_adamw_t* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_half,
+                   const float* dev_lr_step, const float* found_inf, int64_t n, void* stream);
+/* found_inf[0] = 1 if any entry of grads is inf / nan (left untouched otherwise). */
+int nsr_grad_nonfinite(const float* grads, float* found_inf, int64_t n, void* stream);
 
 /* ---- training-step back end (systems/nerf.py:68-97) ---------------------------------------------------
  * background blend + masked smooth-L1 over the valid rays: comp = acc_rgb + bg (1 - opacity), valid = opacity > 0,

@@ -364,3 +364,35 @@ extern "C" int nsr_march_rays_expand(const nsr_march_t* p, const uint32_t* masks
   NSR_CHECK_LAUNCH("nsr_march_rays_expand");
   return 0;
 }
+
+namespace {
+// midpoints -> world positions, per-sample view directions and interval lengths (models/nerf.py:96-99, models/neus.py:222-225:
+// positions = rays_o[ri] + rays_d[ri] * (t_starts + t_ends) / 2, dists = t_ends - t_starts) in one pass; this file is compiled
+// without fma contraction, so the positions equal torch's mul-then-add bit for bit.
+__global__ void __launch_bounds__(256) sample_points_kernel(const float* __restrict__ rays, const int32_t* __restrict__ ray_indices,
+                                                            const float* __restrict__ t_starts, const float* __restrict__ t_ends,
+                                                            float* __restrict__ positions, float* __restrict__ dirs,
+                                                            float* __restrict__ dists, int64_t n) {
+  const int64_t i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= n) return;
+  const float* r = rays + (size_t)ray_indices[i] * 6;
+  const float t0 = t_starts[i], t1 = t_ends[i];
+  const float mid = (t0 + t1) / 2.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float d = __ldg(r + 3 + c);
+    positions[i * 3 + c] = __ldg(r + c) + d * mid;
+    if (dirs) dirs[i * 3 + c] = d;
+  }
+  if (dists) dists[i] = t1 - t0;
+}
+}  // namespace
+
+extern "C" int nsr_sample_points(const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                                 float* positions, float* dirs, float* dists, int64_t n, void* stream) {
+  NSR_REQUIRE(positions != nullptr, "nsr_sample_points: positions is NULL");
+  if (n == 0) return 0;
+  sample_points_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_indices, t_starts, t_ends, positions, dirs, dists, n);
+  NSR_CHECK_LAUNCH("nsr_sample_points");
+  return 0;
+}

@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
                                                                      const __half2* __restrict__ table, const float* __restrict__ W1,
                                                                      const float* __restrict__ b1, const float* __restrict__ W2,
                                                                      const float* __restrict__ b2, float radius, int n_out,
-                                                                     const float* __restrict__ g_out, const float* __restrict__ g_grad,
+                                                                     const float* __restrict__ g_out, const float* __restrict__ g_sdf,
+                                                                     const float* __restrict__ g_grad,
                                                                      const float* __restrict__ amax_ptr, float* __restrict__ grad_table,
                                                                      float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                                                      float* __restrict__ db2, int64_t n) {
@@ -224,12 +225,15 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
       x = (points[i * 3 + 0] + radius) * inv2r;
       y = (points[i * 3 + 1] + radius) * inv2r;
       z = (points[i * 3 + 2] + radius) * inv2r;
-      gx0 = g_grad[i * 3 + 0] * inv2r;
-      gx1 = g_grad[i * 3 + 1] * inv2r;
-      gx2 = g_grad[i * 3 + 2] * inv2r;
+      gx0 = g_grad ? g_grad[i * 3 + 0] * inv2r : 0.f;
+      gx1 = g_grad ? g_grad[i * 3 + 1] * inv2r : 0.f;
+      gx2 = g_grad ? g_grad[i * 3 + 2] * inv2r : 0.f;
+      if (g_out) {
 #pragma unroll
-      for (int o = 0; o < NOUTP; ++o)
-        if (o < n_out) go[o] = g_out[i * n_out + o];
+        for (int o = 0; o < NOUTP; ++o)
+          if (o < n_out) go[o] = g_out[i * n_out + o];
+      }
+      if (g_sdf) go[0] += g_sdf[i];
       e[0] = 2.f * x - 1.f;
       e[1] = 2.f * y - 1.f;
       e[2] = 2.f * z - 1.f;
@@ -366,8 +370,8 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
 }
 
 extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1,
-                                  const float* W2, const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_grad,
-                                  const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n,
+                                  const float* W2, const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_sdf,
+                                  const float* g_grad, const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n,
                                   void* stream) {
   if (int e = check(g, n_out, "nsr_neus_field_bwd")) return e;
   if (n == 0) return 0;
@@ -382,7 +386,35 @@ extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, cons
   }
   const int grid = (int)min((int64_t)nsr_sm_count(), (n + kThreads - 1) / kThreads);
   neus_field_bwd_kernel<<<grid, kThreads, kBwdSmem, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out,
-                                                                            g_out, g_grad, amax, grad_table, dW1, db1, dW2, db2, n);
+                                                                            g_out, g_sdf, g_grad, amax, grad_table, dW1, db1, dW2, db2, n);
   NSR_CHECK_LAUNCH("nsr_neus_field_bwd");
+  return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
+                                                     const float* __restrict__ c, int64_t nc, float* __restrict__ out) {
+  float m = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * 256, t0 = blockIdx.x * 256ll + threadIdx.x;
+  for (int64_t i = t0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+  for (int64_t i = t0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+  for (int64_t i = t0; i < nc; i += stride) m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // non-negative floats order like ints
+}
+}  // namespace
+
+extern "C" int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, void* stream) {
+  NSR_REQUIRE(out != nullptr, "nsr_absmax3: out is NULL");
+  if (a == nullptr) na = 0;
+  if (b == nullptr) nb = 0;
+  if (c == nullptr) nc = 0;
+  cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream);
+  const int64_t nmax = max(na, max(nb, nc));
+  if (nmax == 0) return 0;
+  const int grid = (int)min((int64_t)nsr_sm_count() * 4, (nmax + 255) / 256);
+  absmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, na, b, nb, c, nc, out);
+  NSR_CHECK_LAUNCH("nsr_absmax3");
   return 0;
 }

@@ -176,6 +176,97 @@ __global__ void __launch_bounds__(kWarps * 32) accumulate_kernel(const float* __
   }
 }
 
+// ---- NeuS compositing in one pass per direction (models/neus.py:237-243: render_weight_from_alpha + 4x accumulate_along_rays).
+// forward: weights, transmittance, opacity, depth, rgb and (un-normalised) normal sums per ray.
+__global__ void __launch_bounds__(kWarps * 32) neus_composite_fwd_kernel(const float* __restrict__ alphas, const float* __restrict__ rgbs,
+                                                                         const float* __restrict__ normals, const float* __restrict__ t_starts,
+                                                                         const float* __restrict__ t_ends, const int64_t* __restrict__ offsets,
+                                                                         float* __restrict__ weights, float* __restrict__ trans,
+                                                                         float* __restrict__ opacity, float* __restrict__ depth,
+                                                                         float* __restrict__ comp_rgb, float* __restrict__ comp_normal,
+                                                                         int64_t n_rays) {
+  RAY_PROLOGUE
+  float carry = 1.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // opacity, depth, rgb, normal
+  for (int64_t b = beg; b < end; b += 32) {
+    const int64_t i = b + lane;
+    const bool ok = i < end;
+    const float a = ok ? alphas[i] : 0.f;
+    const float incl = warp_incl_prod(1.f - a, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float T = carry * excl;
+    const float w = T * a;
+    if (ok) {
+      weights[i] = w;
+      trans[i] = T;
+      acc[0] += w;
+      acc[1] += w * ((t_starts[i] + t_ends[i]) * 0.5f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc[2 + c] += w * rgbs[i * 3 + c];
+        acc[5 + c] += w * normals[i * 3 + c];
+      }
+    }
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+    opacity[ray] = acc[0];
+    depth[ray] = acc[1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      comp_rgb[ray * 3 + c] = acc[2 + c];
+      comp_normal[ray * 3 + c] = acc[5 + c];
+    }
+  }
+}
+
+// backward: g_w = g_opacity + g_depth * mid + g_rgb . rgb + g_normal . n (+ g_weights); d alpha as in weight_alpha_bwd_kernel;
+// d rgb_i = w_i g_rgb[ray], d normal_i = w_i g_normal[ray].
+__global__ void __launch_bounds__(kWarps * 32) neus_composite_bwd_kernel(const float* __restrict__ alphas, const float* __restrict__ rgbs,
+                                                                         const float* __restrict__ normals, const float* __restrict__ t_starts,
+                                                                         const float* __restrict__ t_ends, const float* __restrict__ weights,
+                                                                         const float* __restrict__ trans, const int64_t* __restrict__ offsets,
+                                                                         const float* __restrict__ g_weights, const float* __restrict__ g_opacity,
+                                                                         const float* __restrict__ g_depth, const float* __restrict__ g_rgb,
+                                                                         const float* __restrict__ g_normal, float* __restrict__ d_alphas,
+                                                                         float* __restrict__ d_rgbs, float* __restrict__ d_normals,
+                                                                         int64_t n_rays) {
+  RAY_PROLOGUE
+  const float go = g_opacity ? g_opacity[ray] : 0.f, gd = g_depth ? g_depth[ray] : 0.f;
+  float gc[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (g_rgb) gc[c] = g_rgb[ray * 3 + c];
+    if (g_normal) gn[c] = g_normal[ray * 3 + c];
+  }
+  float carry = 0.f;
+  const int64_t n = end - beg;
+  for (int64_t cb = ((n - 1) / 32) * 32; cb >= 0 && n > 0; cb -= 32) {
+    const int64_t i = beg + cb + lane;
+    const bool ok = i < end;
+    float w = 0.f, g = 0.f;
+    if (ok) {
+      w = weights[i];
+      g = go + gd * ((t_starts[i] + t_ends[i]) * 0.5f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g += gc[c] * rgbs[i * 3 + c] + gn[c] * normals[i * 3 + c];
+      if (g_weights) g += g_weights[i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        d_rgbs[i * 3 + c] = w * gc[c];
+        d_normals[i * 3 + c] = w * gn[c];
+      }
+    }
+    const float gw = g * w;
+    const float suf = warp_suffix_sum(gw, lane);
+    if (ok) d_alphas[i] = g * trans[i] - (carry + suf - gw) / fmaxf(1.f - alphas[i], 1e-10f);
+    carry += __shfl_sync(0xffffffffu, suf, 0);
+  }
+}
+
 }  // namespace
 
 #define RAY_LAUNCH(kernel, name, ...)                                                                       \
@@ -212,4 +303,19 @@ extern "C" int nsr_accumulate(const float* weights, const float* values, const i
                               void* stream) {
   NSR_REQUIRE(d >= 1, "nsr_accumulate: d must be >= 1");
   RAY_LAUNCH(accumulate_kernel, "nsr_accumulate", weights, values, offsets, out, d, n_rays);
+}
+
+extern "C" int nsr_neus_composite_fwd(const float* alphas, const float* rgbs, const float* normals, const float* t_starts,
+                                      const float* t_ends, const int64_t* offsets, float* weights, float* trans, float* opacity,
+                                      float* depth, float* comp_rgb, float* comp_normal, int64_t n_rays, void* stream) {
+  RAY_LAUNCH(neus_composite_fwd_kernel, "nsr_neus_composite_fwd", alphas, rgbs, normals, t_starts, t_ends, offsets, weights, trans, opacity,
+             depth, comp_rgb, comp_normal, n_rays);
+}
+extern "C" int nsr_neus_composite_bwd(const float* alphas, const float* rgbs, const float* normals, const float* t_starts,
+                                      const float* t_ends, const float* weights, const float* trans, const int64_t* offsets,
+                                      const float* g_weights, const float* g_opacity, const float* g_depth, const float* g_rgb,
+                                      const float* g_normal, float* d_alphas, float* d_rgbs, float* d_normals, int64_t n_rays,
+                                      void* stream) {
+  RAY_LAUNCH(neus_composite_bwd_kernel, "nsr_neus_composite_bwd", alphas, rgbs, normals, t_starts, t_ends, weights, trans, offsets,
+             g_weights, g_opacity, g_depth, g_rgb, g_normal, d_alphas, d_rgbs, d_normals, n_rays);
 }

@@ -43,6 +43,17 @@ class NerfT(C.Structure):
                 ('density_hidden', C.c_int32), ('color_hidden', C.c_int32)]
 
 
+class RadianceT(C.Structure):
+    """nsr_radiance_t: cat[feature | SH4 | extra] -> FullyFused colour MLP."""
+    _fields_ = [('n_feat', C.c_int32), ('n_extra', C.c_int32), ('act_mode', C.c_int32)]
+
+
+class AdamWT(C.Structure):
+    """nsr_adamw_t: torch.optim.AdamW hyper-parameters of one update."""
+    _fields_ = [('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
+                ('step', C.c_int32), ('inv_grad_scale', C.c_float)]
+
+
 P, I64, F32, I32 = C.c_void_p, C.c_int64, C.c_float, C.c_int32
 
 # name -> argtypes (all return int)
@@ -76,7 +87,17 @@ _SIGNATURES = {
     'nsr_nerf_ray_bwd_loose': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P, F32, P, I64, P],
     'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P],
-    'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_absmax3': [P, I64, P, I64, P, I64, P, P],
+    'nsr_sample_points': [P, P, P, P, P, P, P, I64, P],
+    'nsr_neus_alpha_fwd': [P, P, P, P, P, F32, P, P, I64, P],
+    'nsr_neus_alpha_bwd': [P, P, P, P, P, F32, P, P, P, P, P, I64, P],
+    'nsr_neus_composite_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P],
+    'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P],
+    'nsr_adamw_step': [P, P, P, P, P, P, P, P, I64, P],
+    'nsr_grad_nonfinite': [P, P, I64, P],
     'nsr_nerf_loss_fwd': [P, P, P, P, P, P, I64, P],
     'nsr_nerf_loss_bwd': [P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],

@@ -9,6 +9,7 @@ from . import register
 from ..nerfacc import ContractionType
 from .common import BaseModel, get_activation, scale_anything, update_module_step
 from .networks import get_encoding, get_mlp, get_encoding_with_network
+from .. import ops, tcnn
 
 
 def contract_to_unisphere(x, radius, contraction_type):
@@ -201,8 +202,46 @@ class VolumeRadiance(nn.Module):
         self.encoding = get_encoding(self.n_dir_dims, self.config.dir_encoding_config)
         self.n_input_dims = self.config.input_feature_dim + self.encoding.n_output_dims
         self.network = get_mlp(self.n_input_dims, self.n_output_dims, self.config.mlp_network_config)
+        self._rspec, self._rspec_key = None, None
+
+    def _fused_spec(self, features, dirs, args):
+        """RadianceSpec when the whole module maps onto the one-kernel path (csrc/radiance.cu): SH degree 4 + FullyFusedMLP with
+        two 64-wide ReLU layers over a 32-wide input (every hash-grid config of the reference); None -> composed path."""
+        if not self.config.get('fused', True) or not features.is_cuda or self.n_dir_dims != 3:
+            return None
+        enc, net = self.encoding, self.network
+        if getattr(enc, 'include_xyz', False):
+            return None
+        enc = getattr(enc, 'encoding', enc)  # CompositeEncoding wrapper
+        if not (isinstance(enc, tcnn.Encoding) and enc.otype == 'SphericalHarmonics' and isinstance(net, tcnn.Network)):
+            return None
+        m = net.mlp
+        if m.n_in != 32 or m.n_out != 3 or m.n_hidden != 2 or m.struct.activation != 1 or m.backend != 'mma_sync':
+            return None
+        if len(args) > 1 or features.dim() != 2 or dirs.dim() != 2:
+            return None
+        n_extra = args[0].shape[-1] if args else 0
+        color_act = self.config.get('color_activation', None)
+        oact = m.struct.out_activation
+        if oact == 2 and color_act is None:
+            mode = 1
+        elif oact == 0 and color_act is not None and str(color_act).lower() == 'sigmoid':
+            mode = 2
+        elif oact == 0 and color_act is None:
+            mode = 0
+        else:
+            return None
+        key = (features.shape[-1], n_extra, mode)
+        if self._rspec is None or self._rspec_key != key:
+            if features.shape[-1] + 16 + n_extra != 32:
+                return None
+            self._rspec, self._rspec_key = ops.RadianceSpec(*key), key
+        return self._rspec
 
     def forward(self, features, dirs, *args):
+        spec = self._fused_spec(features, dirs, args)
+        if spec is not None:
+            return ops.radiance(spec, features, dirs, args[0] if args else None, self.network.params, self.network._params_half())
         emb = self.encoding(((dirs + 1.) / 2.).reshape(-1, self.n_dir_dims))  # (-1,1) -> (0,1)
         parts = [features.reshape(-1, features.shape[-1]), emb] + [a.reshape(-1, a.shape[-1]) for a in args]
         color = self.network(torch.cat(parts, dim=-1)).reshape(*features.shape[:-1], self.n_output_dims).float()

@@ -11,6 +11,7 @@ from . import register, make
 from ..nerfacc import (ContractionType, OccupancyGrid, ray_marching, render_weight_from_density, render_weight_from_alpha,
                        accumulate_along_rays, ray_aabb_intersect)
 from .common import BaseModel, chunk_batch, update_module_step
+from .. import ops
 
 
 class VarianceNetwork(nn.Module):
@@ -47,6 +48,15 @@ class VarianceNetwork(nn.Module):
         else:
             ramp = (global_step / self.reach_max_steps) * (self.max_inv_s - self.prev_inv_s) + self.prev_inv_s
             self.mod_val = min(ramp, self.max_inv_s)
+
+
+def _long_keep_offsets(ray_indices):
+    """int64 view of the marcher's ray indices that keeps its cached segment offsets (nerfacc._offsets)."""
+    out = ray_indices.long()
+    off = getattr(ray_indices, '_nsr_offsets', None)
+    if off is not None:
+        out._nsr_offsets = off
+    return out
 
 
 def _logistic_alpha(prev_sdf, next_sdf, inv_s):
@@ -135,7 +145,7 @@ class NeuSModel(BaseModel):
             ray_indices, t_starts, t_ends = ray_marching(rays_o, rays_d, scene_aabb=scene_aabb, grid=grid, sigma_fn=sigma_fn,
                                                          near_plane=near_plane, far_plane=far_plane, render_step_size=step,
                                                          stratified=self.randomized, cone_angle=cone, alpha_thre=0.0, jitter=jitter)
-        ray_indices = ray_indices.long()
+        ray_indices = _long_keep_offsets(ray_indices)
         midpoints = (t_starts + t_ends) / 2.
         t_dirs = rays_d[ray_indices]
         density, feature = geometry(rays_o[ray_indices] + t_dirs * midpoints)
@@ -166,26 +176,40 @@ class NeuSModel(BaseModel):
                                                          grid=self.occupancy_grid if self.config.grid_prune else None, alpha_fn=None,
                                                          near_plane=None, far_plane=None, render_step_size=self.render_step_size,
                                                          stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0, jitter=jitter)
-        ray_indices = ray_indices.long()
+        ri32, ray_indices = ray_indices, _long_keep_offsets(ray_indices)
         midpoints = (t_starts + t_ends) / 2.
-        t_dirs = rays_d[ray_indices]
-        positions = rays_o[ray_indices] + t_dirs * midpoints
-        dists = t_ends - t_starts
+        if rays.is_cuda:
+            positions, t_dirs, dists = ops.sample_points(rays, ri32, t_starts, t_ends)  # one kernel instead of 2 gathers + 4 elementwise
+            dists = dists[:, None]
+        else:
+            t_dirs = rays_d[ray_indices]
+            positions = rays_o[ray_indices] + t_dirs * midpoints
+            dists = t_ends - t_starts
         fd = self.config.geometry.grad_type == 'finite_difference'
         if fd:
             sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True, with_laplace=True)
         else:
             sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
-        normal = F.normalize(sdf_grad, p=2, dim=-1)
-        alpha = self.get_alpha(sdf, normal, t_dirs, dists)[..., None]
-        rgb = self.texture(feature, t_dirs, normal)
-        weights = render_weight_from_alpha(alpha, ray_indices=ray_indices, n_rays=n_rays)
-        opacity = accumulate_along_rays(weights, ray_indices, values=None, n_rays=n_rays)
-        depth = accumulate_along_rays(weights, ray_indices, values=midpoints, n_rays=n_rays)
-        comp_rgb = accumulate_along_rays(weights, ray_indices, values=rgb, n_rays=n_rays)
-        comp_normal = F.normalize(accumulate_along_rays(weights, ray_indices, values=normal, n_rays=n_rays), p=2, dim=-1)
+        if self.config.get('fused_shading', True) and rays.is_cuda and getattr(ray_indices, '_nsr_offsets', None) is not None:
+            # one kernel each for normal + alpha, VolumeRadiance, compositing (and their backwards): csrc/neus_shade.cu, radiance.cu, render.cu
+            inv_s = self.variance.inv_s.clip(1e-6, 1e6).reshape(1)
+            alpha, normal = ops.neus_alpha(sdf, sdf_grad, inv_s, t_dirs, dists.reshape(-1), self.cos_anneal_ratio)
+            rgb = self.texture(feature, t_dirs, normal)
+            weights, opacity, depth, comp_rgb, comp_normal = ops.neus_composite(alpha, rgb, normal, t_starts, t_ends, ray_indices._nsr_offsets)
+            comp_normal = F.normalize(comp_normal, p=2, dim=-1)
+        else:
+            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            alpha = self.get_alpha(sdf, normal, t_dirs, dists)[..., None]
+            rgb = self.texture(feature, t_dirs, normal)
+            weights = render_weight_from_alpha(alpha, ray_indices=ray_indices, n_rays=n_rays)
+            opacity = accumulate_along_rays(weights, ray_indices, values=None, n_rays=n_rays)
+            depth = accumulate_along_rays(weights, ray_indices, values=midpoints, n_rays=n_rays)
+            comp_rgb = accumulate_along_rays(weights, ray_indices, values=rgb, n_rays=n_rays)
+            comp_normal = F.normalize(accumulate_along_rays(weights, ray_indices, values=normal, n_rays=n_rays), p=2, dim=-1)
+        off = getattr(ray_indices, '_nsr_offsets', None)
+        num_samples = off[-1:].to(torch.int32) if off is not None else torch.as_tensor([len(t_starts)], dtype=torch.int32, device=rays.device)
         out = {'comp_rgb': comp_rgb, 'comp_normal': comp_normal, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
-               'num_samples': torch.as_tensor([len(t_starts)], dtype=torch.int32, device=rays.device)}
+               'num_samples': num_samples}
         if self.training:
             out.update({'sdf_samples': sdf, 'sdf_grad_samples': sdf_grad, 'weights': weights.view(-1), 'points': midpoints.view(-1),
                         'intervals': dists.view(-1), 'ray_indices': ray_indices.view(-1)})

@@ -71,6 +71,7 @@ class OccupancyGrid(nn.Module):
         self._bits = None
         self._coarse = None
         self._bits_key = None
+        self._roi_host = [float(v) for v in torch.as_tensor(roi_aabb, dtype=torch.float32).flatten().tolist()]
 
     # nerfacc checkpoints also carry grid_coords / grid_indices (derivable index tables): drop them on load
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
@@ -81,6 +82,12 @@ class OccupancyGrid(nn.Module):
     @property
     def roi_aabb(self):
         return self._roi_aabb
+
+    def roi_host(self):
+        """host copy of the (constant) region of interest: no device->host read per march."""
+        if self._roi_host is None:
+            self._roi_host = self._roi_aabb.tolist()
+        return self._roi_host
 
     @property
     def binary(self):
@@ -194,7 +201,8 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
         bits = torch.ones(1, dtype=torch.int32, device=dev)
     if ctype not in (ContractionType.AABB, ContractionType.UN_BOUNDED_SPHERE):
         raise NotImplementedError(f'contraction type {ctype} not implemented')
-    ms = ops.march_struct(roi.tolist(), res, ctype.value, render_step_size, cone_angle)
+    roi_host = grid.roi_host() if grid is not None else roi.tolist()
+    ms = ops.march_struct(roi_host, res, ctype.value, render_step_size, cone_angle)
     ri, ts, te, offsets = ops.march(ms, rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), bits)
     ts, te = ts[:, None], te[:, None]
     if sigma_fn is not None or alpha_fn is not None:
@@ -206,12 +214,18 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
             else:
                 alphas = alpha_fn(ts, te, ri)
                 assert alphas.shape == ts.shape, f'alphas must have shape of (N, 1)! Got {alphas.shape}'
-            keep, _, _ = ops.visibility(alphas, offsets, early_stop_eps, alpha_thre)
+            keep, _, kept = ops.visibility(alphas, offsets, early_stop_eps, alpha_thre)
             ri, ts, te = ri[keep], ts[keep], te[keep]
+            offsets = torch.zeros_like(offsets)
+            torch.cumsum(kept, 0, out=offsets[1:])
+    ri._nsr_offsets = offsets  # int64 [N+1] segment starts: spares the callers a bincount + cumsum per compositing call
     return ri, ts, te
 
 
 def _offsets(packed_info, ray_indices, n_rays, device):
+    cached = getattr(ray_indices, '_nsr_offsets', None)
+    if cached is not None and (n_rays is None or cached.shape[0] == n_rays + 1):
+        return cached
     if ray_indices is not None:
         if n_rays is None:
             raise ValueError('n_rays must be given with ray_indices')
@@ -247,7 +261,7 @@ def accumulate_along_rays(weights, ray_indices, values=None, n_rays=None):
     d = 1 if values is None else values.shape[-1]
     if ray_indices.numel() == 0:
         return torch.zeros(n_rays, d, device=weights.device)
-    off = ops.offsets_from_ray_indices(ray_indices, n_rays)
+    off = _offsets(None, ray_indices, n_rays, weights.device)
     return ops.accumulate(weights, values, off, ray_indices)
 
 

@@ -10,7 +10,9 @@ import os
 import numpy as np
 import torch
 
-from .lib import lib, ptr, stream, check_cuda, contig, GridT, MlpT, MarchT, NSR_MAX_LEVELS
+import ctypes as _C
+
+from .lib import lib, ptr, stream, check_cuda, contig, GridT, MlpT, MarchT, RadianceT, NSR_MAX_LEVELS
 
 LOSS_SCALE = 128.0  # same constant tiny-cuda-nn uses for fp16 backward passes
 
@@ -397,15 +399,16 @@ class _NeusSDF(torch.autograd.Function):
     def backward(ctx, g_sdf, g_grad, g_feat):
         points, table_h, W1, b1, W2, b2 = ctx.saved_tensors
         n, dev, n_out = points.shape[0], points.device, ctx.n_out
-        g_out = torch.zeros(n, n_out, device=dev) if g_feat is None else contig(g_feat, torch.float32).clone()
-        if g_sdf is not None:
-            g_out[:, 0] += g_sdf.float()
-        g_grad = torch.zeros(n, 3, device=dev) if g_grad is None else contig(g_grad, torch.float32)
-        amax = torch.maximum(g_out.abs().max(), g_grad.abs().max()).reshape(1) if n > 0 else torch.ones(1, device=dev)
+        g_sdf, g_grad, g_feat = contig(g_sdf, torch.float32), contig(g_grad, torch.float32), contig(g_feat, torch.float32)
+        amax = torch.empty(1, device=dev)
+        cnt = lambda t: 0 if t is None else t.numel()
+        lib.call('nsr_absmax3', ptr(g_feat), cnt(g_feat), ptr(g_sdf), cnt(g_sdf), ptr(g_grad), cnt(g_grad), ptr(amax), stream())
         dtable = torch.zeros(ctx.spec.n_params, device=dev)
-        dW1, db1, dW2, db2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
+        sizes = [W1.numel(), b1.numel(), W2.numel(), b2.numel()]
+        flat = torch.zeros(sum(sizes), device=dev)   # one fill for the four small gradients
+        dW1, db1, dW2, db2 = [t.view_as(w) for t, w in zip(flat.split(sizes), (W1, b1, W2, b2))]
         lib.call('nsr_neus_field_bwd', ctx.spec.ref(), ptr(points), ptr(table_h), ptr(W1), ptr(b1), ptr(W2), ptr(b2), float(ctx.radius),
-                 int(n_out), ptr(g_out), ptr(g_grad), ptr(amax), ptr(dtable), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), n, stream())
+                 int(n_out), ptr(g_feat), ptr(g_sdf), ptr(g_grad), ptr(amax), ptr(dtable), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), n, stream())
         return None, None, None, None, dtable, None, dW1, db1, dW2, db2
 
 
@@ -415,3 +418,134 @@ def neus_sdf(spec, radius, points, table_f32, table_h, W1, b1, W2, b2):
     n_out = W2.shape[0]
     return _NeusSDF.apply(spec, float(radius), int(n_out), contig(points.detach(), torch.float32), table_f32, table_h,
                           contig(W1, torch.float32), contig(b1, torch.float32), contig(W2, torch.float32), contig(b2, torch.float32))
+
+
+# --------------------------------------------------------------------------------------------------
+# NeuS shading: SDF -> alpha (+ normal), compositing, fused VolumeRadiance
+# --------------------------------------------------------------------------------------------------
+class _NeusAlpha(torch.autograd.Function):
+    """(alpha [K], normal [K,3]) = get_alpha(sdf, normalize(sdf_grad), dirs, dists) (models/neus.py:117-139,225)."""
+
+    @staticmethod
+    def forward(ctx, sdf, sdf_grad, inv_s, dirs, dists, cos_anneal):
+        n = sdf.shape[0]
+        alpha = torch.empty(n, device=sdf.device)
+        normal = torch.empty(n, 3, device=sdf.device)
+        lib.call('nsr_neus_alpha_fwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), float(cos_anneal), ptr(alpha), ptr(normal),
+                 n, stream())
+        ctx.cos_anneal = float(cos_anneal)
+        ctx.save_for_backward(sdf, sdf_grad, inv_s, dirs, dists)
+        return alpha, normal
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_normal):
+        sdf, sdf_grad, inv_s, dirs, dists = ctx.saved_tensors
+        n = sdf.shape[0]
+        g_alpha = torch.zeros(n, device=sdf.device) if g_alpha is None else contig(g_alpha, torch.float32)
+        d_sdf = torch.empty(n, device=sdf.device)
+        d_grad = torch.empty(n, 3, device=sdf.device)
+        d_inv_s = torch.zeros_like(inv_s)
+        lib.call('nsr_neus_alpha_bwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), ctx.cos_anneal, ptr(g_alpha),
+                 ptr(contig(g_normal, torch.float32)), ptr(d_sdf), ptr(d_grad), ptr(d_inv_s), n, stream())
+        return d_sdf, d_grad, d_inv_s, None, None, None
+
+
+def neus_alpha(sdf, sdf_grad, inv_s, dirs, dists, cos_anneal_ratio):
+    """inv_s: 1-element CUDA tensor (already clipped); returns (alpha [K], unit normal [K,3])."""
+    check_cuda(sdf, sdf_grad, inv_s, dirs, dists, what='neus_alpha')
+    return _NeusAlpha.apply(contig(sdf.reshape(-1), torch.float32), contig(sdf_grad.reshape(-1, 3), torch.float32),
+                            contig(inv_s.reshape(1), torch.float32), contig(dirs.reshape(-1, 3), torch.float32),
+                            contig(dists.reshape(-1), torch.float32), cos_anneal_ratio)
+
+
+class _NeusComposite(torch.autograd.Function):
+    """render_weight_from_alpha + accumulate_along_rays x4 (models/neus.py:237-243) in one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, alpha, rgb, normal, t_starts, t_ends, offsets):
+        n_rays, k, dev = offsets.shape[0] - 1, alpha.shape[0], alpha.device
+        weights, trans = torch.empty(k, device=dev), torch.empty(k, device=dev)
+        opacity, depth = torch.empty(n_rays, 1, device=dev), torch.empty(n_rays, 1, device=dev)
+        comp_rgb, comp_normal = torch.empty(n_rays, 3, device=dev), torch.empty(n_rays, 3, device=dev)
+        lib.call('nsr_neus_composite_fwd', ptr(alpha), ptr(rgb), ptr(normal), ptr(t_starts), ptr(t_ends), ptr(offsets), ptr(weights),
+                 ptr(trans), ptr(opacity), ptr(depth), ptr(comp_rgb), ptr(comp_normal), n_rays, stream())
+        ctx.save_for_backward(alpha, rgb, normal, t_starts, t_ends, offsets, weights, trans)
+        ctx.mark_non_differentiable(trans)
+        return weights, opacity, depth, comp_rgb, comp_normal, trans
+
+    @staticmethod
+    def backward(ctx, g_w, g_op, g_depth, g_rgb, g_nrm, _g_trans):
+        alpha, rgb, normal, t_starts, t_ends, offsets, weights, trans = ctx.saved_tensors
+        k, dev = alpha.shape[0], alpha.device
+        d_alpha, d_rgb, d_normal = torch.empty(k, device=dev), torch.empty(k, 3, device=dev), torch.empty(k, 3, device=dev)
+        f = lambda g: None if g is None else contig(g, torch.float32)
+        lib.call('nsr_neus_composite_bwd', ptr(alpha), ptr(rgb), ptr(normal), ptr(t_starts), ptr(t_ends), ptr(weights), ptr(trans),
+                 ptr(offsets), ptr(f(g_w)), ptr(f(g_op)), ptr(f(g_depth)), ptr(f(g_rgb)), ptr(f(g_nrm)), ptr(d_alpha), ptr(d_rgb),
+                 ptr(d_normal), offsets.shape[0] - 1, stream())
+        return d_alpha, d_rgb, d_normal, None, None, None
+
+
+def neus_composite(alpha, rgb, normal, t_starts, t_ends, offsets):
+    """-> weights [K], opacity [N,1], depth [N,1], comp_rgb [N,3], comp_normal [N,3] (un-normalised weighted sum)."""
+    check_cuda(alpha, rgb, normal, what='neus_composite')
+    c = lambda t, s: contig(t.reshape(*s), torch.float32)
+    out = _NeusComposite.apply(c(alpha, (-1,)), c(rgb, (-1, 3)), c(normal, (-1, 3)), c(t_starts, (-1,)), c(t_ends, (-1,)), offsets)
+    return out[:5]
+
+
+class RadianceSpec:
+    """descriptor of the fused VolumeRadiance kernel (nsr_radiance_t)."""
+
+    def __init__(self, n_feat, n_extra, act_mode):
+        if n_feat + 16 + n_extra != 32:
+            raise NotImplementedError(f'fused radiance: feature ({n_feat}) + SH4 (16) + extra ({n_extra}) must be 32 wide')
+        self.n_feat, self.n_extra, self.act_mode = int(n_feat), int(n_extra), int(act_mode)
+        self._t = RadianceT(self.n_feat, self.n_extra, self.act_mode)
+
+    def ref(self):
+        return _C.byref(self._t)
+
+
+class _Radiance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, feat, dirs, extra, params_f32, params_h):
+        n = feat.shape[0]
+        rgb = torch.empty(n, 3, device=feat.device)
+        lib.call('nsr_radiance_fwd', spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(params_h), ptr(rgb), n, stream())
+        ctx.spec = spec
+        ctx.save_for_backward(feat, dirs, extra, params_h)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        feat, dirs, extra, params_h = ctx.saved_tensors
+        n, dev = feat.shape[0], feat.device
+        g_rgb = contig(g_rgb, torch.float32)
+        amax = g_rgb.abs().amax().reshape(1) if n > 0 else torch.ones(1, device=dev)
+        d_feat = torch.empty_like(feat) if ctx.needs_input_grad[1] else None
+        d_extra = torch.empty_like(extra) if (extra is not None and ctx.needs_input_grad[3]) else None
+        gp = torch.zeros(params_h.shape[0], device=dev)
+        lib.call('nsr_radiance_bwd', ctx.spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(params_h), ptr(g_rgb), 0.0, ptr(amax), ptr(d_feat),
+                 ptr(d_extra), ptr(gp), n, stream())
+        return None, d_feat, None, d_extra, gp, None
+
+
+def radiance(spec, feat, dirs, extra, params_f32, params_h):
+    """cat[feat | SH4(dirs) | extra] -> FullyFused 32->64->64->3 (+ activation per spec.act_mode); fp32 rgb [n,3]."""
+    check_cuda(feat, dirs, extra, params_h, what='VolumeRadiance (fused)')
+    if params_h.shape[0] != 64 * 32 + 64 * 64 + 16 * 64:
+        raise RuntimeError('fused radiance: expected the 7168 parameters of a 32->64->64->3 FullyFusedMLP')
+    return _Radiance.apply(spec, contig(feat.reshape(-1, spec.n_feat), torch.float32), contig(dirs.reshape(-1, 3), torch.float32),
+                           None if extra is None else contig(extra.reshape(-1, spec.n_extra), torch.float32), params_f32, params_h)
+
+
+def sample_points(rays, ray_indices, t_starts, t_ends):
+    """-> positions [K,3], dirs [K,3], dists [K] of the marched samples (no gradient: rays and t come from the no-grad marcher)."""
+    check_cuda(rays, ray_indices, t_starts, t_ends, what='sample_points')
+    rays = contig(rays.detach(), torch.float32)
+    ri = contig(ray_indices, torch.int32)
+    ts, te = contig(t_starts.detach().reshape(-1), torch.float32), contig(t_ends.detach().reshape(-1), torch.float32)
+    k = ri.shape[0]
+    pos, dirs, dists = torch.empty(k, 3, device=rays.device), torch.empty(k, 3, device=rays.device), torch.empty(k, device=rays.device)
+    lib.call('nsr_sample_points', ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(pos), ptr(dirs), ptr(dists), k, stream())
+    return pos, dirs, dists

@@ -273,3 +273,23 @@ def test_neus_field_manual_formulas_match_autograd():
     gm = neus_field.backward(cache, table.detach(), lt, W1.detach(), b1.detach(), W2.detach(), b2.detach(), r, g_out, g_grad)
     for name, ref in (('W1', W1.grad), ('b1', b1.grad), ('W2', W2.grad), ('b2', b2.grad), ('table', table.grad)):
         np.testing.assert_allclose(gm[name].numpy(), ref.numpy(), rtol=1e-7, atol=1e-9, err_msg=name)
+
+
+def test_adamw_oracle_matches_torch():
+    """the reference's optimizer is torch.optim.AdamW itself (systems/utils.py:314-325): pin the restatement against it"""
+    from oracle import optim
+    torch.manual_seed(0)
+    p0 = torch.randn(4099) * 0.1
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pt], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    p, m, v = p0.numpy().copy(), np.zeros(4099, np.float32), np.zeros(4099, np.float32)
+    for step in range(1, 8):
+        g = torch.randn(4099) * (10.0 ** -(step % 4))
+        g[::7] = 0.0
+        pt.grad = g.clone()
+        opt.step()
+        optim.adamw_step(p, g.numpy().copy(), m, v, step)
+        np.testing.assert_allclose(p, pt.detach().numpy(), rtol=2e-6, atol=2e-8)
+    st = opt.state[pt]
+    np.testing.assert_allclose(m, st['exp_avg'].numpy(), rtol=2e-6, atol=1e-7 * float(np.abs(m).max()))  # lerp cancellation near 0
+    np.testing.assert_allclose(v, st['exp_avg_sq'].numpy(), rtol=2e-6, atol=1e-7 * float(v.max()))
