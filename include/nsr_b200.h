@@ -285,6 +285,21 @@ int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* di
                      const void* params_h, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
                      float* grad_params, int64_t n, void* stream);
 
+/* ---- occupancy-grid refresh (nerfacc OccupancyGrid._update behind every_n_step: models/nerf.py:45-55,
+ * models/neus.py:79-111).  The caller draws the cells (int64 flat indices ix*R*R + iy*R + iz; NULL = every cell once) and the
+ * in-cell jitter U[0,1)^3, evaluates its occ function on the returned world points, then:
+ *   update:   occs[cell] = max(occs[cell] * ema_decay, occ)   (duplicates: max of their values), partial = per-block sums of occs
+ *             scratch: f32 [n_cells] work grid (sparse updates only); partial: f64 [1024]
+ *   binarize: binary (u8 [n_cells], may be NULL) = occs > min(mean(occs), occ_thre); bits = packed bitfield (bit idx&31 of word
+ *             idx>>5), coarse_bits (may be NULL; res % 4 == 0) = "any bit in the 4^3 block" over (res/4)^3 cells.
+ * p: only roi, res and contraction (0 AABB, 2 UN_BOUNDED_SPHERE: valid[i] = 0 outside the unit ball) are read. */
+int nsr_occgrid_points(const nsr_march_t* p, const int64_t* cells, const float* jitter, float* x_world, uint8_t* valid, int64_t n,
+                       void* stream);
+int nsr_occgrid_update(float* occs, const int64_t* cells, const float* occ, float* scratch, float ema_decay, double* partial, int64_t n,
+                       int64_t n_cells, void* stream);
+int nsr_occgrid_binarize(const float* occs, const double* partial, float occ_thre, uint8_t* binary, uint32_t* bits, uint32_t* coarse_bits,
+                         int32_t res, int64_t n_cells, void* stream);
+
 /* ---- optimizer (systems/utils.py:314-325) ------------------------------------------------------------------------
  * One fused pass of torch.optim.AdamW over a flat fp32 vector: un-scale, skip on *found_inf != 0, decoupled weight decay, moments,
  * update, and (params_half != NULL) the fp16 copy the kernels read.  dev_lr_step (device float[2] = {lr, step}, or NULL)

@@ -6,6 +6,7 @@
 // parameter.  Arithmetic follows torch's single-tensor AdamW step by step (lerp for exp_avg, sqrt(v)/sqrt(bc2) + eps).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -27,6 +28,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p -= c.step_size * (m / denom);
 }
 
+// U float4 groups per thread per iteration (all loads issued before the first use), grid-stride over U * blockDim chunks.
+template <int U>
 __global__ void __launch_bounds__(256) adamw_kernel(AdamConsts c, float* __restrict__ params, const float* __restrict__ grads,
                                                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                     __half* __restrict__ params_half, const float* __restrict__ dev_lr_step,
@@ -39,24 +42,37 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamConsts c, float* __restr
     c.bc2_sqrt = sqrtf(1.f - powf(c.beta2, t));
   }
   const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 p = reinterpret_cast<float4*>(params)[i];
-    const float4 g = __ldcs(reinterpret_cast<const float4*>(grads) + i);
-    float4 m = reinterpret_cast<float4*>(exp_avg)[i];
-    float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
-    adam_one(p.x, g.x, m.x, v.x, c);
-    adam_one(p.y, g.y, m.y, v.y, c);
-    adam_one(p.z, g.z, m.z, v.z, c);
-    adam_one(p.w, g.w, m.w, v.w, c);
-    reinterpret_cast<float4*>(params)[i] = p;
-    __stcs(reinterpret_cast<float4*>(exp_avg) + i, m);
-    __stcs(reinterpret_cast<float4*>(exp_avg_sq) + i, v);
-    if (params_half != nullptr) {
-      uint2 h;
-      h.x = nsr_pack_h2(p.x, p.y);
-      h.y = nsr_pack_h2(p.z, p.w);
-      reinterpret_cast<uint2*>(params_half)[i] = h;
+  const int64_t chunk = (int64_t)blockDim.x * U;
+  for (int64_t base = blockIdx.x * chunk; base < n4; base += (int64_t)gridDim.x * chunk) {
+    float4 p[U], g[U], m[U], v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * blockDim.x + threadIdx.x;
+      if (i < n4) {
+        p[u] = reinterpret_cast<float4*>(params)[i];
+        g[u] = __ldcs(reinterpret_cast<const float4*>(grads) + i);
+        m[u] = __ldcs(reinterpret_cast<float4*>(exp_avg) + i);
+        v[u] = __ldcs(reinterpret_cast<float4*>(exp_avg_sq) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * blockDim.x + threadIdx.x;
+      if (i < n4) {
+        adam_one(p[u].x, g[u].x, m[u].x, v[u].x, c);
+        adam_one(p[u].y, g[u].y, m[u].y, v[u].y, c);
+        adam_one(p[u].z, g[u].z, m[u].z, v[u].z, c);
+        adam_one(p[u].w, g[u].w, m[u].w, v[u].w, c);
+        reinterpret_cast<float4*>(params)[i] = p[u];
+        __stcs(reinterpret_cast<float4*>(exp_avg) + i, m[u]);
+        __stcs(reinterpret_cast<float4*>(exp_avg_sq) + i, v[u]);
+        if (params_half != nullptr) {
+          uint2 h;
+          h.x = nsr_pack_h2(p[u].x, p[u].y);
+          h.y = nsr_pack_h2(p[u].z, p[u].w);
+          reinterpret_cast<uint2*>(params_half)[i] = h;
+        }
+      }
     }
   }
   // tail (n not a multiple of 4)
@@ -114,8 +130,24 @@ extern "C" int nsr_adamw_step(const nsr_adamw_t* h, float* params, const float* 
   c.inv_scale = h->inv_grad_scale;
   c.lr = h->lr;
   c.weight_decay = h->weight_decay;
-  adamw_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(c, params, grads, exp_avg, exp_avg_sq, (__half*)params_half,
-                                                                       dev_lr_step, found_inf, n);
+  // launch shape: NSR_ADAMW_VARIANT = "<unroll 1|2|4>,<ctas per SM, 0 = one CTA per chunk>" (development knob; default tuned on B200)
+  static int unroll = 2, ctas_per_sm = 0;
+  static bool read_env = false;
+  if (!read_env) {
+    if (const char* e = getenv("NSR_ADAMW_VARIANT")) sscanf(e, "%d,%d", &unroll, &ctas_per_sm);
+    read_env = true;
+  }
+  const int64_t n4 = n >> 2;
+  const int u = unroll == 4 ? 4 : (unroll == 1 ? 1 : 2);
+  const int64_t chunks = max((int64_t)1, (n4 + 256 * u - 1) / (256 * u));
+  const int grid = (int)(ctas_per_sm > 0 ? min(chunks, (int64_t)nsr_sm_count() * ctas_per_sm) : chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (u == 1)
+    adamw_kernel<1><<<grid, 256, 0, st>>>(c, params, grads, exp_avg, exp_avg_sq, (__half*)params_half, dev_lr_step, found_inf, n);
+  else if (u == 2)
+    adamw_kernel<2><<<grid, 256, 0, st>>>(c, params, grads, exp_avg, exp_avg_sq, (__half*)params_half, dev_lr_step, found_inf, n);
+  else
+    adamw_kernel<4><<<grid, 256, 0, st>>>(c, params, grads, exp_avg, exp_avg_sq, (__half*)params_half, dev_lr_step, found_inf, n);
   NSR_CHECK_LAUNCH("nsr_adamw_step");
   return 0;
 }

@@ -282,8 +282,8 @@ int check_desc(const nsr_radiance_t* p, const char* who) {
 extern "C" int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, const float* dirs,
                                 const float* extra, const void* params_h, float* rgb, int64_t n, void* stream) {
   if (check_desc(p, "nsr_radiance_fwd")) return 1;
-  NSR_REQUIRE(p->n_extra == 0 || extra != nullptr, "nsr_radiance_fwd: extra input is NULL");
   if (n == 0) return 0;
+  NSR_REQUIRE(p->n_extra == 0 || extra != nullptr, "nsr_radiance_fwd: extra input is NULL");
   static thread_local bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(radiance_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
@@ -301,6 +301,7 @@ extern "C" int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, cons
                                 const float* extra, const void* params_h, const float* d_rgb, float loss_scale, const float* amax,
                                 float* d_feat, float* d_extra, float* grad_params, int64_t n, void* stream) {
   if (check_desc(p, "nsr_radiance_bwd")) return 1;
+  if (n == 0) return 0;
   NSR_REQUIRE(p->n_extra == 0 || extra != nullptr, "nsr_radiance_bwd: extra input is NULL");
   NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_radiance_bwd: loss_scale <= 0 (automatic) needs the amax pointer");
   NSR_REQUIRE(grad_params != nullptr, "nsr_radiance_bwd: grad_params is NULL");

@@ -96,6 +96,9 @@ _SIGNATURES = {
     'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P],
     'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P],
+    'nsr_occgrid_points': [P, P, P, P, P, I64, P],
+    'nsr_occgrid_update': [P, P, P, P, F32, P, I64, I64, P],
+    'nsr_occgrid_binarize': [P, P, F32, P, P, P, I32, I64, P],
     'nsr_adamw_step': [P, P, P, P, P, P, P, P, I64, P],
     'nsr_grad_nonfinite': [P, P, I64, P],
     'nsr_nerf_loss_fwd': [P, P, P, P, P, P, I64, P],

@@ -71,6 +71,7 @@ class OccupancyGrid(nn.Module):
         self._bits = None
         self._coarse = None
         self._bits_key = None
+        self._work = None
         self._roi_host = [float(v) for v in torch.as_tensor(roi_aabb, dtype=torch.float32).flatten().tolist()]
 
     # nerfacc checkpoints also carry grid_coords / grid_indices (derivable index tables): drop them on load
@@ -127,6 +128,10 @@ class OccupancyGrid(nn.Module):
 
     @torch.no_grad()
     def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256):
+        """nerfacc OccupancyGrid._update.  CUDA grids run the three refresh kernels of csrc/occgrid.cu (points, EMA-max
+        update with deterministic duplicate handling, threshold + bit packing); the torch path below is the same rule for CPU grids."""
+        if self.occs.is_cuda:
+            return self._update_cuda(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps)
         dev = self.occs.device
         R = self._res
         if step < warmup_steps:
@@ -143,6 +148,41 @@ class OccupancyGrid(nn.Module):
         self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
         self._binary = (self.occs > torch.clamp(self.occs.mean(), max=occ_thre)).view(R, R, R)
         self._bits_key = None
+
+    def _update_cuda(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, cells=None, jitter=None):
+        """``cells`` / ``jitter`` (our extension) fix the random draws so tests can compare with the oracle."""
+        from .lib import lib, ptr, stream
+        dev, R, C = self.occs.device, self._res, self.num_cells
+        if cells is None and step >= warmup_steps:
+            cells = self._sample_uniform_and_occupied_cells(C // 4)
+        n = C if cells is None else cells.shape[0]
+        if jitter is None:
+            jitter = torch.rand(n, 3, device=dev)
+        ms = ops.march_struct(self.roi_host(), R, self._contraction_type.value, 1.0, 0.0)
+        import ctypes
+        x = torch.empty(n, 3, device=dev)
+        sphere = self._contraction_type == ContractionType.UN_BOUNDED_SPHERE
+        valid = torch.empty(n, dtype=torch.uint8, device=dev) if sphere else None
+        lib.call('nsr_occgrid_points', ctypes.byref(ms), ptr(cells), ptr(contig(jitter, torch.float32)), ptr(x), ptr(valid), n, stream())
+        if sphere:  # the reference evaluates only the points inside the unit ball
+            keep = valid.bool()
+            x = x[keep]
+            cells = (torch.arange(C, device=dev) if cells is None else cells)[keep]
+            n = x.shape[0]
+        occ = contig(occ_eval_fn(x).reshape(-1), torch.float32)
+        if self._work is None or self._work[0].device != dev:
+            self._work = (torch.empty(C, device=dev), torch.empty(1024, dtype=torch.float64, device=dev))
+        scratch, partial = self._work
+        lib.call('nsr_occgrid_update', ptr(self.occs), ptr(cells), ptr(occ), ptr(scratch), float(ema_decay), ptr(partial), n, C, stream())
+        binary = torch.empty(C, dtype=torch.uint8, device=dev)
+        bits = torch.empty((C + 31) // 32, dtype=torch.int32, device=dev)
+        coarse = None
+        if R % 4 == 0 and R <= 128:
+            coarse = torch.empty(((R // 4) ** 3 + 31) // 32, dtype=torch.int32, device=dev)
+        lib.call('nsr_occgrid_binarize', ptr(self.occs), ptr(partial), float(occ_thre), ptr(binary), ptr(bits), ptr(coarse), R, C, stream())
+        self._binary = binary.view(torch.bool).view(R, R, R)
+        self._bits, self._coarse = bits, coarse
+        self._bits_key = (self._binary._version, self._binary.data_ptr())   # packed by the kernel: bits() must not re-pack
 
     @torch.no_grad()
     def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):

@@ -201,3 +201,52 @@ def test_fused_adamw_skip_on_found_inf_and_capturable_mode():
         oc.step()
         oh.step()
     np.testing.assert_allclose(q.detach().cpu().numpy(), r.detach().cpu().numpy(), rtol=5e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize('ctype_name,R', [('AABB', 32), ('UN_BOUNDED_SPHERE', 24)])
+def test_occupancy_refresh_kernels_match_oracle(ctype_name, R):
+    """csrc/occgrid.cu (points -> EMA-max update -> threshold + packed bitfield + coarse field) vs oracle/occgrid.py on the same
+    cells and jitter: occupancy values within 1e-5 relative (fma contraction of the point transform), binary equal away from
+    threshold ties, bit packing exact."""
+    from oracle import occgrid as oocc, contraction as ocon
+    from nsr_b200 import nerfacc
+    ctype = getattr(nerfacc.ContractionType, ctype_name)
+    radius = 1.5
+    aabb = torch.tensor([-radius] * 3 + [radius] * 3)
+    grid = nerfacc.OccupancyGrid(aabb, R, ctype).to(D)
+    grid.train()
+    C = R ** 3
+    g = torch.Generator().manual_seed(7)
+    occs0 = torch.rand(C, generator=g) * 0.02
+    grid.occs.copy_(occs0)
+    fn = lambda x: (torch.exp(-4.0 * x.norm(dim=-1, keepdim=True)) * 0.05).float()
+    # sparse update with unique cells (exact comparison) ...
+    cells = torch.randperm(C, generator=g)[:C // 4]
+    jitter = torch.rand(cells.shape[0], 3, generator=g)
+    grid._update_cuda(512, fn, 0.01, 0.95, 256, cells=cells.to(D), jitter=jitter.to(D))
+    want_occs, want_bin = oocc.update(occs0.clone(), cells, jitter, fn, radius, ctype.value, R, ema_decay=0.95, occ_thre=0.01)
+    got = grid.occs.cpu()
+    assert float((got - want_occs).abs().max()) <= 1e-5 * float(want_occs.abs().max())
+    thr = min(float(want_occs.mean()), 0.01)
+    tie = (want_occs - thr).abs() < 1e-4 * thr
+    assert bool(((grid.binary.cpu().view(-1) == want_bin.view(-1)) | tie).all()) and int(tie.sum()) < 10
+    # ... the packed bitfield and the coarse "any bit in 4^3" field come out of the same kernel
+    bits = grid.bits().cpu().numpy().view(np.uint32)
+    assert np.array_equal(bits, oocc.pack_bits(grid.binary.cpu().numpy()))
+    if R % 4 == 0:
+        b = grid.binary.cpu().view(R // 4, 4, R // 4, 4, R // 4, 4).any(dim=5).any(dim=3).any(dim=1)
+        assert np.array_equal(grid.coarse_bits().cpu().numpy().view(np.uint32), oocc.pack_bits(b.numpy()))
+    # duplicates: the maximum of the duplicated samples wins, deterministically
+    grid.occs.copy_(occs0)
+    dup = torch.cat([cells[:100], cells[:100]])
+    j2 = torch.rand(200, 3, generator=g)
+    grid._update_cuda(512, fn, 0.01, 0.95, 256, cells=dup.to(D), jitter=j2.to(D))
+    a, _ = oocc.update(occs0.clone(), dup[:100], j2[:100], fn, radius, ctype.value, R)
+    b, _ = oocc.update(occs0.clone(), dup[100:], j2[100:], fn, radius, ctype.value, R)
+    assert float((grid.occs.cpu() - torch.maximum(a, b)).abs().max()) <= 1e-5 * float(a.abs().max())
+    # dense (warm-up) update through the public entry point: every cell once
+    grid.occs.zero_()
+    torch.manual_seed(3)
+    grid.every_n_step(step=0, occ_eval_fn=fn, occ_thre=0.01)
+    inside = grid.occs > 0
+    assert inside.any() and (ctype_name == 'AABB') == bool(inside.all())   # sphere: cells outside the unit ball are never touched
