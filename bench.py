@@ -361,21 +361,29 @@ def gpu_arm(args):
                 p.grad = torch.zeros_like(p)
         for _ in range(3):
             opt.step()
-        evs = []
+        lib.profile = {}   # CUDA events around every C-ABI call: the kernel's own duration, not Python's launch pace
         for i in range(20):
             flush.fill_(float(i))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             opt.step()
-            e1.record()
-            evs.append((e0, e1))
         torch.cuda.synchronize()
-        opt_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        n_calls = len(lib.profile['nsr_adamw_step']) // 20   # one launch per parameter tensor
+        per_step = [sum(a.elapsed_time(b) for a, b in lib.profile['nsr_adamw_step'][j * n_calls:(j + 1) * n_calls]) for j in range(20)]
+        lib.profile = None
+        opt_ms = sum(per_step) / len(per_step)
         n_par = sum(p.numel() for p in params)
         opt_bytes = 30.0 * n_par   # p, g, m, v read (16 B) + p, m, v written (12 B) + fp16 copy written (2 B)
         adamw = {'kernel': 'adamw_kernel (nsr_adamw_step)', 'params': n_par, 'ms': opt_ms, 'algorithmic_bytes': opt_bytes,
                  'achieved_GBps': opt_bytes / (opt_ms * 1e-3) / 1e9, 'frac_of_hbm_peak': opt_bytes / (opt_ms * 1e-3) / 1e9 / peak,
                  'train_step_ms_with_optimizer': ms_step + opt_ms}
+    if roofline is not None and dom == 'nsr_nerf_field_bwd':
+        # the table (25 MB fp16) and its gradient (50 MB fp32) live in the 126 MB L2: the kernel's real ceiling is the L2 atomic unit.
+        # 79.2 REDs (8-byte red.global.add.v2.f32) per kept sample after run merging = ncu l1tex RED sectors / K
+        # (profiles/r1_ncu_fused_kernels_final.md); 140 G RED/s = scatter-only micro-benchmark at full occupancy
+        # (profiles/r1_gather_scatter_microbench.md).
+        reds = 79.2 * k1
+        roofline['secondary'] = {'bound': 'l2_red', 'unit': 'G RED/s', 'achieved': reds / (kern[dom]['ms'] * 1e-3) / 1e9, 'peak': 140.0,
+                                 'frac': reds / (kern[dom]['ms'] * 1e-3) / 1e9 / 140.0,
+                                 'source': 'REDs/sample from ncu (profiles/r1_ncu_fused_kernels_final.md); peak = measured scatter-only floor'}
     cpu = time_cpu(2, 1, n_rays=512) if world == 1 else None
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',

@@ -89,6 +89,12 @@ typedef struct {
   float inv_grad_scale;
 } nsr_adamw_t;
 
+/* weights of the NeuS training losses (systems/neus.py:98-121; configs/neus-blender.yaml:80-89) */
+typedef struct {
+  float lambda_rgb_mse, lambda_rgb_l1, lambda_eikonal, lambda_mask, lambda_opaque, lambda_sparsity, sparsity_scale;
+} nsr_neus_loss_t;
+
+
 
 const char* nsr_last_error(void);
 int nsr_version(void);
@@ -317,6 +323,17 @@ int nsr_nerf_loss_fwd(const float* acc_rgb, const float* opacity, const float* b
                       int64_t n_rays, void* stream);
 int nsr_nerf_loss_bwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, const float* accum2,
                       const float* g_loss, float* g_acc_rgb, float* g_opacity, int64_t n_rays, void* stream);
+/* NeuS losses (systems/neus.py:98-121): comp_rgb [N,3] (= comp_rgb_full), valid u8 [N] (= rays_valid_full), target [N,3],
+ * opacity [N], fg_mask f32 [N] (NULL: no mask loss), sdf_grad [K,3] (eikonal; NULL skips), sdf [K] (sparsity; NULL skips).
+ * fwd: accum8 = device float[8] work (zeroed here), losses7 = {rgb_mse, rgb_l1, eikonal, mask, opaque, sparsity, weighted total};
+ * the rgb means run over the valid rays (denominator clamped to >= 1).  bwd: d total / d inputs times *g_loss (NULL = 1);
+ * g_sdf_grad / g_sdf may be NULL. */
+int nsr_neus_loss_fwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target, const float* opacity,
+                      const float* fg_mask, const float* sdf_grad, const float* sdf, float* accum8, float* losses7, int64_t n_rays,
+                      int64_t k, void* stream);
+int nsr_neus_loss_bwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target, const float* opacity,
+                      const float* fg_mask, const float* sdf_grad, const float* sdf, const float* accum8, const float* g_loss,
+                      float* g_comp_rgb, float* g_opacity, float* g_sdf_grad, float* g_sdf, int64_t n_rays, int64_t k, void* stream);
 /* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
 int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
                    void* stream);

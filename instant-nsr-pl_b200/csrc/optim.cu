@@ -130,15 +130,15 @@ extern "C" int nsr_adamw_step(const nsr_adamw_t* h, float* params, const float* 
   c.inv_scale = h->inv_grad_scale;
   c.lr = h->lr;
   c.weight_decay = h->weight_decay;
-  // launch shape: NSR_ADAMW_VARIANT = "<unroll 1|2|4>,<ctas per SM, 0 = one CTA per chunk>" (development knob; default tuned on B200)
-  static int unroll = 2, ctas_per_sm = 0;
+  // launch shape: NSR_ADAMW_VARIANT = "<unroll 1|2|4>,<ctas per SM, 0 = one CTA per chunk>" (development knob; default = the fastest of tools/adamw_bench.py's sweep on B200: 5.86 TB/s)
+  static int unroll = 1, ctas_per_sm = 0;
   static bool read_env = false;
   if (!read_env) {
     if (const char* e = getenv("NSR_ADAMW_VARIANT")) sscanf(e, "%d,%d", &unroll, &ctas_per_sm);
     read_env = true;
   }
   const int64_t n4 = n >> 2;
-  const int u = unroll == 4 ? 4 : (unroll == 1 ? 1 : 2);
+  const int u = unroll == 4 ? 4 : (unroll == 2 ? 2 : 1);
   const int64_t chunks = max((int64_t)1, (n4 + 256 * u - 1) / (256 * u));
   const int grid = (int)(ctas_per_sm > 0 ? min(chunks, (int64_t)nsr_sm_count() * ctas_per_sm) : chunks);
   cudaStream_t st = (cudaStream_t)stream;

@@ -54,6 +54,12 @@ class AdamWT(C.Structure):
                 ('step', C.c_int32), ('inv_grad_scale', C.c_float)]
 
 
+class NeusLossT(C.Structure):
+    """nsr_neus_loss_t: lambdas of systems/neus.py:98-121."""
+    _fields_ = [(k, C.c_float) for k in ('lambda_rgb_mse', 'lambda_rgb_l1', 'lambda_eikonal', 'lambda_mask', 'lambda_opaque',
+                                         'lambda_sparsity', 'sparsity_scale')]
+
+
 P, I64, F32, I32 = C.c_void_p, C.c_int64, C.c_float, C.c_int32
 
 # name -> argtypes (all return int)
@@ -103,6 +109,8 @@ _SIGNATURES = {
     'nsr_grad_nonfinite': [P, P, I64, P],
     'nsr_nerf_loss_fwd': [P, P, P, P, P, P, I64, P],
     'nsr_nerf_loss_bwd': [P, P, P, P, P, P, P, P, I64, P],
+    'nsr_neus_loss_fwd': [P, P, P, P, P, P, P, P, P, P, I64, I64, P],
+    'nsr_neus_loss_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],
     'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P, P],
     'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],

@@ -28,18 +28,25 @@ def build(cfg_fn, n_rays):
     return m, torch.from_numpy(rays).to(D)
 
 
+FUSED_LOSS = os.environ.get('NEUS_FUSED_LOSS', '1') == '1'
+
+
 def step(m, rays, target, mask):
     out = m(rays)
-    v = out['rays_valid_full'][..., 0].float()[:, None]
-    l_rgb = ((out['comp_rgb_full'] - target) ** 2 * v).sum() / (v.sum() * 3).clamp(min=1)
-    l_eik = ((torch.linalg.norm(out['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
-    op = torch.clamp(out['opacity'].squeeze(-1), 1e-3, 1 - 1e-3)
-    l_mask = F.binary_cross_entropy(op, mask)
-    loss = 10. * l_rgb + 0.1 * l_eik + 0.1 * l_mask
+    if FUSED_LOSS:   # nsr_b200.losses.neus_losses: systems/neus.py:98-121 as two kernels
+        from nsr_b200.losses import neus_losses
+        loss, _ = neus_losses(out, target, mask, lambda_rgb_mse=10., lambda_eikonal=0.1, lambda_mask=0.1)
+    else:
+        v = out['rays_valid_full'][..., 0].float()[:, None]
+        l_rgb = ((out['comp_rgb_full'] - target) ** 2 * v).sum() / (v.sum() * 3).clamp(min=1)
+        l_eik = ((torch.linalg.norm(out['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+        op = torch.clamp(out['opacity'].squeeze(-1), 1e-3, 1 - 1e-3)
+        l_mask = F.binary_cross_entropy(op, mask)
+        loss = 10. * l_rgb + 0.1 * l_eik + 0.1 * l_mask
     for p in m.parameters():
         p.grad = None
     loss.backward()
-    return int(out['num_samples_full'].sum())
+    return out['num_samples_full']
 
 
 res = {}
@@ -63,6 +70,7 @@ for name, fn, n in (('C3 neus-blender', configs.neus_blender, 8192), ('C4 neus-d
     kern = {kname: round(sum(a.elapsed_time(b) for a, b in v) / 5, 3) for kname, v in lib.profile.items()}
     lib.profile = None
     res[name + ' kernels_ms_per_step'] = kern
+    k = int(k.sum())
     res[name] = {'rays': n, 'samples': k, 'ms_per_step': round(ms, 3), 'rays_per_s': round(n / ms * 1e3), 'samples_per_s': round(k / ms * 1e3)}
     del m
     torch.cuda.empty_cache()
