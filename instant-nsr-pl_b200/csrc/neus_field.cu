@@ -169,8 +169,7 @@ constexpr int TT_US = TT_H + NH * LDT;        // [64] ub * s     (scaled)
 constexpr int TT_QB = TT_US + NH * LDT;       // [48] qb         (scaled)
 constexpr int TT_E = TT_QB + 48 * LDT;        // [48] e          (unscaled)
 constexpr int TT_GO = TT_E + 48 * LDT;        // [16] g_out      (scaled)
-constexpr int TT_ONE = TT_GO + 16 * LDT;      // [16] row 0 = 1  (unscaled)
-constexpr int TT_TOTAL = TT_ONE + 16 * LDT;
+constexpr int TT_TOTAL = TT_GO + 16 * LDT;    // 368 rows x 272 B + weights = 113.7 KB => two CTAs per SM
 constexpr size_t kBwdSmem = sizeof(NeusW) + (size_t)TT_TOTAL * sizeof(__half);
 
 // acc[1][2] (16 x 16 output block) += A^T-tile rows m0..m0+15 (x 128 samples) * B-tile rows n0..n0+15
@@ -180,7 +179,7 @@ __device__ __forceinline__ void wgrad_block(float (&acc)[1][2][4], const __half*
   nsr_gemm_w<1, 8, 2>(acc, a, Bt + (size_t)n0 * LDT, LDT);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
+__global__ void __launch_bounds__(kThreads, 2) neus_field_bwd_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
                                                                      const __half2* __restrict__ table, const float* __restrict__ W1,
                                                                      const float* __restrict__ b1, const float* __restrict__ W2,
                                                                      const float* __restrict__ b2, float radius, int n_out,
@@ -194,14 +193,15 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
   __half* T = reinterpret_cast<__half*>(smem_raw + sizeof(NeusW));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, cq = lane & 3;
   stage_neus_weights(w, W1, b1, W2, b2, n_out);
-  for (int i = tid; i < 16 * LDT; i += kThreads) T[TT_ONE + i] = __float2half(i < kThreads ? 1.f : 0.f);  // row 0 = ones
   const float amax = fmaxf(amax_ptr ? __ldg(amax_ptr) : 1.f, 1e-30f);
   const float scale = exp2f(fminf(fmaxf(floorf(log2f(4.f / amax)), -24.f), 40.f));
   const float inv_scale = 1.f / scale, inv2r = 1.f / (2.f * radius);
   __syncthreads();
 
-  // weight-gradient accumulators: dW1 [64 x 48] = 12 blocks, dW2 [16 x 64] = 4, db1 [64 x 16] = 4, db2 [16 x 16] = 1  => 21 / 4 warps
-  constexpr int kBlocks = 21, kSlots = 6;
+  // weight-gradient accumulators: dW1 [64 x 48] = 12 blocks + dW2 [16 x 64] = 4 blocks => 4 per warp, on tensor cores;
+  // the three "times a vector of ones" products (db1 = sum_s zb, db2 = sum_s g_out, dW2[0] += sum_s ub s) are row sums of the
+  // transposed tiles: thread t owns row t of [ZB (64) | US (64)], threads 0..15 additionally row t of GO.
+  constexpr int kBlocks = 16, kSlots = 4;
   float wacc[kSlots][1][2][4];
 #pragma unroll
   for (int s = 0; s < kSlots; ++s)
@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) wacc[s][0][j][i] = 0.f;
+  float rsum = 0.f, rsum_go = 0.f;
 
   const int64_t n_tiles = (n + kThreads - 1) / kThreads;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -311,14 +312,39 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
         const int m0 = (t / 3) * 16, n0 = (t % 3) * 16;
         wgrad_block(wacc[s], T + TT_U, m0, T + TT_QB, n0);
         wgrad_block(wacc[s], T + TT_ZB, m0, T + TT_E, n0);
-      } else if (t < 16) {     // dW2 block: g_out h^T (+ row 0: ones (ub s)^T)
-        const int n0 = (t - 12) * 16;
-        wgrad_block(wacc[s], T + TT_GO, 0, T + TT_H, n0);
-        wgrad_block(wacc[s], T + TT_ONE, 0, T + TT_US, n0);
-      } else if (t < 20) {     // db1 = zb . ones  (column 0)
-        wgrad_block(wacc[s], T + TT_ZB, (t - 16) * 16, T + TT_ONE, 0);
-      } else if (t < kBlocks) {  // db2 = g_out . ones
-        wgrad_block(wacc[s], T + TT_GO, 0, T + TT_ONE, 0);
+      } else if (t < kBlocks) {  // dW2 block: g_out h^T
+        wgrad_block(wacc[s], T + TT_GO, 0, T + TT_H, (t - 12) * 16);
+      }
+    }
+    // ---- row sums over the tile's 128 samples (fp16 tiles, fp32 accumulation)
+    {
+      const __half* row = T + (tid < NH ? TT_ZB + tid * LDT : TT_US + (tid - NH) * LDT);
+      float a = 0.f;
+#pragma unroll
+      for (int v = 0; v < kThreads / 8; ++v) {
+        const uint4 q4 = *reinterpret_cast<const uint4*>(row + v * 8);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 f = __half22float2(h2[e2]);
+          a += f.x + f.y;
+        }
+      }
+      rsum += a;
+      if (tid < NOUTP) {
+        const __half* rg = T + TT_GO + tid * LDT;
+        float b = 0.f;
+#pragma unroll
+        for (int v = 0; v < kThreads / 8; ++v) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(rg + v * 8);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 f = __half22float2(h2[e2]);
+            b += f.x + f.y;
+          }
+        }
+        rsum_go += b;
       }
     }
   }
@@ -337,16 +363,19 @@ __global__ void __launch_bounds__(kThreads, 1) neus_field_bwd_kernel(const __gri
         if (t < 12) {
           const int m = (t / 3) * 16 + r, nn = (t % 3) * 16 + cidx;
           if (nn < NIN) atomicAdd(dW1 + m * NIN + nn, val);
-        } else if (t < 16) {
+        } else {
           const int nn = (t - 12) * 16 + cidx;
           if (r < n_out) atomicAdd(dW2 + r * NH + nn, val);
-        } else if (t < 20) {
-          if (cidx == 0) atomicAdd(db1 + (t - 16) * 16 + r, val);
-        } else {
-          if (cidx == 0 && r < n_out) atomicAdd(db2 + r, val);
         }
       }
   }
+  if (rsum != 0.f) {
+    if (tid < NH)
+      atomicAdd(db1 + tid, rsum * inv_scale);
+    else
+      atomicAdd(dW2 + (tid - NH), rsum * inv_scale);  // row 0 of dW2: + sum_s ub s
+  }
+  if (tid < n_out && rsum_go != 0.f) atomicAdd(db2 + tid, rsum_go * inv_scale);
 }
 
 int check(const nsr_grid_t* g, int n_out, const char* name) {
@@ -384,7 +413,7 @@ extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, cons
     }
     attr_set = true;
   }
-  const int grid = (int)min((int64_t)nsr_sm_count(), (n + kThreads - 1) / kThreads);
+  const int grid = (int)min((int64_t)nsr_sm_count() * 2, (n + kThreads - 1) / kThreads);  // two CTAs per SM: their gather / MLP / scatter phases overlap
   neus_field_bwd_kernel<<<grid, kThreads, kBwdSmem, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out,
                                                                             g_out, g_sdf, g_grad, amax, grad_table, dW1, db1, dW2, db2, n);
   NSR_CHECK_LAUNCH("nsr_neus_field_bwd");
