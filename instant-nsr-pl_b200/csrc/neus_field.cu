@@ -281,17 +281,55 @@ __global__ void __launch_bounds__(kThreads, 2) neus_field_bwd_kernel(const __gri
     }
 #pragma unroll
     for (int o = 0; o < NOUTP; ++o) T[TT_GO + o * LDT + tid] = __float2half(go[o] * scale);
-    // ---- table gradient: first- and second-order terms in one RED per corner
-    if (ok) {
+    // ---- table gradient: first- and second-order terms in one RED per corner.
+    // Levels 0..kMergeLevels-1 can merge runs of equal cells across neighbouring lanes (consecutive samples of a ray) with a segmented
+    // warp scan so that only the last lane of a run issues the 8 REDs (as in nerf_fused_bwd.cu).  Measured on B200 (C3, 313 k samples):
+    // 8 merged levels 0.617 ms vs 0.558 ms without -- with one sample per thread the 85 shuffles per level cost more than the REDs
+    // they save (this kernel is not RED-bound), so merging is compiled out.
+    constexpr int kMergeLevels = 0;
 #pragma unroll
-      for (int l = 0; l < 16; ++l) {
-        const float eb0 = eb[3 + 2 * l], eb1 = eb[4 + 2 * l], q0 = q[3 + 2 * l], q1 = q[4 + 2 * l];
-        const LevelInfo li = nsr_level(g, l);
-        uint32_t cx, cy, cz, idx[8];
-        float fx, fy, fz;
-        nsr_pos_fract(x, li.scale, cx, fx);
-        nsr_pos_fract(y, li.scale, cy, fy);
-        nsr_pos_fract(z, li.scale, cz, fz);
+    for (int l = 0; l < 16; ++l) {
+      const float eb0 = eb[3 + 2 * l], eb1 = eb[4 + 2 * l], q0 = q[3 + 2 * l], q1 = q[4 + 2 * l];
+      const LevelInfo li = nsr_level(g, l);
+      uint32_t cx, cy, cz, idx[8];
+      float fx, fy, fz;
+      nsr_pos_fract(x, li.scale, cx, fx);
+      nsr_pos_fract(y, li.scale, cy, fy);
+      nsr_pos_fract(z, li.scale, cz, fz);
+      if (l < kMergeLevels) {
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float wc = nsr_corner_weight(c, fx, fy, fz);
+          const float coef = li.scale * (gx0 * nsr_corner_dweight(c, 0, fx, fy, fz) + gx1 * nsr_corner_dweight(c, 1, fx, fy, fz) +
+                                         gx2 * nsr_corner_dweight(c, 2, fx, fy, fz));
+          v[2 * c] = ok ? wc * eb0 + coef * q0 : 0.f;
+          v[2 * c + 1] = ok ? wc * eb1 + coef * q1 : 0.f;
+        }
+        const uint32_t key = ok ? (cx + li.res * (cy + li.res * cz)) : (0xFFFFFFC0u + lane);
+        const uint32_t key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (key_prev != key);
+        const int next_head = __shfl_down_sync(0xffffffffu, (int)head, 1);
+        const bool tail = (lane == 31) || next_head;
+        bool flag = head;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int f_up = __shfl_up_sync(0xffffffffu, (int)flag, o);
+          const bool take = (lane >= o) && !flag;
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2) {
+            const float up = __shfl_up_sync(0xffffffffu, v[e2], o);
+            if (take) v[e2] += up;
+          }
+          if (take) flag = f_up;
+        }
+        if (ok && tail) {
+          nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (v[2 * c] != 0.f || v[2 * c + 1] != 0.f) nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[c], v[2 * c], v[2 * c + 1]);
+        }
+      } else if (ok) {
         nsr_corner_indices(li, cx, cy, cz, idx);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
