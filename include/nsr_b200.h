@@ -253,26 +253,30 @@ int nsr_nerf_rays_bwd(const nsr_nerf_t* f, const float* rays, const float* t_min
  * bwd: upstream g_out [n,n_out], g_sdf [n] (added to column 0) and g_grad [n,3] (each may be NULL) -> grad_table f32 (+=, first AND second order terms, one 8-byte RED per corner),
  * dW1, db1, dW2, db2 (+=).  amax: device float, bound on |g_out|, |g_grad| (fp16 scale of the weight-gradient tiles). */
 int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
-                       const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature, int64_t n, void* stream);
+                       const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature, int64_t n, const int64_t* n_dev,
+                       void* stream);
 int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1, const float* W2,
                        const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_sdf, const float* g_grad,
-                       const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n, void* stream);
+                       const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n, const int64_t* n_dev,
+                       void* stream);
 /* out[0] = max(|a|, |b|, |c|) over up to three fp32 arrays (NULL / 0 skipped): the bound nsr_neus_field_bwd's amax wants. */
-int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, void* stream);
+int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, int64_t rows_cap,
+                const int64_t* rows_dev /* non-NULL: arrays are [rows_cap, w] with *rows_dev live rows */, void* stream);
 
 /* sample -> world position / view direction / interval length (models/nerf.py:96-99, models/neus.py:222-225): rays f32 [N,6],
  * positions [K,3] = o + d * (t0 + t1) / 2 (mul then add, no fma), dirs [K,3] and dists [K] = t1 - t0 may be NULL. */
 int nsr_sample_points(const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends, float* positions,
-                      float* dirs, float* dists, int64_t n, void* stream);
+                      float* dirs, float* dists, int64_t n, const int64_t* n_dev, void* stream);
 
 /* ---- NeuS shading pieces (models/neus.py:117-139, 225, 237-243) --------------------------------------------------------------
+ * (n, n_dev) / (k, k_dev) follow the convention above: non-NULL device count => n is the buffer capacity (CUDA-graph capture).
  * nsr_neus_alpha_fwd: normal = normalize(sdf_grad) and alpha = get_alpha(sdf, normal, dirs, dists) with the cos-anneal ratio;
  * dirs f32 [K,3] per-sample view directions, dists f32 [K] = t_ends - t_starts, inv_s: DEVICE scalar (already clipped to [1e-6, 1e6]).
  * nsr_neus_alpha_bwd: d_alpha [K], d_normal [K,3] (may be NULL) -> d_sdf [K], d_sdf_grad [K,3], d_inv_s (+=, device scalar). */
 int nsr_neus_alpha_fwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, float* alpha, float* normal, int64_t n,
-                       void* stream);
+                       const int64_t* n_dev, void* stream);
 int nsr_neus_alpha_bwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, const float* d_alpha, const float* d_normal,
-                       float* d_sdf, float* d_sdf_grad, float* d_inv_s, int64_t n, void* stream);
+                       float* d_sdf, float* d_sdf_grad, float* d_inv_s, int64_t n, const int64_t* n_dev, void* stream);
 /* render_weight_from_alpha + accumulate_along_rays x4 (opacity, depth at the sample midpoints, rgb, normal) in one pass per
  * direction.  offsets int64 [n_rays+1]; comp_normal is the un-normalised weighted sum.  Backward: any of the g_* may be NULL. */
 int nsr_neus_composite_fwd(const float* alphas, const float* rgbs, const float* normals, const float* t_starts, const float* t_ends,
@@ -286,10 +290,10 @@ int nsr_neus_composite_bwd(const float* alphas, const float* rgbs, const float* 
  * rgb f32 [n,3].  Backward: d_rgb [n,3] -> d_feat, d_extra (either may be NULL), grad_params f32 [7168] (+=);
  * loss_scale <= 0: choose the fp16 dgrad scale from *amax (device float: max |d_rgb|). */
 int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra,
-                     const void* params_h, float* rgb, int64_t n, void* stream);
+                     const void* params_h, float* rgb, int64_t n, const int64_t* n_dev, void* stream);
 int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra,
                      const void* params_h, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
-                     float* grad_params, int64_t n, void* stream);
+                     float* grad_params, int64_t n, const int64_t* n_dev, void* stream);
 
 /* ---- occupancy-grid refresh (nerfacc OccupancyGrid._update behind every_n_step: models/nerf.py:45-55,
  * models/neus.py:79-111).  The caller draws the cells (int64 flat indices ix*R*R + iy*R + iz; NULL = every cell once) and the
@@ -330,10 +334,11 @@ int nsr_nerf_loss_bwd(const float* acc_rgb, const float* opacity, const float* b
  * g_sdf_grad / g_sdf may be NULL. */
 int nsr_neus_loss_fwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target, const float* opacity,
                       const float* fg_mask, const float* sdf_grad, const float* sdf, float* accum8, float* losses7, int64_t n_rays,
-                      int64_t k, void* stream);
+                      int64_t k, const int64_t* k_dev, void* stream);
 int nsr_neus_loss_bwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target, const float* opacity,
                       const float* fg_mask, const float* sdf_grad, const float* sdf, const float* accum8, const float* g_loss,
-                      float* g_comp_rgb, float* g_opacity, float* g_sdf_grad, float* g_sdf, int64_t n_rays, int64_t k, void* stream);
+                      float* g_comp_rgb, float* g_opacity, float* g_sdf_grad, float* g_sdf, int64_t n_rays, int64_t k, const int64_t* k_dev,
+                      void* stream);
 /* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
 int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
                    void* stream);

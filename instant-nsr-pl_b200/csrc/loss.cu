@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) neus_loss_fwd_kernel(const float* __restr
                                                             const float* __restrict__ target, const float* __restrict__ opacity,
                                                             const float* __restrict__ fg_mask, const float* __restrict__ sdf_grad,
                                                             const float* __restrict__ sdf, float sparsity_scale, float* __restrict__ accum,
-                                                            int64_t n_rays, int64_t k) {
+                                                            int64_t n_rays, int64_t k_cap, const int64_t* __restrict__ k_dev) {
+  const int64_t k = k_dev ? min(*k_dev, k_cap) : k_cap;
   float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int64_t stride = (int64_t)gridDim.x * 256;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n_rays; i += stride) {
@@ -158,8 +159,9 @@ __global__ void __launch_bounds__(256) neus_loss_fwd_kernel(const float* __restr
 
 // losses[0..5] = rgb_mse, rgb_l1, eikonal, mask, opaque, sparsity;  losses[6] = lambda-weighted total
 __global__ void neus_loss_finalize_kernel(const nsr_neus_loss_t P, const float* __restrict__ accum, float* __restrict__ losses, int64_t n_rays,
-                                          int64_t k) {
+                                          int64_t k_cap, const int64_t* __restrict__ k_dev) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int64_t k = k_dev ? min(*k_dev, k_cap) : k_cap;
   const float nv3 = fmaxf(accum[2] * 3.f, 1.f), nr = fmaxf((float)n_rays, 1.f), nk = fmaxf((float)k, 1.f);
   const float l[6] = {accum[0] / nv3, accum[1] / nv3, accum[5] / nk, accum[3] / nr, accum[4] / nr, accum[6] / nk};
   const float lam[6] = {P.lambda_rgb_mse, P.lambda_rgb_l1, P.lambda_eikonal, P.lambda_mask, P.lambda_opaque, P.lambda_sparsity};
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(256) neus_loss_bwd_kernel(const nsr_neus_loss_
                                                             const float* __restrict__ accum, const float* __restrict__ g_loss,
                                                             float* __restrict__ g_comp_rgb, float* __restrict__ g_opacity,
                                                             float* __restrict__ g_sdf_grad, float* __restrict__ g_sdf, int64_t n_rays,
-                                                            int64_t k) {
+                                                            int64_t k_cap, const int64_t* __restrict__ k_dev) {
+  const int64_t k = k_dev ? min(*k_dev, k_cap) : k_cap;
   const float g = g_loss ? __ldg(g_loss) : 1.f;
   const float inv_nv3 = g / fmaxf(accum[2] * 3.f, 1.f), inv_nr = g / fmaxf((float)n_rays, 1.f), inv_nk = g / fmaxf((float)k, 1.f);
   const int64_t stride = (int64_t)gridDim.x * 256;
@@ -225,16 +228,16 @@ __global__ void __launch_bounds__(256) neus_loss_bwd_kernel(const nsr_neus_loss_
 
 extern "C" int nsr_neus_loss_fwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target,
                                  const float* opacity, const float* fg_mask, const float* sdf_grad, const float* sdf, float* accum8,
-                                 float* losses7, int64_t n_rays, int64_t k, void* stream) {
+                                 float* losses7, int64_t n_rays, int64_t k, const int64_t* k_dev, void* stream) {
   NSR_REQUIRE(p != nullptr && accum8 != nullptr && losses7 != nullptr, "nsr_neus_loss_fwd: descriptor / accum / losses is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(accum8, 0, 8 * sizeof(float), st);
   const int64_t nmax = max(n_rays, k);
   if (nmax > 0) {
     const int grid = (int)min((int64_t)nsr_sm_count() * 4, (nmax + 255) / 256);
-    neus_loss_fwd_kernel<<<grid, 256, 0, st>>>(comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf, p->sparsity_scale, accum8, n_rays, k);
+    neus_loss_fwd_kernel<<<grid, 256, 0, st>>>(comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf, p->sparsity_scale, accum8, n_rays, k, k_dev);
   }
-  neus_loss_finalize_kernel<<<1, 32, 0, st>>>(*p, accum8, losses7, n_rays, k);
+  neus_loss_finalize_kernel<<<1, 32, 0, st>>>(*p, accum8, losses7, n_rays, k, k_dev);
   NSR_CHECK_LAUNCH("nsr_neus_loss_fwd");
   return 0;
 }
@@ -242,14 +245,14 @@ extern "C" int nsr_neus_loss_fwd(const nsr_neus_loss_t* p, const float* comp_rgb
 extern "C" int nsr_neus_loss_bwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uint8_t* valid, const float* target,
                                  const float* opacity, const float* fg_mask, const float* sdf_grad, const float* sdf, const float* accum8,
                                  const float* g_loss, float* g_comp_rgb, float* g_opacity, float* g_sdf_grad, float* g_sdf, int64_t n_rays,
-                                 int64_t k, void* stream) {
+                                 int64_t k, const int64_t* k_dev, void* stream) {
   NSR_REQUIRE(p != nullptr && accum8 != nullptr, "nsr_neus_loss_bwd: descriptor / accum is NULL");
   NSR_REQUIRE(g_comp_rgb != nullptr && g_opacity != nullptr, "nsr_neus_loss_bwd: per-ray gradient outputs are NULL");
   const int64_t nmax = max(n_rays, k);
   if (nmax == 0) return 0;
   const int grid = (int)min((int64_t)nsr_sm_count() * 4, (nmax + 255) / 256);
   neus_loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf, accum8, g_loss,
-                                                                g_comp_rgb, g_opacity, g_sdf_grad, g_sdf, n_rays, k);
+                                                                g_comp_rgb, g_opacity, g_sdf_grad, g_sdf, n_rays, k, k_dev);
   NSR_CHECK_LAUNCH("nsr_neus_loss_bwd");
   return 0;
 }

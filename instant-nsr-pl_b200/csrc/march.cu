@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_expand_kernel(nsr
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kMarchWarps + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
-  const int64_t beg = offsets[ray];
-  if (offsets[ray + 1] == beg) return;
+  const int64_t beg = offsets[ray], end = offsets[ray + 1];  // offsets clamped to a buffer capacity truncate the tail rays
+  if (end <= beg) return;
   const float tmin = t_min[ray], step = p.step;
   int64_t base = beg;
   for (int w0 = 0; w0 < words; w0 += 32) {
@@ -268,9 +268,11 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_expand_kernel(nsr
       const int b = __ffs(m) - 1;
       m &= m - 1u;
       const float k = (float)(w * 32 + b);
-      ray_indices[pos] = (int32_t)ray;
-      t_starts[pos] = __fmaf_rn(k, step, tmin);
-      t_ends[pos] = __fmaf_rn(k + 1.f, step, tmin);
+      if (pos < end) {
+        ray_indices[pos] = (int32_t)ray;
+        t_starts[pos] = __fmaf_rn(k, step, tmin);
+        t_ends[pos] = __fmaf_rn(k + 1.f, step, tmin);
+      }
       ++pos;
     }
     base += __shfl_sync(0xffffffffu, incl, 31);
@@ -372,7 +374,8 @@ namespace {
 __global__ void __launch_bounds__(256) sample_points_kernel(const float* __restrict__ rays, const int32_t* __restrict__ ray_indices,
                                                             const float* __restrict__ t_starts, const float* __restrict__ t_ends,
                                                             float* __restrict__ positions, float* __restrict__ dirs,
-                                                            float* __restrict__ dists, int64_t n) {
+                                                            float* __restrict__ dists, int64_t n_cap, const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int64_t i = blockIdx.x * 256ll + threadIdx.x;
   if (i >= n) return;
   const float* r = rays + (size_t)ray_indices[i] * 6;
@@ -389,10 +392,10 @@ __global__ void __launch_bounds__(256) sample_points_kernel(const float* __restr
 }  // namespace
 
 extern "C" int nsr_sample_points(const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                                 float* positions, float* dirs, float* dists, int64_t n, void* stream) {
+                                 float* positions, float* dirs, float* dists, int64_t n, const int64_t* n_dev, void* stream) {
   NSR_REQUIRE(positions != nullptr, "nsr_sample_points: positions is NULL");
   if (n == 0) return 0;
-  sample_points_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_indices, t_starts, t_ends, positions, dirs, dists, n);
+  sample_points_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_indices, t_starts, t_ends, positions, dirs, dists, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_sample_points");
   return 0;
 }

@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_kernel(const __gri
                                                                   const float* __restrict__ b1, const float* __restrict__ W2,
                                                                   const float* __restrict__ b2, float radius, int n_out,
                                                                   float* __restrict__ sdf, float* __restrict__ grad,
-                                                                  float* __restrict__ feat, int64_t n) {
+                                                                  float* __restrict__ feat, int64_t n_cap,
+                                                                  const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   __shared__ NeusW w;
   stage_neus_weights(w, W1, b1, W2, b2, n_out);
   __syncthreads();
@@ -187,7 +189,9 @@ __global__ void __launch_bounds__(kThreads, 2) neus_field_bwd_kernel(const __gri
                                                                      const float* __restrict__ g_grad,
                                                                      const float* __restrict__ amax_ptr, float* __restrict__ grad_table,
                                                                      float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
-                                                                     float* __restrict__ db2, int64_t n) {
+                                                                     float* __restrict__ db2, int64_t n_cap,
+                                                                     const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   NeusW& w = *reinterpret_cast<NeusW*>(smem_raw);
   __half* T = reinterpret_cast<__half*>(smem_raw + sizeof(NeusW));
@@ -426,12 +430,12 @@ int check(const nsr_grid_t* g, int n_out, const char* name) {
 
 extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1,
                                   const float* W2, const float* b2, float radius, int32_t n_out, float* sdf, float* grad, float* feature,
-                                  int64_t n, void* stream) {
+                                  int64_t n, const int64_t* n_dev, void* stream) {
   if (int e = check(g, n_out, "nsr_neus_field_fwd")) return e;
   if (n == 0) return 0;
   const int grid = (int)min((int64_t)nsr_sm_count() * 8, (n + kThreads - 1) / kThreads);
   neus_field_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out, sdf,
-                                                                     grad, feature, n);
+                                                                     grad, feature, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_neus_field_fwd");
   return 0;
 }
@@ -439,7 +443,7 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
 extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, const void* table_h, const float* W1, const float* b1,
                                   const float* W2, const float* b2, float radius, int32_t n_out, const float* g_out, const float* g_sdf,
                                   const float* g_grad, const float* amax, float* grad_table, float* dW1, float* db1, float* dW2, float* db2, int64_t n,
-                                  void* stream) {
+                                  const int64_t* n_dev, void* stream) {
   if (int e = check(g, n_out, "nsr_neus_field_bwd")) return e;
   if (n == 0) return 0;
   static thread_local bool attr_set = false;
@@ -453,14 +457,21 @@ extern "C" int nsr_neus_field_bwd(const nsr_grid_t* g, const float* points, cons
   }
   const int grid = (int)min((int64_t)nsr_sm_count() * 2, (n + kThreads - 1) / kThreads);  // two CTAs per SM: their gather / MLP / scatter phases overlap
   neus_field_bwd_kernel<<<grid, kThreads, kBwdSmem, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out,
-                                                                            g_out, g_sdf, g_grad, amax, grad_table, dW1, db1, dW2, db2, n);
+                                                                            g_out, g_sdf, g_grad, amax, grad_table, dW1, db1, dW2, db2, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_neus_field_bwd");
   return 0;
 }
 
 namespace {
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
-                                                     const float* __restrict__ c, int64_t nc, float* __restrict__ out) {
+                                                     const float* __restrict__ c, int64_t nc, float* __restrict__ out, int64_t rows_cap,
+                                                     const int64_t* __restrict__ rows_dev) {
+  if (rows_dev != nullptr) {  // arrays are [rows_cap, width]: only the first *rows_dev rows are live
+    const int64_t rows = min(*rows_dev, rows_cap);
+    na = na / rows_cap * rows;
+    nb = nb / rows_cap * rows;
+    nc = nc / rows_cap * rows;
+  }
   float m = 0.f;
   const int64_t stride = (int64_t)gridDim.x * 256, t0 = blockIdx.x * 256ll + threadIdx.x;
   for (int64_t i = t0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
@@ -472,8 +483,10 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a
 }
 }  // namespace
 
-extern "C" int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, void* stream) {
+extern "C" int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out, int64_t rows_cap,
+                           const int64_t* rows_dev, void* stream) {
   NSR_REQUIRE(out != nullptr, "nsr_absmax3: out is NULL");
+  NSR_REQUIRE(rows_dev == nullptr || rows_cap > 0, "nsr_absmax3: rows_dev needs rows_cap > 0");
   if (a == nullptr) na = 0;
   if (b == nullptr) nb = 0;
   if (c == nullptr) nc = 0;
@@ -481,7 +494,7 @@ extern "C" int nsr_absmax3(const float* a, int64_t na, const float* b, int64_t n
   const int64_t nmax = max(na, max(nb, nc));
   if (nmax == 0) return 0;
   const int grid = (int)min((int64_t)nsr_sm_count() * 4, (nmax + 255) / 256);
-  absmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, na, b, nb, c, nc, out);
+  absmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, na, b, nb, c, nc, out, rows_cap, rows_dev);
   NSR_CHECK_LAUNCH("nsr_absmax3");
   return 0;
 }

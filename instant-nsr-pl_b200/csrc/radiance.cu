@@ -56,7 +56,8 @@ constexpr size_t kFwdSmem = (size_t)(W_TOTAL + kFwdRows * LD32) * sizeof(__half)
 __global__ void __launch_bounds__(kFwdWarps * 32) radiance_fwd_kernel(const __grid_constant__ nsr_radiance_t P, const float* __restrict__ feat,
                                                                       const float* __restrict__ dirs,
                                                                       const float* __restrict__ extra, const __half* __restrict__ params,
-                                                                      float* __restrict__ rgb, int64_t n) {
+                                                                      float* __restrict__ rgb, int64_t n_cap, const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* X = smem + W_TOTAL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3, r0 = warp * 16;
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) radiance_bwd_kernel(const __gr
                                                                       const float* __restrict__ extra, const __half* __restrict__ params,
                                                                       const float* __restrict__ d_rgb, float loss_scale,
                                                                       const float* __restrict__ amax_ptr, float* __restrict__ d_feat,
-                                                                      float* __restrict__ d_extra, float* __restrict__ grad_params, int64_t n) {
+                                                                      float* __restrict__ d_extra, float* __restrict__ grad_params, int64_t n_cap,
+                                                                      const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + W_TOTAL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3, r0 = warp * 16;
@@ -280,7 +283,7 @@ int check_desc(const nsr_radiance_t* p, const char* who) {
 }  // namespace
 
 extern "C" int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, const float* dirs,
-                                const float* extra, const void* params_h, float* rgb, int64_t n, void* stream) {
+                                const float* extra, const void* params_h, float* rgb, int64_t n, const int64_t* n_dev, void* stream) {
   if (check_desc(p, "nsr_radiance_fwd")) return 1;
   if (n == 0) return 0;
   NSR_REQUIRE(p->n_extra == 0 || extra != nullptr, "nsr_radiance_fwd: extra input is NULL");
@@ -292,14 +295,14 @@ extern "C" int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, cons
   const int64_t tiles = (n + kFwdRows - 1) / kFwdRows;
   const int grid = (int)min((int64_t)nsr_sm_count() * 6, tiles);
   radiance_fwd_kernel<<<grid, kFwdWarps * 32, kFwdSmem, (cudaStream_t)stream>>>(*p, feat, dirs, extra, (const __half*)params_h,
-                                                                                 rgb, n);
+                                                                                 rgb, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_radiance_fwd");
   return 0;
 }
 
 extern "C" int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* dirs,
                                 const float* extra, const void* params_h, const float* d_rgb, float loss_scale, const float* amax,
-                                float* d_feat, float* d_extra, float* grad_params, int64_t n, void* stream) {
+                                float* d_feat, float* d_extra, float* grad_params, int64_t n, const int64_t* n_dev, void* stream) {
   if (check_desc(p, "nsr_radiance_bwd")) return 1;
   if (n == 0) return 0;
   NSR_REQUIRE(p->n_extra == 0 || extra != nullptr, "nsr_radiance_bwd: extra input is NULL");
@@ -318,7 +321,7 @@ extern "C" int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, cons
   const int64_t tiles = (n + kRows - 1) / kRows;
   const int grid = (int)min((int64_t)nsr_sm_count() * 2, tiles);
   radiance_bwd_kernel<<<grid, kWarps * 32, kBwdSmem, (cudaStream_t)stream>>>(*p, feat, dirs, extra, (const __half*)params_h, d_rgb,
-                                                                             loss_scale, amax, d_feat, d_extra, grad_params, n);
+                                                                             loss_scale, amax, d_feat, d_extra, grad_params, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_radiance_bwd");
   return 0;
 }

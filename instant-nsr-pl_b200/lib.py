@@ -92,16 +92,16 @@ _SIGNATURES = {
     'nsr_pack_kept': [P, P, P, F32, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_ray_bwd_loose': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P, F32, P, I64, P],
-    'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P],
-    'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_absmax3': [P, I64, P, I64, P, I64, P, P],
-    'nsr_sample_points': [P, P, P, P, P, P, P, I64, P],
-    'nsr_neus_alpha_fwd': [P, P, P, P, P, F32, P, P, I64, P],
-    'nsr_neus_alpha_bwd': [P, P, P, P, P, F32, P, P, P, P, P, I64, P],
+    'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P, P],
+    'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, P, I64, P, P],
+    'nsr_absmax3': [P, I64, P, I64, P, I64, P, I64, P, P],
+    'nsr_sample_points': [P, P, P, P, P, P, P, I64, P, P],
+    'nsr_neus_alpha_fwd': [P, P, P, P, P, F32, P, P, I64, P, P],
+    'nsr_neus_alpha_bwd': [P, P, P, P, P, F32, P, P, P, P, P, I64, P, P],
     'nsr_neus_composite_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P],
-    'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P],
+    'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P, P],
+    'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P, P],
     'nsr_occgrid_points': [P, P, P, P, P, I64, P],
     'nsr_occgrid_update': [P, P, P, P, F32, P, I64, I64, P],
     'nsr_occgrid_binarize': [P, P, F32, P, P, P, I32, I64, P],
@@ -109,8 +109,8 @@ _SIGNATURES = {
     'nsr_grad_nonfinite': [P, P, I64, P],
     'nsr_nerf_loss_fwd': [P, P, P, P, P, P, I64, P],
     'nsr_nerf_loss_bwd': [P, P, P, P, P, P, P, P, I64, P],
-    'nsr_neus_loss_fwd': [P, P, P, P, P, P, P, P, P, P, I64, I64, P],
-    'nsr_neus_loss_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, P],
+    'nsr_neus_loss_fwd': [P, P, P, P, P, P, P, P, P, P, I64, I64, P, P],
+    'nsr_neus_loss_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, P, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],
     'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P, P],
     'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],

@@ -44,13 +44,13 @@ def nerf_rgb_loss(acc_rgb, opacity, background_color, target_rgb):
 
 class _NeusLosses(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, desc, comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf):
+    def forward(ctx, desc, comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf, k_dev=None):
         n, k = comp_rgb.shape[0], (sdf_grad.shape[0] if sdf_grad is not None else (sdf.shape[0] if sdf is not None else 0))
         accum = torch.empty(8, device=comp_rgb.device)
         losses = torch.empty(7, device=comp_rgb.device)
         lib.call('nsr_neus_loss_fwd', _C.byref(desc), ptr(comp_rgb), ptr(valid), ptr(target), ptr(opacity), ptr(fg_mask), ptr(sdf_grad),
-                 ptr(sdf), ptr(accum), ptr(losses), n, k, stream())
-        ctx.desc, ctx.k = desc, k
+                 ptr(sdf), ptr(accum), ptr(losses), n, k, ptr(k_dev), stream())
+        ctx.desc, ctx.k, ctx.k_dev = desc, k, k_dev
         ctx.save_for_backward(comp_rgb, valid, target, opacity, fg_mask, sdf_grad, sdf, accum)
         return losses[6], losses[:6].detach()
 
@@ -63,8 +63,8 @@ class _NeusLosses(torch.autograd.Function):
         g_s = torch.empty_like(sdf) if (sdf is not None and ctx.needs_input_grad[7]) else None
         gl = contig(g_total.reshape(1), torch.float32)
         lib.call('nsr_neus_loss_bwd', _C.byref(ctx.desc), ptr(comp_rgb), ptr(valid), ptr(target), ptr(opacity), ptr(fg_mask), ptr(sdf_grad),
-                 ptr(sdf), ptr(accum), ptr(gl), ptr(g_rgb), ptr(g_op), ptr(g_sg), ptr(g_s), n, ctx.k, stream())
-        return None, g_rgb, None, None, g_op, None, g_sg, g_s
+                 ptr(sdf), ptr(accum), ptr(gl), ptr(g_rgb), ptr(g_op), ptr(g_sg), ptr(g_s), n, ctx.k, ptr(ctx.k_dev), stream())
+        return None, g_rgb, None, None, g_op, None, g_sg, g_s, None
 
 
 NEUS_LOSS_NAMES = ('rgb_mse', 'rgb_l1', 'eikonal', 'mask', 'opaque', 'sparsity')
@@ -74,7 +74,8 @@ def neus_losses(out, rgb, fg_mask=None, lambda_rgb_mse=10.0, lambda_rgb_l1=0.0, 
                 lambda_sparsity=0.0, sparsity_scale=1.0):
     """The loss block of systems/neus.py:98-121 as two CUDA kernels (one reduction, one gradient pass) instead of ~65 torch kernels and
     two boolean-mask host syncs.  ``out``: the 'neus' model's output dict (comp_rgb_full, rays_valid_full, opacity, sdf_grad_samples,
-    sdf_samples); ``rgb`` [N,3] target, ``fg_mask`` [N] (None = dataset without masks).  Defaults = configs/neus-blender.yaml:80-89.
+    sdf_samples; plus 'num_samples_dev' -- the device-side live sample count -- when the model ran in static-shape mode);
+    ``rgb`` [N,3] target, ``fg_mask`` [N] (None = dataset without masks).  Defaults = configs/neus-blender.yaml:80-89.
     -> (total, parts) with parts[i] = the un-weighted loss NEUS_LOSS_NAMES[i] (for logging).  curvature / distortion terms
     (lambda 0 in every shipped config) stay with the caller."""
     comp, op = out['comp_rgb_full'], out['opacity']
@@ -86,4 +87,4 @@ def neus_losses(out, rgb, fg_mask=None, lambda_rgb_mse=10.0, lambda_rgb_l1=0.0, 
     return _NeusLosses.apply(d, contig(comp, torch.float32), valid, contig(rgb, torch.float32), contig(op.reshape(-1), torch.float32),
                              None if fg_mask is None else contig(fg_mask.reshape(-1), torch.float32),
                              None if sg is None else contig(sg.reshape(-1, 3), torch.float32),
-                             None if s is None else contig(s.reshape(-1), torch.float32))
+                             None if s is None else contig(s.reshape(-1), torch.float32), out.get('num_samples_dev'))

@@ -90,6 +90,7 @@ class NeuSModel(BaseModel):
         self.background_color = None
         self.render_step_size = 1.732 * 2 * r / cfg.num_samples_per_ray
         self.cos_anneal_ratio = 1.0
+        self._march_static = None
 
     def _inv_s(self, n):
         return self.variance(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6).expand(n, 1)
@@ -168,7 +169,49 @@ class NeuSModel(BaseModel):
         return self._nerf_like(rays, self.geometry_bg, self.texture_bg, self.occupancy_grid_bg if self.config.grid_prune else None,
                                near, self.far_plane_bg, self.render_step_size_bg, self.cone_angle_bg, None, jitter=jitter)
 
-    def forward_(self, rays, jitter=None):
+    def _forward_static(self, rays, jitter=None):
+        cfg = self.config
+        if cfg.learned_background or not cfg.grid_prune or cfg.geometry.grad_type != 'analytic' or not rays.is_cuda:
+            raise NotImplementedError("static NeuS forward: foreground-only configs with grid_prune and analytic normals on CUDA (neus-blender)")
+        import math
+        n_rays, dev = rays.shape[0], rays.device
+        cap = int(cfg.get('static_sample_capacity', 1 << 19))
+        grid = self.occupancy_grid
+        if self._march_static is None:
+            r = float(cfg.radius)
+            self._march_static = (ops.march_struct(grid.roi_host(), grid._res, ContractionType.AABB.value, self.render_step_size, 0.0),
+                                  int(math.ceil(2.0 * math.sqrt(3.0) * r / self.render_step_size)) + 2)
+        ms, cap_per_ray = self._march_static
+        u = None
+        if self.randomized:
+            u = torch.rand(n_rays, device=dev) if jitter is None else jitter.to(dev, torch.float32).contiguous()
+        with torch.no_grad():
+            m = ops.march_masks_static(ms, rays, u, grid.bits(), grid.coarse_bits(), cap_per_ray, cap)
+        ri32, t_starts, t_ends, offsets, k_dev = m['ray_indices'], m['t_starts'][:, None], m['t_ends'][:, None], m['offsets'], m['k_dev']
+        with ops.live_rows(k_dev):
+            positions, t_dirs, dists = ops.sample_points(rays, ri32, t_starts, t_ends)
+            sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
+            inv_s = self.variance.inv_s.clip(1e-6, 1e6).reshape(1)
+            alpha, normal = ops.neus_alpha(sdf, sdf_grad, inv_s, t_dirs, dists, self.cos_anneal_ratio)
+            rgb = self.texture(feature, t_dirs, normal)
+        weights, opacity, depth, comp_rgb, comp_normal = ops.neus_composite(alpha, rgb, normal, t_starts, t_ends, offsets)
+        comp_normal = F.normalize(comp_normal, p=2, dim=-1)
+        num = k_dev.to(torch.int32)
+        valid = opacity > 0
+        out = {'comp_rgb': comp_rgb, 'comp_normal': comp_normal, 'opacity': opacity, 'depth': depth, 'rays_valid': valid, 'num_samples': num,
+               'sdf_samples': sdf, 'sdf_grad_samples': sdf_grad, 'weights': weights, 'points': ((t_starts + t_ends) / 2.).view(-1),
+               'intervals': dists.view(-1), 'ray_indices': ri32, 'num_samples_dev': k_dev, 'overflow': m['overflow']}
+        bg = self.background_color[None, :].expand(*comp_rgb.shape)
+        out.update({'comp_rgb_bg': bg, 'num_samples_bg': torch.zeros_like(num), 'rays_valid_bg': torch.zeros_like(valid),
+                    'comp_rgb_full': comp_rgb + bg * (1.0 - opacity), 'num_samples_full': num, 'rays_valid_full': valid})
+        return out
+
+    def forward_(self, rays, jitter=None, static=False):
+        """``static=True`` (our extension, CUDA-graph capture: nsr_b200.graph.GraphedStep): no host synchronisation -- sample tensors have
+        the fixed capacity ``config.static_sample_capacity`` (default 2^19 rows), the live count stays on the device
+        (out['num_samples_dev']) and every kernel touches only the live rows; out['overflow'] flags a step whose samples did not fit."""
+        if static:
+            return self._forward_static(rays, jitter)
         n_rays = rays.shape[0]
         rays_o, rays_d = rays[:, 0:3], rays[:, 3:6]
         with torch.no_grad():

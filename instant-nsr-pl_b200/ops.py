@@ -10,6 +10,7 @@ import os
 import numpy as np
 import torch
 
+import contextlib
 import ctypes as _C
 
 from .lib import lib, ptr, stream, check_cuda, contig, GridT, MlpT, MarchT, RadianceT, NSR_MAX_LEVELS
@@ -17,6 +18,22 @@ from .lib import lib, ptr, stream, check_cuda, contig, GridT, MlpT, MarchT, Radi
 LOSS_SCALE = 128.0  # same constant tiny-cuda-nn uses for fp16 backward passes
 
 _ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
+
+# ---- static-shape execution (CUDA-graph capture): sample tensors have a fixed capacity and the live row count stays on the device.
+# Inside ``with live_rows(k_dev):`` every sample-level wrapper below passes k_dev (int64 [1], CUDA) to its kernels (forward AND the
+# backward recorded for it), which then touch only rows < *k_dev; rows beyond are never read or written.
+_LIVE_ROWS = None
+
+
+@contextlib.contextmanager
+def live_rows(k_dev):
+    global _LIVE_ROWS
+    prev, _LIVE_ROWS = _LIVE_ROWS, k_dev
+    try:
+        yield
+    finally:
+        _LIVE_ROWS = prev
+
 
 
 # --------------------------------------------------------------------------------------------------
@@ -390,8 +407,8 @@ class _NeusSDF(torch.autograd.Function):
         grad = torch.empty(n, 3, device=dev)
         feat = torch.empty(n, n_out, device=dev)
         lib.call('nsr_neus_field_fwd', spec.ref(), ptr(points), ptr(table_h), ptr(W1), ptr(b1), ptr(W2), ptr(b2), float(radius), int(n_out),
-                 ptr(sdf), ptr(grad), ptr(feat), n, stream())
-        ctx.spec, ctx.radius, ctx.n_out = spec, radius, n_out
+                 ptr(sdf), ptr(grad), ptr(feat), n, ptr(_LIVE_ROWS), stream())
+        ctx.spec, ctx.radius, ctx.n_out, ctx.k_dev = spec, radius, n_out, _LIVE_ROWS
         ctx.save_for_backward(points, table_h, W1, b1, W2, b2)
         return sdf, grad, feat
 
@@ -402,13 +419,14 @@ class _NeusSDF(torch.autograd.Function):
         g_sdf, g_grad, g_feat = contig(g_sdf, torch.float32), contig(g_grad, torch.float32), contig(g_feat, torch.float32)
         amax = torch.empty(1, device=dev)
         cnt = lambda t: 0 if t is None else t.numel()
-        lib.call('nsr_absmax3', ptr(g_feat), cnt(g_feat), ptr(g_sdf), cnt(g_sdf), ptr(g_grad), cnt(g_grad), ptr(amax), stream())
+        lib.call('nsr_absmax3', ptr(g_feat), cnt(g_feat), ptr(g_sdf), cnt(g_sdf), ptr(g_grad), cnt(g_grad), ptr(amax), n, ptr(ctx.k_dev), stream())
         dtable = torch.zeros(ctx.spec.n_params, device=dev)
         sizes = [W1.numel(), b1.numel(), W2.numel(), b2.numel()]
         flat = torch.zeros(sum(sizes), device=dev)   # one fill for the four small gradients
         dW1, db1, dW2, db2 = [t.view_as(w) for t, w in zip(flat.split(sizes), (W1, b1, W2, b2))]
         lib.call('nsr_neus_field_bwd', ctx.spec.ref(), ptr(points), ptr(table_h), ptr(W1), ptr(b1), ptr(W2), ptr(b2), float(ctx.radius),
-                 int(n_out), ptr(g_feat), ptr(g_sdf), ptr(g_grad), ptr(amax), ptr(dtable), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), n, stream())
+                 int(n_out), ptr(g_feat), ptr(g_sdf), ptr(g_grad), ptr(amax), ptr(dtable), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), n, ptr(ctx.k_dev),
+                 stream())
         return None, None, None, None, dtable, None, dW1, db1, dW2, db2
 
 
@@ -432,8 +450,8 @@ class _NeusAlpha(torch.autograd.Function):
         alpha = torch.empty(n, device=sdf.device)
         normal = torch.empty(n, 3, device=sdf.device)
         lib.call('nsr_neus_alpha_fwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), float(cos_anneal), ptr(alpha), ptr(normal),
-                 n, stream())
-        ctx.cos_anneal = float(cos_anneal)
+                 n, ptr(_LIVE_ROWS), stream())
+        ctx.cos_anneal, ctx.k_dev = float(cos_anneal), _LIVE_ROWS
         ctx.save_for_backward(sdf, sdf_grad, inv_s, dirs, dists)
         return alpha, normal
 
@@ -446,7 +464,7 @@ class _NeusAlpha(torch.autograd.Function):
         d_grad = torch.empty(n, 3, device=sdf.device)
         d_inv_s = torch.zeros_like(inv_s)
         lib.call('nsr_neus_alpha_bwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), ctx.cos_anneal, ptr(g_alpha),
-                 ptr(contig(g_normal, torch.float32)), ptr(d_sdf), ptr(d_grad), ptr(d_inv_s), n, stream())
+                 ptr(contig(g_normal, torch.float32)), ptr(d_sdf), ptr(d_grad), ptr(d_inv_s), n, ptr(ctx.k_dev), stream())
         return d_sdf, d_grad, d_inv_s, None, None, None
 
 
@@ -511,8 +529,8 @@ class _Radiance(torch.autograd.Function):
     def forward(ctx, spec, feat, dirs, extra, params_f32, params_h):
         n = feat.shape[0]
         rgb = torch.empty(n, 3, device=feat.device)
-        lib.call('nsr_radiance_fwd', spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(params_h), ptr(rgb), n, stream())
-        ctx.spec = spec
+        lib.call('nsr_radiance_fwd', spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(params_h), ptr(rgb), n, ptr(_LIVE_ROWS), stream())
+        ctx.spec, ctx.k_dev = spec, _LIVE_ROWS
         ctx.save_for_backward(feat, dirs, extra, params_h)
         return rgb
 
@@ -521,12 +539,13 @@ class _Radiance(torch.autograd.Function):
         feat, dirs, extra, params_h = ctx.saved_tensors
         n, dev = feat.shape[0], feat.device
         g_rgb = contig(g_rgb, torch.float32)
-        amax = g_rgb.abs().amax().reshape(1) if n > 0 else torch.ones(1, device=dev)
+        amax = torch.empty(1, device=dev)
+        lib.call('nsr_absmax3', ptr(g_rgb), g_rgb.numel(), None, 0, None, 0, ptr(amax), n, ptr(ctx.k_dev), stream())
         d_feat = torch.empty_like(feat) if ctx.needs_input_grad[1] else None
         d_extra = torch.empty_like(extra) if (extra is not None and ctx.needs_input_grad[3]) else None
         gp = torch.zeros(params_h.shape[0], device=dev)
         lib.call('nsr_radiance_bwd', ctx.spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(params_h), ptr(g_rgb), 0.0, ptr(amax), ptr(d_feat),
-                 ptr(d_extra), ptr(gp), n, stream())
+                 ptr(d_extra), ptr(gp), n, ptr(ctx.k_dev), stream())
         return None, d_feat, None, d_extra, gp, None
 
 
@@ -547,5 +566,31 @@ def sample_points(rays, ray_indices, t_starts, t_ends):
     ts, te = contig(t_starts.detach().reshape(-1), torch.float32), contig(t_ends.detach().reshape(-1), torch.float32)
     k = ri.shape[0]
     pos, dirs, dists = torch.empty(k, 3, device=rays.device), torch.empty(k, 3, device=rays.device), torch.empty(k, device=rays.device)
-    lib.call('nsr_sample_points', ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(pos), ptr(dirs), ptr(dists), k, stream())
+    lib.call('nsr_sample_points', ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(pos), ptr(dirs), ptr(dists), k, ptr(_LIVE_ROWS), stream())
     return pos, dirs, dists
+
+
+def march_masks_static(ms, rays, jitter, bits, coarse_bits, cap_per_ray, cap):
+    """Sync-free marching for static-shape execution (AABB grids, cone_angle 0; same sample sets as ``march``): per-ray lattice masks
+    -> counts -> offsets (clamped to the buffer capacity ``cap``: samples beyond it are dropped, see 'overflow') -> packed samples in
+    capacity-sized buffers.  Returns dict(ray_indices i32 [cap], t_starts, t_ends f32 [cap], offsets i64 [N+1], k_dev i64 [1] = live rows,
+    overflow bool [1] device flag)."""
+    import ctypes
+    check_cuda(rays, bits, what='march_masks_static')
+    rays = contig(rays.detach(), torch.float32)
+    n, dev = rays.shape[0], rays.device
+    words = (cap_per_ray + 31) // 32
+    masks = torch.empty(n * words, dtype=torch.int32, device=dev)
+    t_min = torch.empty(n, device=dev)
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    mref = ctypes.byref(ms)
+    lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(jitter), ptr(bits), ptr(coarse_bits), ptr(masks), words, ptr(t_min), ptr(counts), n,
+             stream())
+    lib.call('nsr_scan_counts', ptr(counts), ptr(offsets), n, stream())
+    overflow = offsets[n:] > cap
+    offsets.clamp_(max=cap)
+    ri = torch.empty(cap, dtype=torch.int32, device=dev)
+    ts, te = torch.empty(cap, device=dev), torch.empty(cap, device=dev)
+    lib.call('nsr_march_rays_expand', mref, ptr(masks), words, ptr(t_min), ptr(offsets), ptr(ri), ptr(ts), ptr(te), n, stream())
+    return {'ray_indices': ri, 't_starts': ts, 't_ends': te, 'offsets': offsets, 'k_dev': offsets[n:], 'overflow': overflow}

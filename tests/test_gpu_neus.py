@@ -210,3 +210,64 @@ def test_neus_model_composed_path_still_matches_fused():
     assert cos(ga, gb) >= 0.99
     for (k, pa), (_, pb) in zip(mf.geometry.network.named_parameters(), mc.geometry.network.named_parameters()):
         assert cos(pa.grad, pb.grad) >= 0.99, k
+
+
+def test_neus_static_forward_and_graphed_step_match_eager():
+    """static-shape NeuS path (sync-free mask marcher, capacity buffers, device-side sample count) == the eager exact-size path,
+    first called directly, then replayed as one CUDA graph (nsr_b200.graph.GraphedStep) with the fused NeuS losses"""
+    from nsr_b200 import configs
+    from nsr_b200.losses import neus_losses
+    from nsr_b200.graph import GraphedStep
+    model, cfg, binary, rays, jitter = build(configs.neus_blender, 300, 7)
+    model.occupancy_grid.set_binary(torch.from_numpy(binary))
+    D = torch.device('cuda:0')
+    rays_d, jit = torch.from_numpy(rays).to(D), torch.from_numpy(jitter)
+    target = torch.rand(len(rays), 3, generator=torch.Generator().manual_seed(3)).to(D)
+    mask = (torch.rand(len(rays), generator=torch.Generator().manual_seed(4)) > 0.5).float().to(D)
+    params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
+
+    def run(static):
+        for p in params:
+            p.grad = None
+        out = model.forward_(rays_d, jitter=jit, static=static)
+        loss, parts = neus_losses(out, target, mask, lambda_rgb_mse=10., lambda_eikonal=0.1, lambda_mask=0.1, lambda_sparsity=0.01)
+        loss.backward()
+        return out, float(loss), parts.tolist(), [p.grad.clone() for p in params]
+
+    out_e, loss_e, parts_e, grads_e = run(False)
+    out_s, loss_s, parts_s, grads_s = run(True)
+    k = int(out_e['num_samples'])
+    assert int(out_s['num_samples_dev']) == k == int(out_s['num_samples']) and not bool(out_s['overflow'])
+    assert out_s['sdf_samples'].shape[0] == int(cfg.get('static_sample_capacity', 1 << 19)) > k
+    assert torch.equal(out_s['ray_indices'][:k].long(), out_e['ray_indices'])
+    assert torch.equal(out_s['sdf_samples'][:k], out_e['sdf_samples']) and torch.equal(out_s['comp_rgb'], out_e['comp_rgb'])
+    assert abs(loss_s - loss_e) <= 1e-6 * abs(loss_e) and np.allclose(parts_s, parts_e, rtol=1e-6)
+    for a, b in zip(grads_s, grads_e):
+        assert cos(a, b) > 0.9999 and float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12
+    del out_e, out_s
+
+    # capacity overflow is flagged, not silent
+    model.config['static_sample_capacity'] = 1024
+    with torch.no_grad():
+        o = model.forward_(rays_d, jitter=jit, static=True)
+    assert bool(o['overflow']) and int(o['num_samples_dev']) == 1024
+    model.config['static_sample_capacity'] = 1 << 16
+    del o
+
+    # the whole step as one graph (jitter off so that replays are comparable with the eager step)
+    model.randomized = False
+    _, loss_e0, _, grads_e0 = run(False)
+    for p in params:
+        p.grad = None
+
+    def loss_fn(out, batch):
+        return neus_losses(out, batch['rgb'], batch['fg_mask'], lambda_rgb_mse=10., lambda_eikonal=0.1, lambda_mask=0.1, lambda_sparsity=0.01)[0]
+
+    step = GraphedStep(model, loss_fn, len(rays), batch_spec={'rgb': (3,), 'fg_mask': ()}, device=D, warmup=2)
+    for _ in range(2):
+        loss_g = step(rays_d, rgb=target, fg_mask=mask, background_color=model.background_color.clone())
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - loss_e0) <= 1e-5 * abs(loss_e0)
+    for p, b in zip(params, grads_e0):
+        assert cos(p.grad, b) > 0.9999
+    assert step.launches_per_replay <= 16

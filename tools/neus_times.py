@@ -72,6 +72,25 @@ for name, fn, n in (('C3 neus-blender', configs.neus_blender, 8192), ('C4 neus-d
     res[name + ' kernels_ms_per_step'] = kern
     k = int(k.sum())
     res[name] = {'rays': n, 'samples': k, 'ms_per_step': round(ms, 3), 'rays_per_s': round(n / ms * 1e3), 'samples_per_s': round(k / ms * 1e3)}
+    if name.startswith('C3') and FUSED_LOSS:   # the same step as ONE CUDA graph (static-shape path, device-side sample count)
+        from nsr_b200.graph import GraphedStep
+        from nsr_b200.losses import neus_losses
+        for p in m.parameters():
+            p.grad = None
+        gs = GraphedStep(m, lambda out, b: neus_losses(out, b['rgb'], b['fg_mask'], lambda_rgb_mse=10., lambda_eikonal=0.1, lambda_mask=0.1)[0],
+                         n, batch_spec={'rgb': (3,), 'fg_mask': ()}, device=D, warmup=3)
+        for _ in range(5):
+            gs(rays, rgb=target, fg_mask=mask, background_color=torch.rand(3, device=D))
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            gs(rays, rgb=target, fg_mask=mask, background_color=torch.rand(3, device=D))
+        e1.record(); torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / 20
+        kd = int(gs.out['num_samples_dev'])
+        res[name + ' graphed'] = {'ms_per_step': round(gms, 3), 'rays_per_s': round(n / gms * 1e3), 'samples': kd, 'launches_per_replay': gs.launches_per_replay,
+                                  'overflow': bool(gs.out['overflow'])}
+        del gs
     del m
     torch.cuda.empty_cache()
 print(json.dumps(res))
