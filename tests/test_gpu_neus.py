@@ -263,9 +263,10 @@ def test_neus_static_forward_and_graphed_step_match_eager():
     def loss_fn(out, batch):
         return neus_losses(out, batch['rgb'], batch['fg_mask'], lambda_rgb_mse=10., lambda_eikonal=0.1, lambda_mask=0.1, lambda_sparsity=0.01)[0]
 
+    bg = model.background_color.clone()   # GraphedStep points model.background_color at its own static buffer
     step = GraphedStep(model, loss_fn, len(rays), batch_spec={'rgb': (3,), 'fg_mask': ()}, device=D, warmup=2)
     for _ in range(2):
-        loss_g = step(rays_d, rgb=target, fg_mask=mask, background_color=model.background_color.clone())
+        loss_g = step(rays_d, rgb=target, fg_mask=mask, background_color=bg)
     torch.cuda.synchronize()
     assert abs(float(loss_g) - loss_e0) <= 1e-5 * abs(loss_e0)
     for p, b in zip(params, grads_e0):
