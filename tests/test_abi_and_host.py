@@ -91,3 +91,22 @@ def test_cpu_tensors_are_rejected_loudly():
                                              n_hidden_layers=1))
     assert list(net.parameters())[0].dtype == torch.float32 and net.n_input_dims == 3 and net.n_output_dims == 16
     assert list(net.state_dict()) == ['params']
+
+
+def test_fused_adamw_and_static_neus_refuse_cpu():
+    """no CPU fallbacks: the optimizer and the static-shape NeuS path raise on CPU tensors instead of computing"""
+    import torch
+    from nsr_b200.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    opt = FusedAdamW([p], lr=1e-2)
+    with pytest.raises(NotImplementedError):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdamW([p], lr=-1.0)
+    from nsr_b200 import models, configs
+    m = models.make('neus', configs.neus_blender())
+    m.train()
+    m.background_color = torch.ones(3)
+    with pytest.raises(NotImplementedError):
+        m.forward_(torch.zeros(4, 6), static=True)
