@@ -215,6 +215,8 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
                        const void* enc_save_h, const void* dparams_h, const void* cparams_h, const float* d_sraw, const float* d_rgb,
                        float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
                        const int64_t* row_pos /* optional: row j of enc_save / d_sraw / d_rgb lives at row_pos[j] (loose layout) */,
+                       const float* xyzdir /* optional f32 [k,6]: unit-cube position + view direction per row (nsr_pack_kept); then rays,
+                                              ray_indices, t_starts, t_ends are not read and every load of a tile is independent */,
                        void* stream);
 
 /* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
@@ -231,12 +233,17 @@ int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* ma
 /* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
 int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                   const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k /* may be NULL */,
-                  int64_t* loose_pos /* packed row -> loose position, may be NULL */, int64_t n_rays, void* stream);
-/* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min). */
+                  int64_t* loose_pos /* packed row -> loose position, may be NULL */,
+                  const nsr_nerf_t* f, const float* rays, const void* enc_loose_h /* inputs of the optional outputs below */,
+                  void* enc_k_h /* fp16 [K,32] packed copy of the saved encodings, may be NULL */,
+                  float* xyzdir_k /* f32 [K,6] unit-cube position + view direction per packed row, may be NULL */, int64_t n_rays,
+                  void* stream);
+/* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min); offsets_k != NULL
+ * writes d_sraw / d_rgb in packed row order (row offsets_k[ray] + j) instead of the loose positions. */
 int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx, const float* trans,
                            const float* weights, const float* sigmas, const float* rgbs, const float* g_rgb, const float* g_opacity,
-                           const float* g_depth, const float* g_weights, float* d_sraw, float* d_rgb, float* amax, int64_t n_rays,
-                           void* stream);
+                           const float* g_depth, const float* g_weights, float* d_sraw, float* d_rgb, float* amax,
+                           const int64_t* offsets_k, int64_t n_rays, void* stream);
 /* nsr_nerf_rays_bwd: compositing backward + both MLPs + hash scatter in ONE kernel (a warp walks its ray's kept samples 16 at
  * a time from the last chunk to the first carrying the suffix sum).  g_weights is in the loose layout.  amax: device float,
  * zeroed; ticket: device uint32, zeroed; loss_scale <= 0 selects the fp16 dgrad scale on the device from the per-ray

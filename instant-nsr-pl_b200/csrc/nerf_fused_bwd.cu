@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
                                                                const float* __restrict__ d_sraw, const float* __restrict__ d_rgb,
                                                                float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
                                                                float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev,
-                                                               const int64_t* __restrict__ row_pos) {
+                                                               const int64_t* __restrict__ row_pos, const float* __restrict__ xyzdir) {
+  // xyzdir != NULL: "packed inputs" mode -- enc_save, d_sraw, d_rgb are in packed row order and xyzdir [n,6] holds the unit-cube position
+  // and the view direction of every row (written by nsr_pack_kept), so every load of a tile is independent of the others (no
+  // row_pos -> data or ray_indices -> rays chains in front of the math).
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + NF_W_TOTAL;
@@ -102,6 +105,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kRows;
     __syncthreads();  // previous tile's wgrad is done with the smem tiles (first iteration: weights are staged)
+    // rows this thread owns in the accumulator layout (g, g+8) and where their per-sample gradients live
+    const int64_t ia = row0 + r0 + g, ib = ia + 8;
+    const int64_t pa = (row_pos && ia < n) ? row_pos[ia] : ia, pb = (row_pos && ib < n) ? row_pos[ib] : ib;
+    // packed-inputs mode: issue the scatter phase's loads now, so that their latency hides behind the tensor-core chain
+    float pre_xyz[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, pre_ds[2] = {0.f, 0.f};
+    if (xyzdir) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int64_t i = hh ? ib : ia;
+        if (i < n) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) pre_xyz[hh][d] = __ldg(xyzdir + i * 6 + d);
+          if (c == 0) pre_ds[hh] = __ldg(d_sraw + i);
+        }
+      }
+    }
     // ---- stage this warp's 16 rows: encoded features and SH of the view direction
     for (int v = lane; v < 64; v += 32) {
       const int r = v >> 2, q = v & 3;
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       const int64_t i = row0 + r0 + lane;
       uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
       if (i < n) {
-        const float* rr = rays + (size_t)ray_indices[i] * 6;
+        const float* rr = xyzdir ? xyzdir + (size_t)i * 6 : rays + (size_t)ray_indices[i] * 6;
         float s[16];
         nsr_sh4(__ldg(rr + 3), __ldg(rr + 4), __ldg(rr + 5), s);
         s0 = make_uint4(nsr_pack_h2(s[0], s[1]), nsr_pack_h2(s[2], s[3]), nsr_pack_h2(s[4], s[5]), nsr_pack_h2(s[6], s[7]));
@@ -161,9 +180,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       nsr_gemm_w<1, 4, 2>(acc16, a_g2, smem + NF_OFF_CW3, NSR_LD64);
     }
     // ---- d(rgb pre-activation) = d_rgb * s (1 - s), s = sigmoid(fp16(raw)); columns 0..2 only
-    const int64_t ia = row0 + r0 + g, ib = ia + 8;
-    // rows of the per-sample gradient buffers (identity for the packed layout, loose positions for the per-ray forward)
-    const int64_t pa = (row_pos && ia < n) ? row_pos[ia] : ia, pb = (row_pos && ib < n) ? row_pos[ib] : ib;
     uint32_t a_dc3[1][1][4];
     {
       float dp[4] = {0.f, 0.f, 0.f, 0.f};  // (row g: col c*2, c*2+1), (row g+8: col c*2, c*2+1)
@@ -203,8 +219,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     nsr_zero_acc(acc16);
     nsr_gemm_wt<1, 4, 2>(acc16, a_d, smem + NF_OFF_CW1, NF_LD32);  // first 16 input columns = the geometry features
     if (c == 0) {  // density path: d(out0) += d sigma / d raw (trunc_exp backward folded in by nsr_nerf_ray_bwd)
-      if (ia < n) acc16[0][0][0] += d_sraw[pa] * loss_scale;
-      if (ib < n) acc16[0][0][2] += d_sraw[pb] * loss_scale;
+      if (ia < n) acc16[0][0][0] += (xyzdir ? pre_ds[0] : d_sraw[pa]) * loss_scale;
+      if (ib < n) acc16[0][0][2] += (xyzdir ? pre_ds[1] : d_sraw[pb]) * loss_scale;
     }
     uint32_t a_do[1][1][4];
     nsr_acc_to_afrag<1, 2>(acc16, a_do, NSR_ACT_NONE);
@@ -226,7 +242,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       const int64_t i = hh ? ib : ia;
       const bool ok = i < n;
       float x = 0.f, y = 0.f, z = 0.f, dx, dy, dz;
-      if (ok) nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
+      if (ok) {
+        if (xyzdir) {
+          x = pre_xyz[hh][0];
+          y = pre_xyz[hh][1];
+          z = pre_xyz[hh][2];
+        } else {
+          nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const float d0 = ok ? accE[0][nt][hh * 2] * inv_scale : 0.f, d1 = ok ? accE[0][nt][hh * 2 + 1] * inv_scale : 0.f;
@@ -305,7 +329,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
 extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
                                   const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
                                   const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
-                                  const float* amax, int64_t k, const int64_t* k_dev, const int64_t* row_pos, void* stream) {
+                                  const float* amax, int64_t k, const int64_t* k_dev, const int64_t* row_pos, const float* xyzdir,
+                                  void* stream) {
   NSR_REQUIRE(f != nullptr, "nsr_nerf_field_bwd: field descriptor is NULL");
   NSR_REQUIRE(f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 && f->color_hidden == 2,
               "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
@@ -325,7 +350,7 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
   if (k_dev != nullptr) grid = nsr_sm_count() * kCtasPerSm;
   nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
                                                                         (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos);
+                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
   return 0;
 }

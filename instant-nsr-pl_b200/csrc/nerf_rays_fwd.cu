@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
                                                         const float* __restrict__ t_min, float step, const int32_t* __restrict__ kidx,
                                                         const float* __restrict__ weights, int32_t* __restrict__ ri_k,
                                                         float* __restrict__ ts_k, float* __restrict__ te_k, float* __restrict__ w_k,
-                                                        int64_t* __restrict__ loose_pos, int64_t n_rays) {
+                                                        int64_t* __restrict__ loose_pos, const __grid_constant__ nsr_nerf_t P,
+                                                        const float* __restrict__ rays, const uint4* __restrict__ enc_loose,
+                                                        uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int64_t n_rays) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
@@ -268,11 +270,21 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
   const float tmin = t_min[ray];
   for (int64_t j = lane; j < cnt; j += 32) {
     const float k = (float)kidx[src + j];
+    const float t0 = __fmaf_rn(k, step, tmin), t1 = __fmaf_rn(k + 1.f, step, tmin);
     ri_k[dst + j] = (int32_t)ray;
-    ts_k[dst + j] = __fmaf_rn(k, step, tmin);
-    te_k[dst + j] = __fmaf_rn(k + 1.f, step, tmin);
+    ts_k[dst + j] = t0;
+    te_k[dst + j] = t1;
     if (w_k) w_k[dst + j] = weights[src + j];
     if (loose_pos) loose_pos[dst + j] = src + j;
+    if (xyzdir_k) {  // inputs of the tile backward in packed order: unit-cube position + view direction, encoded features
+      float x, y, z, dx, dy, dz;
+      nf_sample_position(P, rays, (int)ray, t0, t1, x, y, z, dx, dy, dz);
+      float* o = xyzdir_k + (dst + j) * 6;
+      o[0] = x; o[1] = y; o[2] = z; o[3] = dx; o[4] = dy; o[5] = dz;
+    }
+  }
+  if (enc_k) {  // 64 B rows: 4 lanes per row => every warp iteration moves 8 whole rows with fully used sectors
+    for (int64_t v = lane; v < cnt * 4; v += 32) enc_k[dst * 4 + v] = enc_loose[src * 4 + v];
   }
 }
 
@@ -284,11 +296,12 @@ __global__ void __launch_bounds__(256) ray_bwd_loose_kernel(const int64_t* __res
                                                             const float* __restrict__ g_rgb, const float* __restrict__ g_opacity,
                                                             const float* __restrict__ g_depth, const float* __restrict__ g_weights,
                                                             float* __restrict__ d_sraw, float* __restrict__ d_rgb, float* __restrict__ amax,
-                                                            int64_t n_rays) {
+                                                            const int64_t* __restrict__ off_k, int64_t n_rays) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
   const int64_t beg = off_m[ray];
+  const int64_t out0 = off_k ? off_k[ray] : beg;  // off_k != NULL: gradients are written in packed row order
   const int n = kept[ray];
   if (n <= 0) return;
   const float tmin = t_min[ray];
@@ -306,9 +319,9 @@ __global__ void __launch_bounds__(256) ray_bwd_loose_kernel(const int64_t* __res
       const float t0 = __fmaf_rn(kf, step, tmin), t1 = __fmaf_rn(kf + 1.f, step, tmin);
       delta = t1 - t0;
       gi = gr * rgbs[i * 3 + 0] + gg * rgbs[i * 3 + 1] + gb * rgbs[i * 3 + 2] + go + gd * ((t0 + t1) * 0.5f) + (g_weights ? g_weights[i] : 0.f);
-      d_rgb[i * 3 + 0] = w * gr;
-      d_rgb[i * 3 + 1] = w * gg;
-      d_rgb[i * 3 + 2] = w * gb;
+      d_rgb[(out0 + j) * 3 + 0] = w * gr;
+      d_rgb[(out0 + j) * 3 + 1] = w * gg;
+      d_rgb[(out0 + j) * 3 + 2] = w * gb;
       vmax = fmaxf(vmax, 0.25f * w * fmaxf(fabsf(gr), fmaxf(fabsf(gg), fabsf(gb))));
     }
     const float gw = gi * w;
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(256) ray_bwd_loose_kernel(const int64_t* __res
     if (ok) {
       const float ds = delta * (gi * (trans[i] - w) - (carry + suf - gw));
       const float dr = ds * fminf(sigmas[i], 3269017.37f);
-      d_sraw[i] = dr;
+      d_sraw[out0 + j] = dr;
       vmax = fmaxf(vmax, fabsf(dr));
     }
     carry += __shfl_sync(0xffffffffu, suf, 0);
@@ -370,10 +383,17 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
 
 extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                              const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k,
-                             int64_t* loose_pos, int64_t n_rays, void* stream) {
+                             int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h, void* enc_k_h,
+                             float* xyzdir_k, int64_t n_rays, void* stream) {
   if (n_rays == 0) return 0;
+  NSR_REQUIRE(xyzdir_k == nullptr || (f != nullptr && rays != nullptr), "nsr_pack_kept: xyzdir_k needs the field descriptor and the rays");
+  NSR_REQUIRE(enc_k_h == nullptr || enc_loose_h != nullptr, "nsr_pack_kept: enc_k needs the loose encoding buffer");
+  nsr_nerf_t dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  dummy.radius = 1.f;
   pack_kept_kernel<<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, t_min, step, kidx, weights, ray_indices_k,
-                                                                            t_starts_k, t_ends_k, weights_k, loose_pos, n_rays);
+                                                                            t_starts_k, t_ends_k, weights_k, loose_pos, f ? *f : dummy, rays,
+                                                                            (const uint4*)enc_loose_h, (uint4*)enc_k_h, xyzdir_k, n_rays);
   NSR_CHECK_LAUNCH("nsr_pack_kept");
   return 0;
 }
@@ -381,10 +401,10 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
 extern "C" int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx,
                                       const float* trans, const float* weights, const float* sigmas, const float* rgbs, const float* g_rgb,
                                       const float* g_opacity, const float* g_depth, const float* g_weights, float* d_sraw, float* d_rgb,
-                                      float* amax, int64_t n_rays, void* stream) {
+                                      float* amax, const int64_t* offsets_k, int64_t n_rays, void* stream) {
   if (n_rays == 0) return 0;
   ray_bwd_loose_kernel<<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, kept, t_min, step, kidx, trans, weights, sigmas, rgbs,
-                                                                                g_rgb, g_opacity, g_depth, g_weights, d_sraw, d_rgb, amax, n_rays);
+                                                                                g_rgb, g_opacity, g_depth, g_weights, d_sraw, d_rgb, amax, offsets_k, n_rays);
   NSR_CHECK_LAUNCH("nsr_nerf_ray_bwd_loose");
   return 0;
 }

@@ -63,7 +63,7 @@ class _NerfRender(torch.autograd.Function):
             lib.call('nsr_nerf_ray_bwd', ptr(offsets_k), ptr(ts), ptr(te), ptr(trans), ptr(weights), ptr(sig), ptr(rgbs), ptr(f32(g_rgb)),
                      ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n_rays, stream())
             lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc), ptr(dh), ptr(ch), ptr(d_sraw),
-                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n_rays:]), None, stream())
+                     ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n_rays:]), None, None, stream())
         return gd, gc, None, None, None
 
 
@@ -107,12 +107,19 @@ class _NerfRenderRays(torch.autograd.Function):
                  ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, stream())
         lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
+        # plus (training, tile backward) the backward's inputs in packed row order: encodings, unit-cube position + view direction
         ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
+        packed_bwd = need_grad and fused.bwd_kernel == 'tiles' and fused.packed_bwd_inputs
+        enc_k = torch.empty(cap, 32, dtype=torch.float16, device=dev) if packed_bwd else None
+        xyzdir = f32(cap, 6) if packed_bwd else None
         lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
-                 ptr(pos), n, stream())
+                 ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
         ctx.fused, ctx.n_rays, ctx.cap = fused, n, cap
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch)
+        if packed_bwd:
+            enc = None   # the loose copy is not needed any more
+        ctx.save_for_backward(rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch,
+                              enc_k, xyzdir)
         counts_mk = torch.cat([offsets_m[n:], offsets_k[n:]])  # [M, K] on the device
         ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k, counts_mk)
         return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, counts_mk
@@ -120,13 +127,13 @@ class _NerfRenderRays(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_op, g_depth, g_w, *_):
         fused = ctx.fused
-        rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch = ctx.saved_tensors
+        rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch, enc_k, xyzdir = ctx.saved_tensors
         dev = rays.device
         n, cap = ctx.n_rays, ctx.cap
         step = float(fused.model.render_step_size)
         gd = torch.zeros(fused.n_dparams, device=dev)
         gc = torch.zeros(fused.n_cparams, device=dev)
-        if enc is not None and n > 0:
+        if (enc is not None or enc_k is not None) and n > 0:
             f32 = lambda t: None if t is None else contig(t, torch.float32)
             amax = torch.zeros(1, device=dev)
             if fused.bwd_kernel == 'rays':
@@ -137,11 +144,13 @@ class _NerfRenderRays(torch.autograd.Function):
             else:
                 d_sraw = torch.empty(cap, device=dev)
                 d_rgb = torch.empty(cap, 3, device=dev)
+                packed = enc_k is not None   # gradients + encodings in packed row order: no index chains in front of the tile math
                 lib.call('nsr_nerf_ray_bwd_loose', ptr(offsets_m), ptr(kept), ptr(t_min), step, ptr(kidx), ptr(trans), ptr(weights), ptr(sig),
-                         ptr(rgbs), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax), n,
-                         stream())
-                lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc), ptr(dh), ptr(ch), ptr(d_sraw),
-                         ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(pos), stream())
+                         ptr(rgbs), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax),
+                         ptr(offsets_k) if packed else None, n, stream())
+                lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc_k if packed else enc), ptr(dh), ptr(ch),
+                         ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]),
+                         None if packed else ptr(pos), ptr(xyzdir), stream())
         return gd, gc, None, None, None
 
 
@@ -170,6 +179,7 @@ class NerfFused:
         self.last_stats = {}
         self._ticket = None
         self.mode = 'per_ray'   # 'per_ray' (persistent per-ray forward kernel) | 'two_pass' (pre-pass / compaction / sample-tile kernels)
+        self.packed_bwd_inputs = True   # tile backward reads its inputs in packed row order (written by nsr_pack_kept)
         self.bwd_kernel = 'tiles'  # 'tiles' (sample-tile backward through the packed->loose index) | 'rays' (single per-ray backward kernel)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 
