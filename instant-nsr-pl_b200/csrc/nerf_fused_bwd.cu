@@ -27,8 +27,17 @@ constexpr int T_DG2 = T_DC3 + kRows * 24;       // [128][72]
 constexpr int T_DG1 = T_DG2 + kRows * NSR_LD64; // [128][72]
 constexpr int T_DO = T_DG1 + kRows * NSR_LD64;  // [128][24]  d(out16)
 constexpr int T_DH1 = T_DO + kRows * 24;        // [128][72]
-constexpr int T_TOTAL = T_DH1 + kRows * NSR_LD64;
-constexpr size_t kSmemBytes = (size_t)(NF_W_TOTAL + T_TOTAL) * sizeof(__half);
+constexpr int T_X0B = T_DH1 + kRows * NSR_LD64; // [64][40]  second encoded-feature buffer (packed mode: cp.async double buffering)
+constexpr int T_TOTAL = T_X0B + kRows * NF_LD32;
+// packed mode: per-row inputs of two tiles in flight (floats): xyz+dir [64][6], d_sraw [64], d_rgb [64][3]
+constexpr int S_XYZ = 0, S_DS = S_XYZ + kRows * 6, S_DRGB = S_DS + kRows, S_ROWF = S_DRGB + kRows * 3;  // 640 floats per buffer
+constexpr size_t kSmemBytes = (size_t)(NF_W_TOTAL + T_TOTAL) * sizeof(__half) + 2 * S_ROWF * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 constexpr int kSlots = 40 / kWarps;  // 40 wgrad pair-tiles split over the warps
 
@@ -69,6 +78,11 @@ __device__ __forceinline__ void relu_mask_pack(const float (&acc)[1][8][4], cons
     }
 }
 
+// PACKED: enc_save, d_sraw, d_rgb are in packed row order and xyzdir [n,6] holds the unit-cube position and the view direction of
+// every row (written by nsr_pack_kept; buffers padded by one tile).  All global inputs of tile t+1 are then fetched with cp.async
+// into the second smem buffer while tile t computes: no load of the kernel sits in front of the math any more (ncu before:
+// 37 % of the stall samples were long-scoreboard waits on the row_pos -> enc / ray_indices -> rays chains and on the tile's loads).
+template <bool PACKED>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __grid_constant__ nsr_nerf_t P, const float* __restrict__ rays,
                                                                const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                                                                const float* __restrict__ t_ends, const __half* __restrict__ enc_save,
@@ -77,12 +91,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
                                                                float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
                                                                float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev,
                                                                const int64_t* __restrict__ row_pos, const float* __restrict__ xyzdir) {
-  // xyzdir != NULL: "packed inputs" mode -- enc_save, d_sraw, d_rgb are in packed row order and xyzdir [n,6] holds the unit-cube position
-  // and the view direction of every row (written by nsr_pack_kept), so every load of a tile is independent of the others (no
-  // row_pos -> data or ray_indices -> rays chains in front of the math).
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + NF_W_TOTAL;
+  float* rowf = reinterpret_cast<float*>(smem + NF_W_TOTAL + T_TOTAL);  // [2][S_ROWF]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int r0 = warp * 16;
   if (loss_scale <= 0.f) {  // automatic: bring the largest incoming gradient to ~2^8
@@ -102,40 +114,66 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       for (int i = 0; i < 4; ++i) wacc[s][j][i] = 0.f;
 
   const int64_t n_tiles = (n + kRows - 1) / kRows;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // packed mode: asynchronous fetch of one tile's inputs into buffer `buf` (all threads; 16-byte chunks, L1 bypassed)
+  auto fetch_tile = [&](int64_t tile, int buf) {
     const int64_t row0 = tile * kRows;
+    __half* xb = T + (buf ? T_X0B : T_X0);
+    float* rf = rowf + buf * S_ROWF;
+    for (int v = threadIdx.x; v < kRows * 4; v += kThreads)  // 64 rows x 4 chunks of the 64-byte encodings
+      cp_async16(xb + (v >> 2) * NF_LD32 + (v & 3) * 8, enc_save + (row0 + (v >> 2)) * 32 + (v & 3) * 8);
+    for (int v = threadIdx.x; v < kRows * 6 / 4; v += kThreads) cp_async16(rf + S_XYZ + v * 4, xyzdir + row0 * 6 + v * 4);
+    if (threadIdx.x < kRows / 4) cp_async16(rf + S_DS + threadIdx.x * 4, d_sraw + row0 + threadIdx.x * 4);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kRows * 3 / 4)
+      cp_async16(rf + S_DRGB + (threadIdx.x - 64) * 4, d_rgb + row0 * 3 + (threadIdx.x - 64) * 4);
+    cp_async_commit();
+  };
+  int buf = 0;
+  if (PACKED && (int64_t)blockIdx.x < n_tiles) fetch_tile(blockIdx.x, 0);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t row0 = tile * kRows;
+    if (PACKED) cp_async_wait_all();  // this tile's inputs have landed (issued one tile ago)
     __syncthreads();  // previous tile's wgrad is done with the smem tiles (first iteration: weights are staged)
-    // rows this thread owns in the accumulator layout (g, g+8) and where their per-sample gradients live
-    const int64_t ia = row0 + r0 + g, ib = ia + 8;
-    const int64_t pa = (row_pos && ia < n) ? row_pos[ia] : ia, pb = (row_pos && ib < n) ? row_pos[ib] : ib;
-    // packed-inputs mode: issue the scatter phase's loads now, so that their latency hides behind the tensor-core chain
-    float pre_xyz[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, pre_ds[2] = {0.f, 0.f};
-    if (xyzdir) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int64_t i = hh ? ib : ia;
-        if (i < n) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) pre_xyz[hh][d] = __ldg(xyzdir + i * 6 + d);
-          if (c == 0) pre_ds[hh] = __ldg(d_sraw + i);
+    const __half* X0 = T + ((PACKED && buf) ? T_X0B : T_X0);
+    const int x0_off = (PACKED && buf) ? T_X0B : T_X0;
+    const float* rf = rowf + buf * S_ROWF;
+    if (PACKED) {
+      if (tile + gridDim.x < n_tiles) fetch_tile(tile + gridDim.x, buf ^ 1);
+      if (row0 + kRows > n) {  // last, partial tile: rows >= n hold stale data; zero them so that 0 * garbage never reaches the wgrad sums
+        for (int v = threadIdx.x; v < kRows * 4; v += kThreads)
+          if (row0 + (v >> 2) >= n) *reinterpret_cast<uint4*>(T + x0_off + (v >> 2) * NF_LD32 + (v & 3) * 8) = make_uint4(0, 0, 0, 0);
+        float* rw = rowf + buf * S_ROWF;
+        for (int v = threadIdx.x; v < S_ROWF; v += kThreads) {
+          const int r = v < S_DS ? v / 6 : (v < S_DRGB ? v - S_DS : (v - S_DRGB) / 3);
+          if (row0 + r >= n) rw[v] = 0.f;
         }
+        __syncthreads();
       }
     }
+    // rows this thread owns in the accumulator layout (g, g+8) and where their per-sample gradients live
+    const int64_t ia = row0 + r0 + g, ib = ia + 8;
+    const int64_t pa = (!PACKED && row_pos && ia < n) ? row_pos[ia] : ia, pb = (!PACKED && row_pos && ib < n) ? row_pos[ib] : ib;
     // ---- stage this warp's 16 rows: encoded features and SH of the view direction
-    for (int v = lane; v < 64; v += 32) {
-      const int r = v >> 2, q = v & 3;
-      const int64_t i = row0 + r0 + r;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (i < n) val = __ldg(reinterpret_cast<const uint4*>(enc_save + (row_pos ? row_pos[i] : i) * 32) + q);
-      *reinterpret_cast<uint4*>(T + T_X0 + (r0 + r) * NF_LD32 + q * 8) = val;
+    if (!PACKED) {
+      for (int v = lane; v < 64; v += 32) {
+        const int r = v >> 2, q = v & 3;
+        const int64_t i = row0 + r0 + r;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (i < n) val = __ldg(reinterpret_cast<const uint4*>(enc_save + (row_pos ? row_pos[i] : i) * 32) + q);
+        *reinterpret_cast<uint4*>(T + T_X0 + (r0 + r) * NF_LD32 + q * 8) = val;
+      }
     }
     if (lane < 16) {
       const int64_t i = row0 + r0 + lane;
       uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
       if (i < n) {
-        const float* rr = xyzdir ? xyzdir + (size_t)i * 6 : rays + (size_t)ray_indices[i] * 6;
         float s[16];
-        nsr_sh4(__ldg(rr + 3), __ldg(rr + 4), __ldg(rr + 5), s);
+        if (PACKED) {
+          const float* rr = rf + S_XYZ + (r0 + lane) * 6;
+          nsr_sh4(rr[3], rr[4], rr[5], s);
+        } else {
+          const float* rr = rays + (size_t)ray_indices[i] * 6;
+          nsr_sh4(__ldg(rr + 3), __ldg(rr + 4), __ldg(rr + 5), s);
+        }
         s0 = make_uint4(nsr_pack_h2(s[0], s[1]), nsr_pack_h2(s[2], s[3]), nsr_pack_h2(s[4], s[5]), nsr_pack_h2(s[6], s[7]));
         s1 = make_uint4(nsr_pack_h2(s[8], s[9]), nsr_pack_h2(s[10], s[11]), nsr_pack_h2(s[12], s[13]), nsr_pack_h2(s[14], s[15]));
       }
@@ -150,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     float acc[1][8][4], acc16[1][2][4];
     {
       uint32_t a_in[1][2][4];
-      nsr_load_afrag<1, 2>(a_in, T + T_X0, NF_LD32, r0);
+      nsr_load_afrag<1, 2>(a_in, X0, NF_LD32, r0);
       nsr_zero_acc(acc);
       nsr_gemm_w<1, 2, 8>(acc, a_in, smem + NF_OFF_DW1, NF_LD32);
       nsr_acc_to_afrag<1, 8>(acc, a_h1, NSR_ACT_RELU);
@@ -194,7 +232,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
               if (col < 3) {
                 const float raw = __half2float(__float2half_rn(acc16[0][0][hh * 2 + e]));
                 const float s = 1.f / (1.f + expf(-raw));
-                dp[hh * 2 + e] = d_rgb[pi * 3 + col] * s * (1.f - s) * loss_scale;
+                const float dr = PACKED ? rf[S_DRGB + (r0 + g + hh * 8) * 3 + col] : d_rgb[pi * 3 + col];
+                dp[hh * 2 + e] = dr * s * (1.f - s) * loss_scale;
               }
             }
           }
@@ -219,8 +258,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     nsr_zero_acc(acc16);
     nsr_gemm_wt<1, 4, 2>(acc16, a_d, smem + NF_OFF_CW1, NF_LD32);  // first 16 input columns = the geometry features
     if (c == 0) {  // density path: d(out0) += d sigma / d raw (trunc_exp backward folded in by nsr_nerf_ray_bwd)
-      if (ia < n) acc16[0][0][0] += (xyzdir ? pre_ds[0] : d_sraw[pa]) * loss_scale;
-      if (ib < n) acc16[0][0][2] += (xyzdir ? pre_ds[1] : d_sraw[pb]) * loss_scale;
+      if (ia < n) acc16[0][0][0] += (PACKED ? rf[S_DS + r0 + g] : d_sraw[pa]) * loss_scale;
+      if (ib < n) acc16[0][0][2] += (PACKED ? rf[S_DS + r0 + g + 8] : d_sraw[pb]) * loss_scale;
     }
     uint32_t a_do[1][1][4];
     nsr_acc_to_afrag<1, 2>(acc16, a_do, NSR_ACT_NONE);
@@ -243,10 +282,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       const bool ok = i < n;
       float x = 0.f, y = 0.f, z = 0.f, dx, dy, dz;
       if (ok) {
-        if (xyzdir) {
-          x = pre_xyz[hh][0];
-          y = pre_xyz[hh][1];
-          z = pre_xyz[hh][2];
+        if (PACKED) {
+          const float* rr = rf + S_XYZ + (r0 + g + hh * 8) * 6;
+          x = rr[0];
+          y = rr[1];
+          z = rr[2];
         } else {
           nf_sample_position(P, rays, ray_indices[i], t_starts[i], t_ends[i], x, y, z, dx, dy, dz);
         }
@@ -307,7 +347,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
       const WgradTile w = wgrad_tile(warp + s * kWarps);
-      nsr_wgrad_tile(wacc[s][0], wacc[s][1], T + w.dy_off, w.ldy, w.m0, T + w.x_off, w.ldx, w.n0, kRows);
+      const int xo = (w.x_off == T_X0) ? x0_off : w.x_off;  // the encoded features live in the current double buffer
+      nsr_wgrad_tile(wacc[s][0], wacc[s][1], T + w.dy_off, w.ldy, w.m0, T + xo, w.ldx, w.n0, kRows);
     }
   }
 #pragma unroll
@@ -336,9 +377,11 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
               "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
   NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_nerf_field_bwd: loss_scale <= 0 (automatic) needs the amax pointer");
   if (k == 0) return 0;
+  NSR_REQUIRE(xyzdir == nullptr || row_pos == nullptr, "nsr_nerf_field_bwd: packed inputs (xyzdir) and row_pos are mutually exclusive");
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nerf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(nerf_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
       nsr_set_error("nsr_nerf_field_bwd: cannot reserve %zu B shared memory: %s", kSmemBytes, cudaGetErrorString(e));
       return 2;
@@ -348,9 +391,14 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
   const int64_t tiles = (k + kRows - 1) / kRows;
   int grid = (int)min((int64_t)nsr_sm_count() * kCtasPerSm, tiles);
   if (k_dev != nullptr) grid = nsr_sm_count() * kCtasPerSm;
-  nerf_bwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
-                                                                        (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                        grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
+  if (xyzdir != nullptr)
+    nerf_bwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
+                                                                                (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
+                                                                                grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
+  else
+    nerf_bwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
+                                                                                 (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
+                                                                                 grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
   return 0;
 }

@@ -110,8 +110,9 @@ class _NerfRenderRays(torch.autograd.Function):
         # plus (training, tile backward) the backward's inputs in packed row order: encodings, unit-cube position + view direction
         ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
         packed_bwd = need_grad and fused.bwd_kernel == 'tiles' and fused.packed_bwd_inputs
-        enc_k = torch.empty(cap, 32, dtype=torch.float16, device=dev) if packed_bwd else None
-        xyzdir = f32(cap, 6) if packed_bwd else None
+        # (+64 rows: the tile backward prefetches whole 64-row tiles with cp.async, the last one may reach past K)
+        enc_k = torch.empty(cap + 64, 32, dtype=torch.float16, device=dev) if packed_bwd else None
+        xyzdir = f32(cap + 64, 6) if packed_bwd else None
         lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
                  ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
         ctx.fused, ctx.n_rays, ctx.cap = fused, n, cap
@@ -142,9 +143,9 @@ class _NerfRenderRays(torch.autograd.Function):
                          ptr(weights), ptr(trans), ptr(kidx), ptr(dh), ptr(ch), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)),
                          ptr(f32(g_w)), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), float(fused.t_bound), ptr(tick), n, stream())
             else:
-                d_sraw = torch.empty(cap, device=dev)
-                d_rgb = torch.empty(cap, 3, device=dev)
-                packed = enc_k is not None   # gradients + encodings in packed row order: no index chains in front of the tile math
+                packed = enc_k is not None
+                d_sraw = torch.empty(cap + 64, device=dev)
+                d_rgb = torch.empty(cap + 64, 3, device=dev)   # gradients + encodings in packed row order: no index chains in front of the tile math
                 lib.call('nsr_nerf_ray_bwd_loose', ptr(offsets_m), ptr(kept), ptr(t_min), step, ptr(kidx), ptr(trans), ptr(weights), ptr(sig),
                          ptr(rgbs), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax),
                          ptr(offsets_k) if packed else None, n, stream())
