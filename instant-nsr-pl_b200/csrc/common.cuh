@@ -99,6 +99,25 @@ __device__ __forceinline__ void nsr_red_add_f32x2(float* addr, float a, float b)
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// 16-byte RED: two adjacent table entries (F = 2 features each) in one request; addr must be 16-byte aligned (sm_90+)
+__device__ __forceinline__ void nsr_red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// the two x-adjacent corners (i0 = x bit 0, i1 = x bit 1) of one (y, z) combination: when i1 == i0 ^ 1 (hashed levels: cx even;
+// dense levels: i0 even) the entries are neighbours in memory and one 16-byte RED carries both, otherwise two 8-byte REDs.
+__device__ __forceinline__ void nsr_red_corner_pair(float* grad_table, uint32_t i0, uint32_t i1, float a0, float a1, float b0, float b1) {
+  if (i1 == (i0 ^ 1u)) {
+    if (i0 & 1u)
+      nsr_red_add_f32x4(grad_table + 2 * (size_t)i1, b0, b1, a0, a1);
+    else
+      nsr_red_add_f32x4(grad_table + 2 * (size_t)i0, a0, a1, b0, b1);
+  } else {
+    nsr_red_add_f32x2(grad_table + 2 * (size_t)i0, a0, a1);
+    nsr_red_add_f32x2(grad_table + 2 * (size_t)i1, b0, b1);
+  }
+}
+
 __device__ __forceinline__ float2 nsr_ld_table(const __half2* table, uint32_t idx) {
   return __half22float2(__ldg(table + idx));
 }

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) dbg_scatter_kernel(const __grid_constant_
                                                           const __half2* __restrict__ denc, float* __restrict__ grad, int64_t n) {
   // VARIANT 0: thread per sample, red.v2.f32 | 1: thread per sample, 2 x red.f32 | 2: thread per sample, red.f16x2 (grad viewed as half2)
   // VARIANT 3: thread per (sample, level), red.v2.f32 | 4: thread per (sample, level), red.f16x2
+  // VARIANT 5: thread per sample, x-adjacent corner pairs as one red.v4.f32 when they are neighbours in memory
   const bool per_level = VARIANT >= 3;
   const int64_t total = per_level ? n * 16 : n;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
@@ -138,6 +139,14 @@ __global__ void __launch_bounds__(256) dbg_scatter_kernel(const __grid_constant_
       nsr_pos_fract(y, li.scale, cy, fy);
       nsr_pos_fract(z, li.scale, cz, fz);
       nsr_corner_indices(li, cx, cy, cz, idx);
+      if (VARIANT == 5) {
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          const float w0 = nsr_corner_weight(c, fx, fy, fz), w1 = nsr_corner_weight(c + 1, fx, fy, fz);
+          nsr_red_corner_pair(grad, idx[c], idx[c + 1], w0 * d.x, w0 * d.y, w1 * d.x, w1 * d.y);
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float w = nsr_corner_weight(c, fx, fy, fz);
@@ -174,6 +183,7 @@ extern "C" int nsr_dbg_scatter(const nsr_grid_t* g, const float* pos, const void
     case 2: return launch_scatter<2>(g, pos, denc_h, grad, n, st);
     case 3: return launch_scatter<3>(g, pos, denc_h, grad, n, st);
     case 4: return launch_scatter<4>(g, pos, denc_h, grad, n, st);
+    case 5: return launch_scatter<5>(g, pos, denc_h, grad, n, st);
   }
   NSR_REQUIRE(false, "nsr_dbg_scatter: unknown variant %d", variant);
 }

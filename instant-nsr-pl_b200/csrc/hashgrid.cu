@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(kThreads) hashgrid_bwd_kernel(nsr_grid_t g, co
       nsr_pos_fract(pz, li.scale, cz, fz);
       nsr_corner_indices(li, cx, cy, cz, idx);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float w = nsr_corner_weight(c, fx, fy, fz);
-        nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[c], w * dv.x, w * dv.y);
+      for (int c = 0; c < 8; c += 2) {  // x-adjacent corners: one 16-byte RED when they are neighbours in memory
+        const float w0 = nsr_corner_weight(c, fx, fy, fz), w1 = nsr_corner_weight(c + 1, fx, fy, fz);
+        nsr_red_corner_pair(grad_table, idx[c], idx[c + 1], w0 * dv.x, w0 * dv.y, w1 * dv.x, w1 * dv.y);
       }
     }
   }

@@ -54,7 +54,7 @@ k = int(n * 0.6)
 denc = (torch.randn(k, 32, device=dev) * 0.01).half()
 grad = torch.zeros(f.grid.n_params, device=dev)
 sres = {'k': k}
-for variant in (0, 1, 2, 3, 4):
+for variant in (0, 1, 2, 3, 4, 5):
     def run():
         lib.call('nsr_dbg_scatter', f.grid.ref(), ptr(pos), ptr(denc), ptr(grad), k, variant, stream())
     for _ in range(3):
@@ -67,4 +67,9 @@ for variant in (0, 1, 2, 3, 4):
         e0.record(); run(); e1.record(); torch.cuda.synchronize()
         ts_.append(e0.elapsed_time(e1))
     sres[f'v{variant}'] = round(sorted(ts_)[len(ts_) // 2] * 1e3, 1)
+    if variant == 0:
+        ref_grad = grad.clone()
+    elif variant == 5:   # the paired 16-byte REDs add up to the same table (atomic order aside)
+        grad.zero_(); run(); torch.cuda.synchronize()
+        assert (grad - ref_grad).abs().max().item() <= 1e-3 * ref_grad.abs().max().item(), 'v5 mismatch'
 print(json.dumps(sres))
