@@ -328,19 +328,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
           }
           if (ok && tail) {
             nsr_corner_indices(li, cx, cy, cz, idx);
-            // x-adjacent corners are neighbours in memory half of the time: one 16-byte RED instead of two 8-byte ones
-            // (scatter-only micro-benchmark: 262 -> 192 us, profiles/r1_gather_scatter_microbench.md)
+            // (pairing x-adjacent corners into one 16-byte RED, nsr_red_corner_pair, wins 27 % in the scatter-only micro-benchmark but
+            //  not here: 205 -> 209 us -- at 8 warps/SM the cost is per RED instruction, and the divergent pair test adds instructions)
 #pragma unroll
-            for (int cc = 0; cc < 8; cc += 2)
-              if (v[2 * cc] != 0.f || v[2 * cc + 1] != 0.f || v[2 * cc + 2] != 0.f || v[2 * cc + 3] != 0.f)
-                nsr_red_corner_pair(grad_table, idx[cc], idx[cc + 1], v[2 * cc], v[2 * cc + 1], v[2 * cc + 2], v[2 * cc + 3]);
+            for (int cc = 0; cc < 8; ++cc)
+              if (v[2 * cc] != 0.f || v[2 * cc + 1] != 0.f) nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], v[2 * cc], v[2 * cc + 1]);
           }
         } else if (ok && (d0 != 0.f || d1 != 0.f)) {
           nsr_corner_indices(li, cx, cy, cz, idx);
 #pragma unroll
-          for (int cc = 0; cc < 8; cc += 2) {
-            const float w0 = nsr_corner_weight(cc, fx, fy, fz), w1 = nsr_corner_weight(cc + 1, fx, fy, fz);
-            nsr_red_corner_pair(grad_table, idx[cc], idx[cc + 1], w0 * d0, w0 * d1, w1 * d0, w1 * d1);
+          for (int cc = 0; cc < 8; ++cc) {
+            const float w = nsr_corner_weight(cc, fx, fy, fz);
+            nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[cc], w * d0, w * d1);
           }
         }
       }

@@ -335,20 +335,13 @@ __global__ void __launch_bounds__(kThreads, 2) neus_field_bwd_kernel(const __gri
         }
       } else if (ok) {
         nsr_corner_indices(li, cx, cy, cz, idx);
-        // x-adjacent corner pairs: one 16-byte RED when the two entries are neighbours in memory (half of the time)
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          float pv[4];
-#pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const float wc = nsr_corner_weight(c + e2, fx, fy, fz);
-            const float coef = li.scale * (gx0 * nsr_corner_dweight(c + e2, 0, fx, fy, fz) + gx1 * nsr_corner_dweight(c + e2, 1, fx, fy, fz) +
-                                           gx2 * nsr_corner_dweight(c + e2, 2, fx, fy, fz));
-            pv[2 * e2] = wc * eb0 + coef * q0;
-            pv[2 * e2 + 1] = wc * eb1 + coef * q1;
-          }
-          if (pv[0] != 0.f || pv[1] != 0.f || pv[2] != 0.f || pv[3] != 0.f)
-            nsr_red_corner_pair(grad_table, idx[c], idx[c + 1], pv[0], pv[1], pv[2], pv[3]);
+        for (int c = 0; c < 8; ++c) {
+          const float wc = nsr_corner_weight(c, fx, fy, fz);
+          const float coef = li.scale * (gx0 * nsr_corner_dweight(c, 0, fx, fy, fz) + gx1 * nsr_corner_dweight(c, 1, fx, fy, fz) +
+                                         gx2 * nsr_corner_dweight(c, 2, fx, fy, fz));
+          const float v0 = wc * eb0 + coef * q0, v1 = wc * eb1 + coef * q1;
+          if (v0 != 0.f || v1 != 0.f) nsr_red_add_f32x2(grad_table + 2 * (size_t)idx[c], v0, v1);
         }
       }
     }
