@@ -193,7 +193,7 @@ def gpu_arm(args):
     import torch.distributed as dist
     from nsr_b200 import synthetic
     from nsr_b200.lib import lib
-    from nsr_b200.parallel import GradSync
+    from nsr_b200.parallel import make_grad_sync
     from nsr_b200.graph import GraphedStep
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -229,7 +229,12 @@ def gpu_arm(args):
     # the public fast path: whole step (march .. backward) as one CUDA graph, no host sync inside
     # N > 1: the NCCL all-reduce (mean) of the parameter gradients is captured into the same graph, right behind the backward
     comm = os.environ.get('NSR_GRAD_COMM_DTYPE', 'fp32')  # 'bf16': opt-in wire compression of the table gradient
-    sync = GradSync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None)) if world > 1 else None
+    # exchange: our own reduce-scatter + all-gather kernel over NVLink peer memory (csrc/p2p.cu); NCCL if symmetric memory / P2P is
+    # unavailable, if NSR_GRAD_SYNC=nccl, or for the bf16 wire format
+    sync, sync_desc = (None, None)
+    if world > 1:
+        sync, sync_desc = make_grad_sync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None),
+                                         prefer_p2p=os.environ.get('NSR_GRAD_SYNC', 'p2p') != 'nccl')
     gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
                         post_backward=(sync.all_reduce_mean if sync is not None else None))
 
@@ -311,6 +316,8 @@ def gpu_arm(args):
         marched += mm / POOL
         kept += kk / POOL
     if world > 1:
+        if hasattr(sync, 'check'):
+            sync.check()
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
@@ -395,7 +402,7 @@ def gpu_arm(args):
                    'rays_per_gpu': N_RAYS, 'marched_samples_per_step': marched, 'kept_samples_per_step': kept,
                    'samples_per_s': kept * args.steps / (ms * 1e-3), 'l2': 'flushed (256 MB write) before every timed step',
                    'parallelism': f'dp{world}' if world > 1 else 'single',
-                   'step': 'mask march + per-ray forward (early termination) + fused smooth-L1 loss + backward, one CUDA graph (nsr_b200.graph.GraphedStep)' + (f' + NCCL all-reduce of grads ({comm})' if world > 1 else ''),
+                   'step': 'mask march + per-ray forward (early termination) + fused smooth-L1 loss + backward, one CUDA graph (nsr_b200.graph.GraphedStep)' + (f' + gradient mean over the ranks: {sync_desc}' if world > 1 else ''),
                    'eager_api_ms_per_step': ms_eager},
         'e2e': {'value': N_RAYS * world * args.steps / (ms_e2e * 1e-3), 'unit': 'rays/s',
                 'h2d_bytes_per_step': N_RAYS * 6 * 4 + N_RAYS * 3 * 4, 'd2h_bytes_per_step': 4},

@@ -302,6 +302,17 @@ int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* di
                      const void* params_h, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
                      float* grad_params, int64_t n, const int64_t* n_dev, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory (replaces the NCCL all-reduce of Lightning DDP, launch.py:98) ---------
+ * Every rank holds its flat fp32 gradient vector in a peer-mapped (symmetric) buffer of n floats (n % 4 == 0).
+ * nsr_p2p_barrier: all-ranks barrier on the stream: flags = one peer-mapped int32[>= world] array per rank (zeroed once),
+ *   flag_ptrs_host[q] = address of rank q's array in THIS process; epoch_dev / err_dev: local device int32 (zeroed once;
+ *   *err_dev becomes 1 if a peer never arrived within the spin bound).
+ * nsr_p2p_allreduce_mean: in-place mean over the ranks; rank r reduces chunk r (P2P loads from peer_ptrs_host[q], or one
+ *   multimem.ld_reduce on multicast_ptr when the buffer has an NVSwitch multicast mapping) and writes it into every replica.
+ *   Must be bracketed by barriers: barrier, allreduce, barrier. */
+int nsr_p2p_barrier(const uint64_t* flag_ptrs_host, int32_t* epoch_dev, int32_t* err_dev, int32_t rank, int32_t world, void* stream);
+int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* multicast_ptr, int32_t rank, int32_t world, int64_t n, void* stream);
+
 /* ---- occupancy-grid refresh (nerfacc OccupancyGrid._update behind every_n_step: models/nerf.py:45-55,
  * models/neus.py:79-111).  The caller draws the cells (int64 flat indices ix*R*R + iy*R + iz; NULL = every cell once) and the
  * in-cell jitter U[0,1)^3, evaluates its occ function on the returned world points, then:

@@ -1,0 +1,120 @@
+// Gradient all-reduce (mean) over NVLink peer memory -- the one exchange step of the data-parallel path (what the
+// reference gets from Lightning DDP / NCCL, launch.py:98).  Every rank's flat gradient buffer lives in symmetric memory (same
+// size, peer-mapped); after the backward
+//     barrier  -> every rank's gradients are complete and visible
+//     reduce   -> rank r owns chunk r: it sums the chunk over all peers (P2P loads, or ONE multimem.ld_reduce when the buffer has
+//                 an NVSwitch multicast mapping: the switch adds the replicas), scales by 1/world and writes the result straight
+//                 into every peer's buffer (P2P stores / multimem.st): reduce-scatter and all-gather in one kernel, in place
+//     barrier  -> all chunks have landed everywhere
+// Chunks are disjoint, so the in-place update is race free.  Barriers are monotonically increasing epochs in a peer-mapped flag
+// array (st.release.sys / ld.acquire.sys), with a bounded spin so that a lost peer sets an error flag instead of hanging the GPU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr long long kSpinLimit = 1LL << 28;  // ~ a few seconds of polling
+
+// flags layout (int32, per rank, peer-mapped): flags[p] = last epoch signalled by rank p
+struct FlagPeers {
+  int32_t* p[kMaxWorld];
+};
+
+__global__ void p2p_barrier_kernel(const FlagPeers flags, int32_t* __restrict__ epoch, int32_t* __restrict__ err, int rank, int world) {
+  __shared__ int e_s;
+  if (threadIdx.x == 0) e_s = atomicAdd(epoch, 1) + 1;
+  __syncthreads();
+  const int e = e_s, p = threadIdx.x;
+  if (p < world) {
+    __threadfence_system();
+    int32_t* dst = flags.p[p] + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
+    const int32_t* src = flags.p[rank] + p;
+    long long spins = 0;
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    } while (v - e < 0 && ++spins < kSpinLimit);
+    if (v - e < 0) atomicExch(err, 1);
+  }
+}
+
+struct Peers {
+  float4* p[kMaxWorld];
+};
+
+__global__ void __launch_bounds__(256) p2p_allreduce_mean_kernel(const Peers peers, int rank, int world, int64_t n4, float inv) {
+  const int64_t chunk = (n4 + world - 1) / world;
+  const int64_t lo = rank * chunk, hi = min(n4, lo + chunk);
+  for (int64_t i = lo + blockIdx.x * 256ll + threadIdx.x; i < hi; i += (int64_t)gridDim.x * 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q) {
+      if (q < world) {  // fixed summation order 0..world-1; the owner broadcasts ONE result, so all replicas stay bit-identical
+        const float4 v = __ldcv(peers.p[q] + i);  // never from a stale cache line: peers wrote this memory over NVLink
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+    }
+    acc.x *= inv;
+    acc.y *= inv;
+    acc.z *= inv;
+    acc.w *= inv;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q < world) peers.p[q][i] = acc;
+  }
+}
+
+// NVSwitch multicast variant: the switch reduces the replicas on the load and broadcasts the store
+__global__ void __launch_bounds__(256) p2p_allreduce_mean_multimem_kernel(float* __restrict__ mc, int rank, int world, int64_t n4, float inv) {
+  const int64_t chunk = (n4 + world - 1) / world;
+  const int64_t lo = rank * chunk, hi = min(n4, lo + chunk);
+  for (int64_t i = lo + blockIdx.x * 256ll + threadIdx.x; i < hi; i += (int64_t)gridDim.x * 256) {
+    float4 v;
+    float* a = mc + i * 4;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(a)
+                 : "memory");
+    v.x *= inv;
+    v.y *= inv;
+    v.z *= inv;
+    v.w *= inv;
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int nsr_p2p_barrier(const uint64_t* flag_ptrs_host, int32_t* epoch_dev, int32_t* err_dev, int32_t rank, int32_t world, void* stream) {
+  NSR_REQUIRE(flag_ptrs_host != nullptr && epoch_dev != nullptr && err_dev != nullptr, "nsr_p2p_barrier: NULL argument");
+  NSR_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "nsr_p2p_barrier: bad rank / world (max %d)", kMaxWorld);
+  FlagPeers fl;
+  for (int q = 0; q < kMaxWorld; ++q) fl.p[q] = q < world ? reinterpret_cast<int32_t*>(flag_ptrs_host[q]) : nullptr;
+  p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fl, epoch_dev, err_dev, rank, world);
+  NSR_CHECK_LAUNCH("nsr_p2p_barrier");
+  return 0;
+}
+
+extern "C" int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* multicast_ptr, int32_t rank, int32_t world, int64_t n,
+                                      void* stream) {
+  NSR_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "nsr_p2p_allreduce_mean: bad rank / world (max %d)", kMaxWorld);
+  NSR_REQUIRE(n % 4 == 0, "nsr_p2p_allreduce_mean: n must be a multiple of 4 floats");
+  NSR_REQUIRE(multicast_ptr != nullptr || peer_ptrs_host != nullptr, "nsr_p2p_allreduce_mean: no peer pointers");
+  if (n == 0 || world == 1) return 0;
+  const int64_t n4 = n / 4, chunk = (n4 + world - 1) / world;
+  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * 4, (chunk + 255) / 256));
+  const float inv = 1.f / (float)world;
+  if (multicast_ptr != nullptr) {
+    p2p_allreduce_mean_multimem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)multicast_ptr, rank, world, n4, inv);
+  } else {
+    Peers peers;
+    for (int q = 0; q < kMaxWorld; ++q) peers.p[q] = q < world ? reinterpret_cast<float4*>(peer_ptrs_host[q]) : nullptr;
+    p2p_allreduce_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, n4, inv);
+  }
+  NSR_CHECK_LAUNCH("nsr_p2p_allreduce_mean");
+  return 0;
+}

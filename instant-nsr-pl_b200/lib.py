@@ -102,6 +102,8 @@ _SIGNATURES = {
     'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P, P],
     'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P, P],
+    'nsr_p2p_barrier': [P, P, P, I32, I32, P],
+    'nsr_p2p_allreduce_mean': [P, P, I32, I32, I64, P],
     'nsr_occgrid_points': [P, P, P, P, P, I64, P],
     'nsr_occgrid_update': [P, P, P, P, F32, P, I64, I64, P],
     'nsr_occgrid_binarize': [P, P, F32, P, P, P, I32, I64, P],

@@ -42,6 +42,82 @@ class GradSync:
             g.mul_(inv)
 
 
+class P2PGradSync:
+    """The same mean, as OUR kernels over NVLink peer memory instead of NCCL (csrc/p2p.cu): the flat gradient vector of every rank
+    lives in a symmetric (peer-mapped) buffer; ``all_reduce_mean`` = copy-in, barrier, one in-place reduce-scatter + all-gather
+    kernel (rank r sums chunk r over the peers -- in the NVSwitch when the buffer has a multicast mapping -- and writes it into
+    every replica), barrier; afterwards ``p.grad`` IS the view of the symmetric buffer that holds the mean (no copy-out).
+    Capturable into the step's CUDA graph (no NCCL call inside).  Needs torch.distributed._symmetric_memory (CUDA backend) and P2P
+    access between the ranks' GPUs; ``make_grad_sync`` falls back to NCCL when that is not available."""
+
+    def __init__(self, params, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.params = [p for p in params if p.requires_grad and p.numel() > 0]
+        if not self.params or not self.params[0].is_cuda:
+            raise RuntimeError('P2PGradSync needs CUDA parameters')
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = self.params[0].device
+        if hasattr(symm, 'enable_symm_mem_for_group') and not symm.is_symm_mem_enabled_for_group(group.group_name):
+            symm.enable_symm_mem_for_group(group.group_name)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]       # every slice 16-byte aligned
+        self.n = sum(sizes)
+        self.buf = symm.empty(self.n, dtype=torch.float32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.flags = symm.empty(64, dtype=torch.int32, device=dev)
+        self.fhdl = symm.rendezvous(self.flags, group)
+        self.buf.zero_()
+        self.flags.zero_()
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.views, off = [], 0
+        for p, sz in zip(self.params, sizes):
+            self.views.append(self.buf[off:off + p.numel()].view_as(p))
+            off += sz
+        A = ctypes.c_uint64 * self.world
+        self._peer = A(*[int(x) for x in self.hdl.buffer_ptrs])
+        self._fpeer = A(*[int(x) for x in self.fhdl.buffer_ptrs])
+        mc = int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
+        self.multicast = mc if (mc and self.n % (4 * self.world) == 0) else 0
+        torch.cuda.synchronize()
+        dist.barrier(group)   # every rank has zeroed its flags before anyone signals
+
+    def all_reduce_mean(self):
+        import ctypes
+        from .lib import lib, ptr, stream
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+        bar = lambda: lib.call('nsr_p2p_barrier', self._fpeer, ptr(self.epoch), ptr(self.err), self.rank, self.world, stream())
+        bar()
+        lib.call('nsr_p2p_allreduce_mean', self._peer, ctypes.c_void_p(self.multicast) if self.multicast else None, self.rank, self.world,
+                 self.n, stream())
+        bar()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def check(self):
+        """host-side check of the device error flag (a peer that never reached a barrier); one sync."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError('P2PGradSync: a peer did not reach the barrier within the spin bound')
+
+
+def make_grad_sync(params, world, group=None, comm_dtype=None, prefer_p2p=True):
+    """-> (sync object with .all_reduce_mean(), description).  P2P kernels over NVLink when available, NCCL otherwise."""
+    params = list(params)
+    if world > 1 and prefer_p2p and comm_dtype is None and params and params[0].is_cuda:
+        try:
+            s = P2PGradSync(params, group)
+            return s, 'nsr p2p kernels over NVLink peer memory' + (' (NVSwitch multicast reduce)' if s.multicast else ' (P2P loads/stores)')
+        except Exception as e:  # symmetric memory / P2P mapping unavailable: NCCL does the same exchange
+            why = f'{type(e).__name__}: {e}'.splitlines()[0][:160]
+            return GradSync(params, world, group, comm_dtype), f'NCCL all-reduce (p2p unavailable: {why})'
+    return GradSync(params, world, group, comm_dtype), 'NCCL all-reduce' + (f' ({comm_dtype})' if comm_dtype is not None else '')
+
+
 def shard_rays(rays, rank, world):
     """contiguous shard of a [N, 6] ray batch for this rank (N divisible by world, SURVEY 8e: 65,536 / 8)."""
     n = rays.shape[0] // world

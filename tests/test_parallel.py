@@ -26,6 +26,10 @@ def _worker(rank, world, port, q):
     for i, p in enumerate(params):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     GradSync(params, world).all_reduce_mean()
+    # make_grad_sync: CPU parameters / no symmetric memory -> the NCCL-style path (here gloo) with a description saying so
+    from nsr_b200.parallel import make_grad_sync
+    s2, desc = make_grad_sync(params, world)
+    assert isinstance(s2, GradSync) and 'all-reduce' in desc
     rays = torch.arange(8 * 6, dtype=torch.float32).view(8, 6)
     mine = shard_rays(rays, rank, world)
     q.put((rank, [float(p.grad.flatten()[0]) for p in params], mine[:, 0].tolist()))

@@ -1,0 +1,58 @@
+"""2+ GPU check of the NVLink peer-memory gradient exchange (csrc/p2p.cu) against NCCL, with timings.  Launch:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+dist.init_process_group('nccl', device_id=dev)
+from nsr_b200.parallel import make_grad_sync, GradSync, P2PGradSync
+
+n_big = 12602992
+params = [torch.nn.Parameter(torch.zeros(n_big, device=dev)), torch.nn.Parameter(torch.zeros(7168, device=dev)), torch.nn.Parameter(torch.zeros(3, device=dev))]
+out = {'rank': rank, 'world': world}
+try:
+    for variant in ('p2p', 'multimem'):
+        sync, desc = make_grad_sync(params, world)
+        out['desc'] = desc
+        if not isinstance(sync, P2PGradSync):
+            break
+        if variant == 'p2p':
+            sync.multicast = 0
+        elif not sync.multicast:
+            out['multimem'] = 'no multicast mapping'
+            break
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        grads = [torch.randn(p.shape, device=dev, generator=g) for p in params]
+        ref = [x.clone() for x in grads]
+        for r in ref:
+            dist.all_reduce(r)
+            r.div_(world)
+        for p, x in zip(params, grads):
+            p.grad = x.clone()
+        sync.all_reduce_mean()
+        torch.cuda.synchronize()
+        sync.check()
+        err = max(float((p.grad - r).abs().max()) for p, r in zip(params, ref))
+        out[variant + '_max_err'] = err
+        # timing: copy-in + barrier + reduce + barrier, vs NCCL all-reduce + scale
+        nccl = GradSync(params, world)
+        for name, fn in ((variant, sync.all_reduce_mean), ('nccl', nccl.all_reduce_mean)):
+            ts = []
+            for i in range(12):
+                for p, x in zip(params, grads):
+                    p.grad = x.clone()
+                dist.barrier(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            out[name + '_ms'] = round(sorted(ts[2:])[len(ts[2:]) // 2], 4)
+        sync.check()
+except Exception as e:
+    out['error'] = f'{type(e).__name__}: {e}'[:300]
+print(json.dumps(out), flush=True)
+sys.stdout.flush()
+os._exit(0)
