@@ -43,28 +43,46 @@ struct Peers {
   float4* p[kMaxWorld];
 };
 
+// U independent float4 columns per thread per iteration: all world x U remote loads are in flight before the first add
+// (NVLink round trips are ~2-3 us; one load per thread leaves the links mostly idle)
+template <int U>
 __global__ void __launch_bounds__(256) p2p_allreduce_mean_kernel(const Peers peers, int rank, int world, int64_t n4, float inv) {
   const int64_t chunk = (n4 + world - 1) / world;
   const int64_t lo = rank * chunk, hi = min(n4, lo + chunk);
-  for (int64_t i = lo + blockIdx.x * 256ll + threadIdx.x; i < hi; i += (int64_t)gridDim.x * 256) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t span = 256ll * U;
+  for (int64_t base = lo + blockIdx.x * span; base < hi; base += (int64_t)gridDim.x * span) {
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < kMaxWorld; ++q) {
       if (q < world) {  // fixed summation order 0..world-1; the owner broadcasts ONE result, so all replicas stay bit-identical
-        const float4 v = __ldcv(peers.p[q] + i);  // never from a stale cache line: peers wrote this memory over NVLink
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = base + u * 256 + threadIdx.x;
+          // never from a stale cache line: peers wrote this memory over NVLink
+          v[u] = i < hi ? __ldcv(peers.p[q] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[u].x += v[u].x;
+          acc[u].y += v[u].y;
+          acc[u].z += v[u].z;
+          acc[u].w += v[u].w;
+        }
       }
     }
-    acc.x *= inv;
-    acc.y *= inv;
-    acc.z *= inv;
-    acc.w *= inv;
 #pragma unroll
-    for (int q = 0; q < kMaxWorld; ++q)
-      if (q < world) peers.p[q][i] = acc;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < hi) {
+        const float4 r = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
+#pragma unroll
+        for (int q = 0; q < kMaxWorld; ++q)
+          if (q < world) peers.p[q][i] = r;
+      }
+    }
   }
 }
 
@@ -106,14 +124,15 @@ extern "C" int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* mult
   NSR_REQUIRE(multicast_ptr != nullptr || peer_ptrs_host != nullptr, "nsr_p2p_allreduce_mean: no peer pointers");
   if (n == 0 || world == 1) return 0;
   const int64_t n4 = n / 4, chunk = (n4 + world - 1) / world;
-  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * 4, (chunk + 255) / 256));
+  constexpr int kU = 4;
+  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * 4, (chunk + 256 * kU - 1) / (256 * kU)));
   const float inv = 1.f / (float)world;
   if (multicast_ptr != nullptr) {
     p2p_allreduce_mean_multimem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)multicast_ptr, rank, world, n4, inv);
   } else {
     Peers peers;
     for (int q = 0; q < kMaxWorld; ++q) peers.p[q] = q < world ? reinterpret_cast<float4*>(peer_ptrs_host[q]) : nullptr;
-    p2p_allreduce_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, n4, inv);
+    p2p_allreduce_mean_kernel<kU><<<grid, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, n4, inv);
   }
   NSR_CHECK_LAUNCH("nsr_p2p_allreduce_mean");
   return 0;

@@ -50,6 +50,14 @@ try:
                 e0.record(); fn(); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             out[name + '_ms'] = round(sorted(ts[2:])[len(ts[2:]) // 2], 4)
+        # exchange alone (gradients already in the symmetric buffer: p.grad IS the view => no copy-in)
+        ts = []
+        for i in range(12):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); sync.all_reduce_mean(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out[variant + '_no_copy_ms'] = round(sorted(ts[2:])[len(ts[2:]) // 2], 4)
         sync.check()
 except Exception as e:
     out['error'] = f'{type(e).__name__}: {e}'[:300]
