@@ -62,7 +62,7 @@ class P2PGradSync:
         if hasattr(symm, 'enable_symm_mem_for_group') and not symm.is_symm_mem_enabled_for_group(group.group_name):
             symm.enable_symm_mem_for_group(group.group_name)
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]       # every slice 16-byte aligned
-        self.n = sum(sizes)
+        self.n = (sum(sizes) + 4 * self.world - 1) // (4 * self.world) * (4 * self.world)   # equal float4 chunks per rank
         self.buf = symm.empty(self.n, dtype=torch.float32, device=dev)
         self.hdl = symm.rendezvous(self.buf, group)
         self.flags = symm.empty(64, dtype=torch.int32, device=dev)
@@ -79,7 +79,14 @@ class P2PGradSync:
         self._peer = A(*[int(x) for x in self.hdl.buffer_ptrs])
         self._fpeer = A(*[int(x) for x in self.fhdl.buffer_ptrs])
         mc = int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
-        self.multicast = mc if (mc and self.n % (4 * self.world) == 0) else 0
+        # NVSwitch multicast reduce (multimem.ld_reduce / multimem.st): NSR_P2P_MULTIMEM = 1 | 0 | auto.  Measured on 2 x B200: plain P2P
+        # loads/stores 0.118 ms vs 0.17 ms through the multicast mapping for the 50 MB exchange, so auto uses it only from 4 ranks up
+        # (in-switch reduction moves 1/world of the bytes per GPU).
+        import os
+        want = os.environ.get('NSR_P2P_MULTIMEM', 'auto')
+        use_mc = mc != 0 and (want == '1' or (want == 'auto' and self.world >= 4))
+        self.multicast_available = mc != 0
+        self.multicast = mc if use_mc else 0
         torch.cuda.synchronize()
         dist.barrier(group)   # every rank has zeroed its flags before anyone signals
 
@@ -99,6 +106,29 @@ class P2PGradSync:
         for p, v in zip(self.params, self.views):
             p.grad = v
 
+    def self_test(self, group=None):
+        """one exchange of a rank-dependent pattern, compared with torch.distributed's all-reduce; False => do not use this path."""
+        saved = [p.grad for p in self.params]
+        try:
+            gen = torch.Generator(device=self.buf.device).manual_seed(1234 + self.rank)
+            pat = [torch.randn(p.shape, device=p.device, generator=gen) for p in self.params]
+            ref = [x.clone() for x in pat]
+            for r in ref:
+                dist.all_reduce(r, group=group)
+                r.div_(self.world)
+            for p, x in zip(self.params, pat):
+                p.grad = x
+            self.all_reduce_mean()
+            torch.cuda.synchronize()
+            ok = int(self.err.item()) == 0 and all(bool(torch.allclose(p.grad, r, rtol=1e-5, atol=1e-6)) for p, r in zip(self.params, ref))
+        except Exception:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=self.buf.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # every rank takes the same decision
+        for p, g in zip(self.params, saved):
+            p.grad = g
+        return bool(flag.item())
+
     def check(self):
         """host-side check of the device error flag (a peer that never reached a barrier); one sync."""
         if int(self.err.item()) != 0:
@@ -111,6 +141,8 @@ def make_grad_sync(params, world, group=None, comm_dtype=None, prefer_p2p=True):
     if world > 1 and prefer_p2p and comm_dtype is None and params and params[0].is_cuda:
         try:
             s = P2PGradSync(params, group)
+            if not s.self_test(group):
+                return GradSync(params, world, group, comm_dtype), 'NCCL all-reduce (p2p self-test failed)'
             return s, 'nsr p2p kernels over NVLink peer memory' + (' (NVSwitch multicast reduce)' if s.multicast else ' (P2P loads/stores)')
         except Exception as e:  # symmetric memory / P2P mapping unavailable: NCCL does the same exchange
             why = f'{type(e).__name__}: {e}'.splitlines()[0][:160]

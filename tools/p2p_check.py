@@ -22,9 +22,11 @@ try:
             break
         if variant == 'p2p':
             sync.multicast = 0
-        elif not sync.multicast:
+        elif not sync.multicast_available:
             out['multimem'] = 'no multicast mapping'
             break
+        else:
+            sync.multicast = int(sync.hdl.multicast_ptr)
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         grads = [torch.randn(p.shape, device=dev, generator=g) for p in params]
         ref = [x.clone() for x in grads]
