@@ -235,8 +235,12 @@ def gpu_arm(args):
     if world > 1:
         sync, sync_desc = make_grad_sync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None),
                                          prefer_p2p=os.environ.get('NSR_GRAD_SYNC', 'p2p') != 'nccl')
+    # inside the graph only what the fused loss reads is materialised (comp_rgb / rays_valid come out of nsr_nerf_loss_fwd itself)
+    model._fused.lean_static_outputs = True
     gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
                         post_backward=(sync.all_reduce_mean if sync is not None else None))
+
+    model._fused.lean_static_outputs = False   # (captured already; the eager API below returns the full dict)
 
     def step(rays, target, do_sync=True):
         bg = torch.rand(3, device=dev)                      # systems/nerf.py:71 (random background per step)

@@ -339,8 +339,9 @@ int nsr_grad_nonfinite(const float* grads, float* found_inf, int64_t n, void* st
 
 /* ---- training-step back end (systems/nerf.py:68-97) ---------------------------------------------------
  * background blend + masked smooth-L1 over the valid rays: comp = acc_rgb + bg (1 - opacity), valid = opacity > 0,
- * loss = sum smooth_l1(comp - target) / max(3 n_valid, 1).  accum2: device float[2] (loss sum, n_valid), zeroed by the
- * caller; comp_rgb [n,3] optional output.  The backward writes dL/d acc_rgb and dL/d opacity. */
+ * loss = sum smooth_l1(comp - target) / max(3 n_valid, 1).  accum: device float[4], zeroed by the entry point:
+ * [0] loss sum, [1] n_valid, [2] the loss (written by a one-thread epilogue); comp_rgb [n,3] optional output.
+ * The backward writes dL/d acc_rgb and dL/d opacity. */
 int nsr_nerf_loss_fwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, float* comp_rgb, float* accum2,
                       int64_t n_rays, void* stream);
 int nsr_nerf_loss_bwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, const float* accum2,

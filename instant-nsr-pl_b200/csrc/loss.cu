@@ -78,11 +78,23 @@ __global__ void __launch_bounds__(256) nerf_loss_bwd_kernel(const float* __restr
 
 }  // namespace
 
+namespace {
+// accum[2] = loss = sum / max(3 n_valid, 1)
+__global__ void nerf_loss_finalize_kernel(float* __restrict__ accum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) accum[2] = accum[0] / fmaxf(accum[1] * 3.f, 1.f);
+}
+}  // namespace
+
 extern "C" int nsr_nerf_loss_fwd(const float* acc_rgb, const float* opacity, const float* bg3, const float* target, float* comp_rgb,
-                                 float* accum2, int64_t n_rays, void* stream) {
-  if (n_rays == 0) return 0;
-  const int grid = (int)min((int64_t)nsr_sm_count(), (n_rays + 255) / 256);
-  nerf_loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc_rgb, opacity, bg3, target, comp_rgb, accum2, n_rays);
+                                 float* accum4, int64_t n_rays, void* stream) {
+  NSR_REQUIRE(accum4 != nullptr, "nsr_nerf_loss_fwd: accum is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(accum4, 0, 4 * sizeof(float), st);
+  if (n_rays > 0) {
+    const int grid = (int)min((int64_t)nsr_sm_count(), (n_rays + 255) / 256);
+    nerf_loss_fwd_kernel<<<grid, 256, 0, st>>>(acc_rgb, opacity, bg3, target, comp_rgb, accum4, n_rays);
+  }
+  nerf_loss_finalize_kernel<<<1, 32, 0, st>>>(accum4);
   NSR_CHECK_LAUNCH("nsr_nerf_loss_fwd");
   return 0;
 }

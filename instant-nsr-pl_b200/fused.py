@@ -100,7 +100,8 @@ class _NerfRenderRays(torch.autograd.Function):
         acc_rgb, opacity, depth, kept = f32(n, 3), f32(n, 1), f32(n, 1), i32(n)
         offsets_k = i64(n + 1)
         dh, ch = fused.dparams_half(), fused.cparams_half()
-        tick = torch.zeros(1, dtype=torch.int32, device=dev)
+        zz = torch.zeros(2, dtype=torch.int32, device=dev)   # one fill: the forward's ray ticket + the backward's gradient amax
+        tick, amax0 = zz[0:1], zz[1:2].view(torch.float32)
         step = float(m.render_step_size)
         lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
@@ -120,15 +121,14 @@ class _NerfRenderRays(torch.autograd.Function):
         if packed_bwd:
             enc = None   # the loose copy is not needed any more
         ctx.save_for_backward(rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch,
-                              enc_k, xyzdir)
-        counts_mk = torch.cat([offsets_m[n:], offsets_k[n:]])  # [M, K] on the device
-        ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k, counts_mk)
-        return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, counts_mk
+                              enc_k, xyzdir, amax0)
+        ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k)
+        return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k
 
     @staticmethod
     def backward(ctx, g_rgb, g_op, g_depth, g_w, *_):
         fused = ctx.fused
-        rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch, enc_k, xyzdir = ctx.saved_tensors
+        rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch, enc_k, xyzdir, amax0 = ctx.saved_tensors
         dev = rays.device
         n, cap = ctx.n_rays, ctx.cap
         step = float(fused.model.render_step_size)
@@ -136,7 +136,7 @@ class _NerfRenderRays(torch.autograd.Function):
         gc = torch.zeros(fused.n_cparams, device=dev)
         if (enc is not None or enc_k is not None) and n > 0:
             f32 = lambda t: None if t is None else contig(t, torch.float32)
-            amax = torch.zeros(1, device=dev)
+            amax = amax0   # zeroed together with the forward's ticket (a retained-graph second backward only makes the scale smaller)
             if fused.bwd_kernel == 'rays':
                 tick = torch.zeros(1, dtype=torch.int32, device=dev)
                 lib.call('nsr_nerf_rays_bwd', fused.ref(), ptr(rays), ptr(t_min), ptr(offsets_m), ptr(kept), step, ptr(enc), ptr(sig), ptr(rgbs),
@@ -180,6 +180,7 @@ class NerfFused:
         self.last_stats = {}
         self._ticket = None
         self.mode = 'per_ray'   # 'per_ray' (persistent per-ray forward kernel) | 'two_pass' (pre-pass / compaction / sample-tile kernels)
+        self.lean_static_outputs = False   # static=True: skip the per-ray outputs the fused loss op produces itself (comp_rgb, rays_valid)
         self.packed_bwd_inputs = True   # tile backward reads its inputs in packed row order (written by nsr_pack_kept)
         self.bwd_kernel = 'tiles'  # 'tiles' (sample-tile backward through the packed->loose index) | 'rays' (single per-ray backward kernel)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
@@ -278,11 +279,17 @@ class NerfFused:
         rays = contig(rays, torch.float32)
         if self.mode == 'two_pass':
             return self._render_two_pass(rays, jitter, static)
-        acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, counts = _NerfRenderRays.apply(
+        acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k = _NerfRenderRays.apply(
             self.net.params, self.cnet.params, self, rays, jitter)
-        comp_rgb = acc_rgb + m.background_color * (1.0 - opacity)
-        out = {'comp_rgb': comp_rgb, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
-               'num_samples': counts[1:].to(torch.int32)}
+        n = rays.shape[0]
+        counts = (offsets_m[n:], offsets_k[n:])   # (marched, kept) on the device
+        if static and self.lean_static_outputs:
+            # graph capture with the fused loss: comp_rgb / rays_valid come out of nsr_nerf_loss_fwd, nothing else reads them
+            out = {'opacity': opacity, 'depth': depth, 'num_samples_dev': counts[1]}
+        else:
+            comp_rgb = acc_rgb + m.background_color * (1.0 - opacity)
+            out = {'comp_rgb': comp_rgb, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
+                   'num_samples': counts[1].to(torch.int32)}
         if static:
             self.last_stats = {'counts_dev': counts}
             out['acc_rgb'] = acc_rgb  # pre-blend per-ray colour sum (input of nsr_b200.losses.nerf_rgb_loss)
@@ -292,7 +299,7 @@ class NerfFused:
                 out.update({'weights': weights, 't_starts': ts, 't_ends': te, 'ray_indices': ri, 'loose_pos': pos,
                             'offsets_loose': offsets_m, 'offsets_packed': offsets_k})
             return out
-        n_marched, k = counts.tolist()
+        n_marched, k = torch.cat(counts).tolist()
         self.last_stats = {'n_marched': n_marched, 'n_kept': k}
         if m.training:
             ts_, te_ = ts[:k], te[:k]

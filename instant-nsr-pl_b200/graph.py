@@ -81,4 +81,5 @@ class GraphedStep:
 
     def counts(self):
         """(n_marched, n_kept) of the last replay -- one device->host read."""
-        return tuple(self.model._fused.last_stats['counts_dev'].tolist())
+        c = self.model._fused.last_stats['counts_dev']
+        return tuple((torch.cat(list(c)) if isinstance(c, (tuple, list)) else c).tolist())

@@ -16,13 +16,12 @@ class _NerfRgbLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, acc_rgb, opacity, bg, target):
         n = acc_rgb.shape[0]
-        accum = torch.zeros(2, device=acc_rgb.device)
+        accum = torch.empty(4, device=acc_rgb.device)   # zeroed by the entry point; [2] = the loss
         comp = torch.empty_like(acc_rgb)
         lib.call('nsr_nerf_loss_fwd', ptr(acc_rgb), ptr(opacity), ptr(bg), ptr(target), ptr(comp), ptr(accum), n, stream())
         ctx.save_for_backward(acc_rgb, opacity, bg, target, accum)
         ctx.mark_non_differentiable(comp)
-        loss = accum[0] / torch.clamp(accum[1] * 3.0, min=1.0)
-        return loss, comp
+        return accum[2], comp
 
     @staticmethod
     def backward(ctx, g_loss, _g_comp):
