@@ -388,15 +388,27 @@ def gpu_arm(args):
                  'algorithmic_bytes': opt_bytes, 'achieved_GBps': opt_bytes / (opt_ms * 1e-3) / 1e9,
                  'frac_of_hbm_peak': opt_bytes / (opt_ms * 1e-3) / 1e9 / peak, 'all_tensors_ms': opt_ms_all,
                  'train_step_ms_with_optimizer': ms_step + opt_ms_all}
+    # DRAM traffic of the dominant kernel from the committed ncu capture (per launch, same workload): far BELOW the algorithmic bytes
+    # because the table and its gradient are L2 resident
+    ncu_info = {}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_traffic.json')) as fh:
+            ncu_info = json.load(fh)
+    except (OSError, ValueError):
+        pass
+    if roofline is not None and dom in ncu_info:
+        roofline['traffic'] = ncu_info[dom].get('dram_bytes_per_launch')
+        roofline['traffic_source'] = ncu_info.get('source')
     if roofline is not None and dom == 'nsr_nerf_field_bwd':
         # the table (25 MB fp16) and its gradient (50 MB fp32) live in the 126 MB L2: the kernel's real ceiling is the L2 atomic unit.
-        # 79.2 REDs (8-byte red.global.add.v2.f32) per kept sample after run merging = ncu l1tex RED sectors / K
-        # (profiles/r1_ncu_fused_kernels_final.md); 140 G RED/s = scatter-only micro-benchmark at full occupancy
+        # ~80 REDs (8-byte red.global.add.v2.f32) per kept sample after run merging = ncu RED sectors / K
+        # (profiles/r1_ncu_traffic.json); 140 G RED/s = scatter-only micro-benchmark at full occupancy
         # (profiles/r1_gather_scatter_microbench.md).
-        reds = 79.2 * k1
+        info = ncu_info.get(dom, {})
+        reds = (info['red_sectors_per_launch'] / info['kept_samples'] if 'red_sectors_per_launch' in info else 79.2) * k1
         roofline['secondary'] = {'bound': 'l2_red', 'unit': 'G RED/s', 'achieved': reds / (kern[dom]['ms'] * 1e-3) / 1e9, 'peak': 140.0,
                                  'frac': reds / (kern[dom]['ms'] * 1e-3) / 1e9 / 140.0,
-                                 'source': 'REDs/sample from ncu (profiles/r1_ncu_fused_kernels_final.md); peak = measured scatter-only floor'}
+                                 'source': 'REDs/sample from ncu (profiles/r1_ncu_traffic.json); peak = measured scatter-only floor (profiles/r1_gather_scatter_microbench.md)'}
     cpu = time_cpu(2, 1, n_rays=512) if world == 1 else None
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
