@@ -159,13 +159,17 @@ class _Lib:
         rc = fn(*args)
         if rc != 0:
             raise NsrError(f'{name} failed ({rc}): {self.dll.nsr_last_error().decode()}')
-        self.launches += 1
+        self.launches += _KERNELS_PER_CALL.get(name, 1)
         if self.profile is not None:
             e1.record()
             self.profile.setdefault(name, []).append((e0, e1))
 
 
 lib = _Lib()
+
+
+# entry points that launch more than one kernel (lib.launches counts kernels, not calls)
+_KERNELS_PER_CALL = {'nsr_nerf_loss_fwd': 2, 'nsr_neus_loss_fwd': 2, 'nsr_occgrid_update': 2}
 
 
 def register_signatures(sigs):
