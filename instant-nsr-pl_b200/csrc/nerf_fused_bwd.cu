@@ -17,16 +17,16 @@ constexpr int kRows = kWarps * 16;  // 64-row CTA tile: ~96 KB of smem => 2 CTAs
 constexpr int kCtasPerSm = 2;
 
 // smem tile offsets (halves) after the weights
-constexpr int T_X0 = 0;                         // [128][40]  encoded features
-constexpr int T_H1 = T_X0 + kRows * NF_LD32;    // [128][72]  density hidden (post ReLU)
-constexpr int T_CI = T_H1 + kRows * NSR_LD64;   // [128][40]  colour input: out16 | SH16
-constexpr int T_G1 = T_CI + kRows * NF_LD32;    // [128][72]
-constexpr int T_G2 = T_G1 + kRows * NSR_LD64;   // [128][72]
-constexpr int T_DC3 = T_G2 + kRows * NSR_LD64;  // [128][24]  d(rgb pre-activation)
-constexpr int T_DG2 = T_DC3 + kRows * 24;       // [128][72]
-constexpr int T_DG1 = T_DG2 + kRows * NSR_LD64; // [128][72]
-constexpr int T_DO = T_DG1 + kRows * NSR_LD64;  // [128][24]  d(out16)
-constexpr int T_DH1 = T_DO + kRows * 24;        // [128][72]
+constexpr int T_X0 = 0;                         // [64][40]  encoded features
+constexpr int T_H1 = T_X0 + kRows * NF_LD32;    // [64][72]  density hidden (post ReLU)
+constexpr int T_CI = T_H1 + kRows * NSR_LD64;   // [64][40]  colour input: out16 | SH16
+constexpr int T_G1 = T_CI + kRows * NF_LD32;    // [64][72]
+constexpr int T_G2 = T_G1 + kRows * NSR_LD64;   // [64][72]
+constexpr int T_DC3 = T_G2 + kRows * NSR_LD64;  // [64][24]  d(rgb pre-activation)
+constexpr int T_DG2 = T_DC3 + kRows * 24;       // [64][72]
+constexpr int T_DG1 = T_DG2 + kRows * NSR_LD64; // [64][72]
+constexpr int T_DO = T_DG1 + kRows * NSR_LD64;  // [64][24]  d(out16)
+constexpr int T_DH1 = T_DO + kRows * 24;        // [64][72]
 constexpr int T_X0B = T_DH1 + kRows * NSR_LD64; // [64][40]  second encoded-feature buffer (packed mode: cp.async double buffering)
 constexpr int T_TOTAL = T_X0B + kRows * NF_LD32;
 // packed mode: per-row inputs of two tiles in flight (floats): xyz+dir [64][6], d_sraw [64], d_rgb [64][3]
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
       }
     }
     __syncthreads();
-    // ---- weight gradients over the 128 rows of the tile
+    // ---- weight gradients over the 64 rows of the tile
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
       const WgradTile w = wgrad_tile(warp + s * kWarps);
