@@ -127,6 +127,16 @@ int nsr_mlp_fwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, void*
  * dx fp16 [n,in_pad] (may be NULL) = loss_scale * true gradient. */
 int nsr_mlp_bwd(const nsr_mlp_t* m, const void* x_h, const void* params_h, const void* y_h, const void* dy_h,
                 float* grad_params, void* dx_h, float loss_scale, int64_t n, void* stream);
+/* The reference's VanillaMLP with ReLU (models/network_utils.py:95-139: nn.Linear WITH biases, fp32 in/out under autocast(False))
+ * on the same kernels: x fp16 [n, in_pad] (columns beyond n_in zero), weights_h fp16 in the FullyFused layout above (W1 columns
+ * beyond n_in zero, last matrix rows beyond n_out zero), bias f32 [64 * n_hidden + 16], out f32 [n, n_out] (compact).  fp16
+ * tensor-core operands, fp32 accumulation starting from the bias.  Backward: dy f32 [n, n_out]; grad_weights f32 (+=, layout of
+ * weights_h), grad_bias f32 [64 * n_hidden + 16] (+=), dx f32 [n, n_in] = dL/dx (compact, unscaled; may be NULL); loss_scale > 0
+ * fixes the scale of the fp16 dgrad chain, <= 0 derives it from *amax (device float: max |dy|). */
+int nsr_mlp_vanilla_fwd(const nsr_mlp_t* m, const void* x_h, const void* weights_h, const float* bias, float* out, int64_t n,
+                        void* stream);
+int nsr_mlp_vanilla_bwd(const nsr_mlp_t* m, const void* x_h, const void* weights_h, const float* bias, const float* dy,
+                        float* grad_weights, float* grad_bias, float* dx, float loss_scale, const float* amax, int64_t n, void* stream);
 
 /* tcgen05 / TMEM version of nsr_mlp_fwd (same tensors): 128-row CTA tiles, operands in the canonical K-major smem layout,
  * accumulators in tensor memory, tcgen05.ld epilogue.  variant bit 0 = swap LBO/SBO in the smem descriptors (bring-up switch);
@@ -301,6 +311,17 @@ int nsr_radiance_fwd(const nsr_radiance_t* p, const float* feat, const float* di
 int nsr_radiance_bwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra,
                      const void* params_h, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
                      float* grad_params, int64_t n, const int64_t* n_dev, void* stream);
+/* The same module when its network is the reference's VanillaMLP (models/network_utils.py:95-139; configs/neus-dtu.yaml:58-70
+ * texture, :93-105 texture_bg: ReLU, 64 neurons, two hidden layers, biases, fp32 output, computed under autocast(False)):
+ * n_feat + 16 + n_extra <= 32 (narrower inputs are zero padded), weights_h fp16 [7168] = W1 [64,32] (columns beyond the input
+ * width zero) | W2 [64,64] | W3 [16,64] (rows 3.. zero), bias f32 [144] = b1 | b2 | b3 (padded to 16); fp16 tensor-core operands,
+ * fp32 accumulation starting from the bias, fp32 output (act_mode 0 none, 1/2 sigmoid).  Backward adds grad_weights f32 [7168] (+=)
+ * and grad_bias f32 [144] (+=). */
+int nsr_radiance_vanilla_fwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra, const void* weights_h,
+                             const float* bias, float* rgb, int64_t n, const int64_t* n_dev, void* stream);
+int nsr_radiance_vanilla_bwd(const nsr_radiance_t* p, const float* feat, const float* dirs, const float* extra, const void* weights_h,
+                             const float* bias, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
+                             float* grad_weights, float* grad_bias, int64_t n, const int64_t* n_dev, void* stream);
 
 /* ---- gradient exchange over NVLink peer memory (replaces the NCCL all-reduce of Lightning DDP, launch.py:98) ---------
  * Every rank holds its flat fp32 gradient vector in a peer-mapped (symmetric) buffer of n floats (n % 4 == 0).

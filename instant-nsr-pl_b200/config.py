@@ -43,3 +43,14 @@ def to_primitive(c):
     if isinstance(c, (list, tuple)):
         return [to_primitive(v) for v in c]
     return c
+
+
+def experimental(name):
+    """True when the kernel path ``name`` is switched on.  Paths listed here were written after this round's GPU budget was spent: they
+    compile for sm_100a and have oracle-backed tests, but have not run on a B200 yet, so they stay off unless the environment asks
+    for them: NSR_EXPERIMENTAL=1 (all) or a comma-separated list of names."""
+    import os
+    v = os.environ.get('NSR_EXPERIMENTAL', '').strip()
+    if v in ('', '0'):
+        return False
+    return v == '1' or name in [x.strip() for x in v.split(',')]

@@ -72,6 +72,8 @@ _SIGNATURES = {
     'nsr_sh4_fwd': [P, P, I64, P],
     'nsr_mlp_fwd': [P, P, P, P, I64, P],
     'nsr_mlp_bwd': [P, P, P, P, P, P, P, F32, I64, P],
+    'nsr_mlp_vanilla_fwd': [P, P, P, P, P, I64, P],
+    'nsr_mlp_vanilla_bwd': [P, P, P, P, P, P, P, P, F32, P, I64, P],
     'nsr_mlp_fwd_tc': [P, P, P, P, I64, I32, P, P],
     'nsr_ray_aabb': [P, P, P, P, P, I64, P],
     'nsr_march_count': [P, P, P, P, P, P, P, I64, P],
@@ -102,6 +104,8 @@ _SIGNATURES = {
     'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P, P],
     'nsr_radiance_bwd': [P, P, P, P, P, P, F32, P, P, P, P, I64, P, P],
+    'nsr_radiance_vanilla_fwd': [P, P, P, P, P, P, P, I64, P, P],
+    'nsr_radiance_vanilla_bwd': [P, P, P, P, P, P, P, F32, P, P, P, P, P, I64, P, P],
     'nsr_p2p_barrier': [P, P, P, I32, I32, P],
     'nsr_p2p_allreduce_mean': [P, P, I32, I32, I64, P],
     'nsr_occgrid_points': [P, P, P, P, P, I64, P],

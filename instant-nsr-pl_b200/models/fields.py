@@ -8,7 +8,8 @@ import torch.nn as nn
 from . import register
 from ..nerfacc import ContractionType
 from .common import BaseModel, get_activation, scale_anything, update_module_step
-from .networks import get_encoding, get_mlp, get_encoding_with_network
+from .networks import get_encoding, get_mlp, get_encoding_with_network, VanillaMLP
+from ..config import experimental
 from .. import ops, tcnn
 
 
@@ -213,7 +214,11 @@ class VolumeRadiance(nn.Module):
         if getattr(enc, 'include_xyz', False):
             return None
         enc = getattr(enc, 'encoding', enc)  # CompositeEncoding wrapper
-        if not (isinstance(enc, tcnn.Encoding) and enc.otype == 'SphericalHarmonics' and isinstance(net, tcnn.Network)):
+        if not (isinstance(enc, tcnn.Encoding) and enc.otype == 'SphericalHarmonics'):
+            return None
+        if isinstance(net, VanillaMLP):
+            return self._fused_spec_vanilla(features, dirs, args)
+        if not isinstance(net, tcnn.Network):
             return None
         m = net.mlp
         if m.n_in != 32 or m.n_out != 3 or m.n_hidden != 2 or m.struct.activation != 1 or m.backend != 'mma_sync':
@@ -238,8 +243,35 @@ class VolumeRadiance(nn.Module):
             self._rspec, self._rspec_key = ops.RadianceSpec(*key), key
         return self._rspec
 
+    def _fused_spec_vanilla(self, features, dirs, args):
+        """VanillaMLP colour network (neus-dtu.yaml:58-70,93-105: ReLU, 64 x 2 hidden, biases) on the same one-kernel path
+        (nsr_radiance_vanilla_*); input cat[feature | SH4 | extra] at most 32 wide."""
+        net = self.network
+        if not self.config.get('fused_vanilla', experimental('radiance_vanilla')):
+            return None
+        if net.sphere_init or net.n_neurons != 64 or net.n_hidden_layers != 2 or len(args) > 1 or features.dim() != 2 or dirs.dim() != 2:
+            return None
+        out_act = str(self.config.mlp_network_config.get('output_activation', 'none')).lower()
+        color_act = self.config.get('color_activation', None)
+        color_act = None if color_act is None else str(color_act).lower()
+        if (out_act, color_act) in (('none', None), ('none', 'none')):
+            mode = 0
+        elif (out_act, color_act) in (('none', 'sigmoid'), ('sigmoid', None), ('sigmoid', 'none')):
+            mode = 2
+        else:
+            return None
+        n_extra = args[0].shape[-1] if args else 0
+        key = (features.shape[-1], n_extra, mode, 'vanilla')
+        if self._rspec is None or self._rspec_key != key:
+            if features.shape[-1] + 16 + n_extra > 32:
+                return None
+            self._rspec, self._rspec_key = ops.RadianceSpec(features.shape[-1], n_extra, mode, vanilla=True), key
+        return self._rspec
+
     def forward(self, features, dirs, *args):
         spec = self._fused_spec(features, dirs, args)
+        if spec is not None and spec.vanilla:
+            return ops.radiance_vanilla(spec, features, dirs, args[0] if args else None, self.network.linear_params())
         if spec is not None:
             return ops.radiance(spec, features, dirs, args[0] if args else None, self.network.params, self.network._params_half())
         emb = self.encoding(((dirs + 1.) / 2.).reshape(-1, self.n_dir_dims))  # (-1,1) -> (0,1)

@@ -112,8 +112,29 @@ class VanillaMLP(nn.Module):
                 mods.append(self.make_activation())
         self.layers = nn.Sequential(*mods)
         self.output_activation = get_activation(config['output_activation'])
+        self.fused = bool(config.get('fused', True))  # our extension key: False pins the torch (cuBLAS) layers
+        self._spec = None
+
+    def _fused_spec(self, x):
+        """VanillaMlpSpec when this network maps onto the one-kernel path (ReLU, 64 neurons, <= 3 hidden layers, n_in <= 64,
+        n_out <= 16, CUDA input, no double backward needed => not the sphere-init SDF network); None -> torch layers."""
+        from .. import ops
+        from ..config import experimental
+        if self.sphere_init or not x.is_cuda or not self.fused or not experimental('mlp_vanilla') or ops.static_rows_active():
+            return None
+        if self._spec is None:
+            lins = [m for m in self.layers if isinstance(m, nn.Linear)]
+            n_in, n_out = lins[0].in_features, lins[-1].out_features
+            ok = self.n_neurons == 64 and 1 <= self.n_hidden_layers <= 3 and n_in <= 64 and n_out <= 16
+            self._spec = ops.VanillaMlpSpec(n_in, n_out, self.n_hidden_layers) if ok else False
+        return self._spec or None
 
     def forward(self, x):
+        spec = self._fused_spec(x)
+        if spec is not None:
+            from .. import ops
+            with torch.autocast('cuda', enabled=False):
+                return self.output_activation(ops.vanilla_mlp(spec, x, self.linear_params()).reshape(*x.shape[:-1], spec.n_out))
         with torch.autocast('cuda', enabled=False):
             return self.output_activation(self.layers(x.float()))
 
@@ -135,6 +156,16 @@ class VanillaMLP(nn.Module):
 
     def make_activation(self):
         return nn.Softplus(beta=100) if self.sphere_init else nn.ReLU(inplace=True)
+
+    def linear_params(self):
+        """[(effective weight [out,in], bias)] per linear layer; the weight-norm reparametrisation is applied here (differentiably),
+        which is what the fused kernels consume."""
+        out = []
+        for m in self.layers:
+            if isinstance(m, nn.Linear):
+                w = torch._weight_norm(m.weight_v, m.weight_g, 0) if hasattr(m, 'weight_g') else m.weight
+                out.append((w, m.bias))
+        return out
 
 
 def sphere_init_tcnn_network(n_input_dims, n_output_dims, config, network):

@@ -261,6 +261,89 @@ def mlp(spec, x, params_f32, params_h):
     return out[:, :spec.n_out]
 
 
+class VanillaMlpSpec:
+    """descriptor of the reference's VanillaMLP with ReLU on the fused-MLP kernels (nsr_mlp_vanilla_*): n_in <= 64 -> 64 (x n_hidden
+    <= 3) -> n_out <= 16, biases, fp32 output."""
+
+    def __init__(self, n_in, n_out, n_hidden):
+        if not (1 <= n_in <= 64 and 1 <= n_out <= 16 and 1 <= n_hidden <= 3):
+            raise NotImplementedError(f'fused VanillaMLP: {n_in} -> 64 x {n_hidden} -> {n_out} is outside n_in <= 64, n_out <= 16, 1..3 layers')
+        self.n_in, self.n_out, self.n_hidden = int(n_in), int(n_out), int(n_hidden)
+        self.in_pad = (self.n_in + 15) // 16 * 16
+        self.n_weights = 64 * self.in_pad + 64 * 64 * (self.n_hidden - 1) + 16 * 64
+        self.n_bias = 64 * self.n_hidden + 16
+        s = MlpT()
+        s.n_in, s.n_out, s.n_hidden, s.activation, s.out_activation = self.n_in, self.n_out, self.n_hidden, _ACT['relu'], _ACT['none']
+        self.struct = s
+
+    def ref(self):
+        return _C.byref(self.struct)
+
+    def pack(self, layers):
+        """[(W [out,in], b)] per linear layer -> (weights f32 [n_weights], bias f32 [n_bias]) in the kernel layout, zero padded.
+        Differentiable torch ops: autograd hands the kernel's flat gradients back to the layers (through weight-norm, if any)."""
+        if len(layers) != self.n_hidden + 1:
+            raise RuntimeError(f'fused VanillaMLP: expected {self.n_hidden + 1} linear layers, got {len(layers)}')
+        F = torch.nn.functional
+        ws, bs = [], []
+        for li, (W, b) in enumerate(layers):
+            W, b = W.float(), b.float()
+            if li == 0:
+                W = F.pad(W, (0, self.in_pad - W.shape[1]))
+            if li == len(layers) - 1:
+                W, b = F.pad(W, (0, 0, 0, 16 - W.shape[0])), F.pad(b, (0, 16 - b.shape[0]))
+            ws.append(W.reshape(-1))
+            bs.append(b)
+        weights, bias = torch.cat(ws), torch.cat(bs)
+        if weights.shape[0] != self.n_weights or bias.shape[0] != self.n_bias:
+            raise RuntimeError('fused VanillaMLP: layer shapes do not match the descriptor')
+        return weights, bias
+
+
+class _VanillaMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, x, weights, bias):
+        n = x.shape[0]
+        xh = x.detach().to(torch.float16)
+        if spec.in_pad > spec.n_in:
+            xh = torch.nn.functional.pad(xh, (0, spec.in_pad - spec.n_in))
+        xh = xh.contiguous()
+        weights_h = weights.detach().to(torch.float16)
+        bias = contig(bias.detach(), torch.float32)
+        out = torch.empty(n, spec.n_out, dtype=torch.float32, device=x.device)
+        lib.call('nsr_mlp_vanilla_fwd', spec.ref(), ptr(xh), ptr(weights_h), ptr(bias), ptr(out), n, stream())
+        ctx.spec, ctx.x_dtype = spec, x.dtype
+        ctx.save_for_backward(xh, weights_h, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        xh, weights_h, bias = ctx.saved_tensors
+        n, dev = xh.shape[0], xh.device
+        dy = contig(dy, torch.float32)
+        amax = torch.empty(1, device=dev)
+        lib.call('nsr_absmax3', ptr(dy), dy.numel(), None, 0, None, 0, ptr(amax), n, None, stream())
+        gw, gb = torch.zeros(spec.n_weights, device=dev), torch.zeros(spec.n_bias, device=dev)
+        dx = torch.empty(n, spec.n_in, device=dev) if ctx.needs_input_grad[1] else None
+        lib.call('nsr_mlp_vanilla_bwd', spec.ref(), ptr(xh), ptr(weights_h), ptr(bias), ptr(dy), ptr(gw), ptr(gb), ptr(dx), 0.0, ptr(amax), n,
+                 stream())
+        return None, (None if dx is None else dx.to(ctx.x_dtype)), gw, gb
+
+
+def vanilla_mlp(spec, x, layers):
+    """x [N, n_in] (fp16 or fp32) -> fp32 [N, n_out]: VanillaMLP(ReLU) with biases in one kernel per direction (no output activation:
+    the caller applies it)."""
+    check_cuda(x, what='VanillaMLP (fused)')
+    weights, bias = spec.pack(layers)
+    return _VanillaMlpFn.apply(spec, x.reshape(-1, spec.n_in), weights, bias)
+
+
+def static_rows_active():
+    """True inside a static-shape region (ops carry a device-side live-row count); kernels without that argument must not run there."""
+    return _LIVE_ROWS is not None
+
+
 # --------------------------------------------------------------------------------------------------
 # marching / compositing
 # --------------------------------------------------------------------------------------------------
@@ -512,11 +595,15 @@ def neus_composite(alpha, rgb, normal, t_starts, t_ends, offsets):
 
 
 class RadianceSpec:
-    """descriptor of the fused VolumeRadiance kernel (nsr_radiance_t)."""
+    """descriptor of the fused VolumeRadiance kernel (nsr_radiance_t); vanilla=True: the VanillaMLP variant (biases, fp32 output,
+    input width <= 32)."""
 
-    def __init__(self, n_feat, n_extra, act_mode):
-        if n_feat + 16 + n_extra != 32:
-            raise NotImplementedError(f'fused radiance: feature ({n_feat}) + SH4 (16) + extra ({n_extra}) must be 32 wide')
+    def __init__(self, n_feat, n_extra, act_mode, vanilla=False):
+        width = n_feat + 16 + n_extra
+        if (width > 32) if vanilla else (width != 32):
+            raise NotImplementedError(f'fused radiance: feature ({n_feat}) + SH4 (16) + extra ({n_extra}) must be '
+                                      f'{"at most " if vanilla else ""}32 wide')
+        self.vanilla = bool(vanilla)
         self.n_feat, self.n_extra, self.act_mode = int(n_feat), int(n_extra), int(act_mode)
         self._t = RadianceT(self.n_feat, self.n_extra, self.act_mode)
 
@@ -556,6 +643,61 @@ def radiance(spec, feat, dirs, extra, params_f32, params_h):
         raise RuntimeError('fused radiance: expected the 7168 parameters of a 32->64->64->3 FullyFusedMLP')
     return _Radiance.apply(spec, contig(feat.reshape(-1, spec.n_feat), torch.float32), contig(dirs.reshape(-1, 3), torch.float32),
                            None if extra is None else contig(extra.reshape(-1, spec.n_extra), torch.float32), params_f32, params_h)
+
+
+class _RadianceVanilla(torch.autograd.Function):
+    """cat[feat | SH4 | extra] -> VanillaMLP (ReLU, 64, 64, biases) -> 3 in one kernel per direction (nsr_radiance_vanilla_*)."""
+
+    @staticmethod
+    def forward(ctx, spec, feat, dirs, extra, weights, bias):
+        n = feat.shape[0]
+        weights_h = weights.detach().to(torch.float16)
+        bias = contig(bias.detach(), torch.float32)
+        rgb = torch.empty(n, 3, device=feat.device)
+        lib.call('nsr_radiance_vanilla_fwd', spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(weights_h), ptr(bias), ptr(rgb), n,
+                 ptr(_LIVE_ROWS), stream())
+        ctx.spec, ctx.k_dev = spec, _LIVE_ROWS
+        ctx.save_for_backward(feat, dirs, extra, weights_h, bias)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        feat, dirs, extra, weights_h, bias = ctx.saved_tensors
+        n, dev = feat.shape[0], feat.device
+        g_rgb = contig(g_rgb, torch.float32)
+        amax = torch.empty(1, device=dev)
+        lib.call('nsr_absmax3', ptr(g_rgb), g_rgb.numel(), None, 0, None, 0, ptr(amax), n, ptr(ctx.k_dev), stream())
+        d_feat = torch.empty_like(feat) if ctx.needs_input_grad[1] else None
+        d_extra = torch.empty_like(extra) if (extra is not None and ctx.needs_input_grad[3]) else None
+        gw, gb = torch.zeros(weights_h.shape[0], device=dev), torch.zeros(bias.shape[0], device=dev)
+        lib.call('nsr_radiance_vanilla_bwd', ctx.spec.ref(), ptr(feat), ptr(dirs), ptr(extra), ptr(weights_h), ptr(bias), ptr(g_rgb), 0.0,
+                 ptr(amax), ptr(d_feat), ptr(d_extra), ptr(gw), ptr(gb), n, ptr(ctx.k_dev), stream())
+        return None, d_feat, None, d_extra, gw, gb
+
+
+def pack_vanilla_radiance(layers):
+    """[(W1 [64,in<=32], b1), (W2 [64,64], b2), (W3 [3,64], b3)] -> (weights f32 [7168], bias f32 [144]) in the kernel's padded layout
+    (nsr_radiance_vanilla_fwd).  Plain differentiable torch ops, so autograd routes the kernel's flat gradients back to the layers
+    (and through a weight-norm reparametrisation, if any)."""
+    (W1, b1), (W2, b2), (W3, b3) = layers
+    if W1.shape[0] != 64 or W1.shape[1] > 32 or tuple(W2.shape) != (64, 64) or W3.shape[1] != 64 or W3.shape[0] > 16:
+        raise NotImplementedError('fused VanillaMLP radiance: needs in (<= 32) -> 64 -> 64 -> out (<= 16)')
+    F = torch.nn.functional
+    weights = torch.cat([F.pad(W1.float(), (0, 32 - W1.shape[1])).reshape(-1), W2.float().reshape(-1),
+                         F.pad(W3.float(), (0, 0, 0, 16 - W3.shape[0])).reshape(-1)])
+    bias = torch.cat([b1.float(), b2.float(), F.pad(b3.float(), (0, 16 - b3.shape[0]))])
+    return weights, bias
+
+
+def radiance_vanilla(spec, feat, dirs, extra, layers):
+    """cat[feat | SH4(dirs) | extra] -> VanillaMLP (layers = [(W, b)] * 3, see pack_vanilla_radiance) -> fp32 rgb [n,3] (+ sigmoid
+    when spec.act_mode != 0).  fp16 tensor-core operands with fp32 accumulation against the reference's fp32 cuBLAS GEMMs."""
+    check_cuda(feat, dirs, extra, what='VolumeRadiance (fused VanillaMLP)')
+    if not spec.vanilla:
+        raise RuntimeError('radiance_vanilla needs a RadianceSpec(vanilla=True)')
+    weights, bias = pack_vanilla_radiance(layers)
+    return _RadianceVanilla.apply(spec, contig(feat.reshape(-1, spec.n_feat), torch.float32), contig(dirs.reshape(-1, 3), torch.float32),
+                                  None if extra is None else contig(extra.reshape(-1, spec.n_extra), torch.float32), weights, bias)
 
 
 def sample_points(rays, ray_indices, t_starts, t_ends):

@@ -110,3 +110,65 @@ def test_fused_adamw_and_static_neus_refuse_cpu():
     m.background_color = torch.ones(3)
     with pytest.raises(NotImplementedError):
         m.forward_(torch.zeros(4, 6), static=True)
+
+
+def test_vanilla_mlp_packing_matches_layers_and_routes_gradients():
+    """host side of nsr_mlp_vanilla_* / nsr_radiance_vanilla_*: the flat padded weight / bias vectors reproduce the VanillaMLP
+    (models/network_utils.py:95-139) exactly when evaluated with plain matrix products, and gradients of the flat vectors flow back to
+    the layers (through the weight-norm reparametrisation)."""
+    from nsr_b200 import ops
+    from nsr_b200.models.networks import VanillaMLP
+    torch.manual_seed(0)
+    for n_in, n_out, nh, wn in [(24, 3, 2, False), (32, 8, 1, True), (60, 16, 3, False)]:
+        net = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=nh, output_activation='none', weight_norm=wn))
+        with torch.no_grad():
+            for m in net.layers:
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.2, 0.2)
+        spec = ops.VanillaMlpSpec(n_in, n_out, nh)
+        weights, bias = spec.pack(net.linear_params())
+        assert weights.shape == (spec.n_weights,) and bias.shape == (spec.n_bias,) and spec.in_pad % 16 == 0
+        x = torch.randn(50, n_in)
+        h = torch.nn.functional.pad(x, (0, spec.in_pad - n_in))
+        off, widths = 0, [spec.in_pad] + [64] * nh
+        for li in range(nh + 1):
+            o = 64 if li < nh else 16
+            W = weights[off:off + o * widths[li]].view(o, widths[li])
+            off += o * widths[li]
+            h = h @ W.t() + bias[64 * li:64 * li + o]
+            if li < nh:
+                h = torch.relu(h)
+        y = net(x)
+        assert torch.allclose(h[:, :n_out], y, atol=1e-5) and float(h[:, n_out:].detach().abs().max() if n_out < 16 else 0.0) == 0.0
+        (h[:, :n_out].sum()).backward()
+        g_flat = {k: p.grad.clone() for k, p in net.named_parameters()}
+        net.zero_grad()
+        net(x).sum().backward()
+        for k, p in net.named_parameters():
+            assert torch.allclose(g_flat[k], p.grad, atol=1e-4), k
+    with pytest.raises(NotImplementedError):
+        ops.VanillaMlpSpec(65, 3, 2)
+    # radiance packing = the 32 -> 64 -> 64 -> 16 special case
+    net = VanillaMLP(24, 3, dict(n_neurons=64, n_hidden_layers=2, output_activation='none'))
+    w, b = ops.pack_vanilla_radiance(net.linear_params())
+    w2, b2 = ops.VanillaMlpSpec(24, 3, 2).pack(net.linear_params())
+    assert w.shape == (7168,) and b.shape == (144,) and torch.equal(w, w2) and torch.equal(b, b2)
+    assert ops.RadianceSpec(8, 0, 2, vanilla=True).vanilla and not ops.RadianceSpec(16, 0, 1).vanilla
+    with pytest.raises(NotImplementedError):
+        ops.RadianceSpec(8, 0, 2)            # the FullyFused kernel needs exactly 32 inputs
+    with pytest.raises(NotImplementedError):
+        ops.RadianceSpec(16, 3, 2, vanilla=True)
+
+
+def test_experimental_switch_and_vanilla_mlp_stays_on_torch_for_cpu(monkeypatch):
+    from nsr_b200.config import experimental
+    from nsr_b200.models.networks import VanillaMLP
+    monkeypatch.delenv('NSR_EXPERIMENTAL', raising=False)
+    assert not experimental('mlp_vanilla')
+    monkeypatch.setenv('NSR_EXPERIMENTAL', 'mlp_vanilla, other')
+    assert experimental('mlp_vanilla') and experimental('other') and not experimental('radiance_vanilla')
+    monkeypatch.setenv('NSR_EXPERIMENTAL', '1')
+    assert experimental('anything')
+    net = VanillaMLP(8, 3, dict(n_neurons=64, n_hidden_layers=2, output_activation='none'))
+    x = torch.randn(5, 8)
+    assert net._fused_spec(x) is None and net(x).shape == (5, 3)   # CPU tensors: the torch layers (the reference's own CPU behaviour)
