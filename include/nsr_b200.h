@@ -323,6 +323,17 @@ int nsr_radiance_vanilla_bwd(const nsr_radiance_t* p, const float* feat, const f
                              const float* bias, const float* d_rgb, float loss_scale, const float* amax, float* d_feat, float* d_extra,
                              float* grad_weights, float* grad_bias, int64_t n, const int64_t* n_dev, void* stream);
 
+/* ---- training-batch front end (preprocess_data of systems/nerf.py:33-91 / systems/neus.py:34-96 + models/ray_utils.py:23-43)
+ * ray r comes from image index[r], pixel (x[r], y[r]) (index == NULL: image fixed_index, pixel (r % W, r / W): a whole image in
+ * row-major order).  directions f32 [H,W,3] (dirs_per_image 0) or [n_images,H,W,3] (1); c2w f32 [n_images, c2w_rows (3|4), 4];
+ * rays f32 [n,6] = c2w[:,3] | normalize(sum_j directions_j * c2w[i][j]) (F.normalize, eps 1e-12).  Optional (NULL = skip):
+ * rgb f32 [n,3] = images[index,y,x,:3] (images f32 [n_images,H,W,channels]), fg f32 [n] = masks[index,y,x] (masks f32
+ * [n_images,H,W]); apply_mask: rgb = rgb * fg + bg * (1 - fg), bg f32 [3].  Out-of-range indices are clamped. */
+int nsr_gather_rays(const float* directions, int32_t dirs_per_image, const float* c2w, int32_t c2w_rows, const float* images,
+                    int32_t channels, const float* masks, const int64_t* index, const int64_t* x, const int64_t* y, int32_t fixed_index,
+                    const float* bg, int32_t apply_mask, int32_t H, int32_t W, int32_t n_images, float* rays, float* rgb, float* fg,
+                    int64_t n, void* stream);
+
 /* ---- gradient exchange over NVLink peer memory (replaces the NCCL all-reduce of Lightning DDP, launch.py:98) ---------
  * Every rank holds its flat fp32 gradient vector in a peer-mapped (symmetric) buffer of n floats (n % 4 == 0).
  * nsr_p2p_barrier: all-ranks barrier on the stream: flags = one peer-mapped int32[>= world] array per rank (zeroed once),

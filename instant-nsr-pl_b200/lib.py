@@ -117,6 +117,7 @@ _SIGNATURES = {
     'nsr_nerf_loss_bwd': [P, P, P, P, P, P, P, P, I64, P],
     'nsr_neus_loss_fwd': [P, P, P, P, P, P, P, P, P, P, I64, I64, P, P],
     'nsr_neus_loss_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, P, P],
+    'nsr_gather_rays': [P, I32, P, I32, P, I32, P, P, P, P, I32, P, I32, I32, I32, I32, P, P, P, I64, P],
     'nsr_nerf_density': [P, P, P, P, I64, P],
     'nsr_nerf_prepass': [P, P, P, P, P, P, P, I64, P, P],
     'nsr_compact_prefix': [P, P, P, P, P, P, P, P, P, P, I64, P],

@@ -172,3 +172,20 @@ def test_experimental_switch_and_vanilla_mlp_stays_on_torch_for_cpu(monkeypatch)
     net = VanillaMLP(8, 3, dict(n_neurons=64, n_hidden_layers=2, output_activation='none'))
     x = torch.randn(5, 8)
     assert net._fused_spec(x) is None and net(x).shape == (5, 3)   # CPU tensors: the torch layers (the reference's own CPU behaviour)
+
+
+def test_ray_helpers_match_golden_and_kernel_entry_refuses_cpu(golden):
+    """nsr_b200.rays: the load-time helpers keep the reference's signatures / numbers (models/ray_utils.py:9-43); the per-step
+    kernel path has no CPU fallback."""
+    from nsr_b200 import rays
+    d = rays.get_ray_directions(8, 6, 11.0, 11.0, 4.0, 3.0)
+    np.testing.assert_array_equal(d.numpy(), golden['rays/directions'])
+    o, w = rays.get_rays(d, torch.from_numpy(golden['rays/c2w']))
+    np.testing.assert_array_equal(o.numpy(), golden['rays/o'])
+    np.testing.assert_allclose(w.numpy(), golden['rays/d'], rtol=1e-6, atol=1e-7)
+    c2w = torch.from_numpy(golden['rays/c2w'])
+    z = torch.zeros(4, dtype=torch.int64)
+    with pytest.raises(NotImplementedError):
+        rays.training_batch(d, c2w, torch.zeros(2, 6, 8, 3), torch.zeros(2, 6, 8), z, z, z)
+    with pytest.raises(NotImplementedError):
+        rays.image_batch(d, c2w, 0)
