@@ -334,6 +334,22 @@ int nsr_gather_rays(const float* directions, int32_t dirs_per_image, const float
                     const float* bg, int32_t apply_mask, int32_t H, int32_t W, int32_t n_images, float* rays, float* rgb, float* fg,
                     int64_t n, void* stream);
 
+/* ---- isosurface extraction (models/geometry.py:32-112: MarchingCubeHelper + isosurface_; replaces the host copy of the
+ * level grid and the single-core PyMCubes call).  field f32 [nx,ny,nz] (z fastest = torch.meshgrid(indexing='ij').reshape(-1));
+ * INSIDE <=> value > iso, value = negate ? -field : field (the reference hands -level to mcubes: geometry.py:62).
+ *   nsr_mc_count: block_offsets int32 [2 * B], B = ceil(nx*ny*nz / 256): on return the exclusive prefix sums of the per-block vertex
+ *                 counts ([0,B)) and triangle counts ([B,2B)); totals int64 [2] (device) = (V, F).  The caller reads totals (one host
+ *                 sync), allocates verts f32 [V,3] and faces int64 [F,3], then
+ *   nsr_mc_emit:  vid_map int32 [nx*ny*nz] workspace; verts = (index coordinate / (n-1)) * (hi - lo) + lo per axis (lo, hi: HOST
+ *                 float[3], the box the grid spans); vertices in (grid point, axis) order, triangles in (cell, case-table) order,
+ *                 wound so that their normals point to the outside (smaller values).  Deterministic, no atomics.
+ * The case table (csrc/mc_table.inc) is generated by mc_table.py with one fixed rule for ambiguous faces => no holes. */
+int nsr_mc_count(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, int32_t negate, int32_t* block_offsets, int64_t* totals,
+                 void* stream);
+int nsr_mc_emit(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, int32_t negate, const int32_t* block_offsets,
+                const float* lo, const float* hi, int32_t* vid_map, float* verts, int64_t n_verts, int64_t* faces, int64_t n_faces,
+                void* stream);
+
 /* ---- gradient exchange over NVLink peer memory (replaces the NCCL all-reduce of Lightning DDP, launch.py:98) ---------
  * Every rank holds its flat fp32 gradient vector in a peer-mapped (symmetric) buffer of n floats (n % 4 == 0).
  * nsr_p2p_barrier: all-ranks barrier on the stream: flags = one peer-mapped int32[>= world] array per rank (zeroed once),

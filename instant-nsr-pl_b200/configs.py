@@ -23,7 +23,8 @@ def nerf_blender(radius=1.5):
         dynamic_ray_sampling=True, batch_image_sampling=True, randomized=True, ray_chunk=32768, learned_background=False,
         background_color='random',
         geometry=dict(name='volume-density', radius=radius, feature_dim=16, density_activation='trunc_exp', density_bias=-1,
-                      isosurface=None, xyz_encoding_config=_HASH_NERF, mlp_network_config=_ff(1)),
+                      isosurface=dict(method='mc', resolution=256, chunk=2097152, threshold=5.0),
+                      xyz_encoding_config=_HASH_NERF, mlp_network_config=_ff(1)),
         texture=dict(name='volume-radiance', input_feature_dim=16, dir_encoding_config=dict(otype='SphericalHarmonics', degree=4),
                      mlp_network_config=_ff(2, 'Sigmoid'))))
 
@@ -34,7 +35,8 @@ def neus_blender(radius=1.5):
         grid_prune_occ_thre=0.001, dynamic_ray_sampling=True, batch_image_sampling=True, randomized=True, ray_chunk=4096,
         cos_anneal_end=20000, learned_background=False, background_color='random',
         variance=dict(init_val=0.3, modulate=False),
-        geometry=dict(name='volume-sdf', radius=radius, feature_dim=13, grad_type='analytic', isosurface=None,
+        geometry=dict(name='volume-sdf', radius=radius, feature_dim=13, grad_type='analytic',
+                      isosurface=dict(method='mc', resolution=512, chunk=2097152, threshold=0.),
                       xyz_encoding_config=dict(_HASH_NEUS, include_xyz=True),
                       mlp_network_config=_vanilla(1, sphere_init=True, sphere_init_radius=0.5, weight_norm=True)),
         texture=dict(name='volume-radiance', input_feature_dim=16, dir_encoding_config=dict(otype='SphericalHarmonics', degree=4),

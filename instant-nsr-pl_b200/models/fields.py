@@ -1,7 +1,6 @@
 """Geometry and texture fields: 'volume-density', 'volume-sdf', 'volume-radiance', 'volume-color'
 (models/geometry.py:17-29,115-238 and models/texture.py:10-57 of the reference), same constructor
-config, forward signatures and return conventions.  Isosurface extraction (marching cubes) is an
-export-time feature outside the rendering hot path and is not provided."""
+config, forward signatures and return conventions; ``isosurface()`` extracts the mesh on the GPU (nsr_b200.mcubes)."""
 import torch
 import torch.nn as nn
 
@@ -32,9 +31,25 @@ class BaseImplicitGeometry(BaseModel):
         self.radius = self.config.radius
         self.contraction_type = None  # assigned by the renderer that owns this field
 
+        iso = self.config.get('isosurface', None)
+        if iso is not None:
+            if iso.method not in ('mc', 'mc-torch'):
+                raise ValueError(f"isosurface.method must be 'mc' (or 'mc-torch'), got {iso.method!r}")
+            if iso.method == 'mc-torch':
+                raise NotImplementedError('Please do not use mc-torch (models/geometry.py:77-78)')
+
+    def forward_level(self, points):
+        raise NotImplementedError
+
+    @torch.no_grad()
     def isosurface(self):
-        raise NotImplementedError('isosurface extraction (marching cubes export) is outside the rendering hot path '
-                                  'and not provided by nsr_b200')
+        """models/geometry.py:80-112: coarse + refined marching cubes over the level field, here extracted on the GPU (nsr_b200.mcubes)"""
+        iso = self.config.get('isosurface', None)
+        if iso is None:
+            raise NotImplementedError
+        from .. import mcubes
+        device = next(self.parameters()).device
+        return mcubes.isosurface(self.forward_level, self.radius, iso.resolution, iso.threshold, iso.chunk, device)
 
 
 @register('volume-density')

@@ -134,4 +134,12 @@ class NeRFModel(BaseModel):
 
     @torch.no_grad()
     def export(self, export_config):
-        return self.isosurface()
+        """models/nerf.py:153-161: isosurface mesh (+ per-vertex colour seen from above)"""
+        mesh = self.isosurface()
+        if export_config.export_vertex_color:
+            dev = next(self.parameters()).device
+            _, feature = chunk_batch(self.geometry, export_config.chunk_size, False, mesh['v_pos'].to(dev))
+            viewdirs = torch.zeros(feature.shape[0], 3).to(feature)
+            viewdirs[..., 2] = -1.  # looking down -z
+            mesh['v_rgb'] = self.texture(feature, viewdirs).clamp(0, 1).cpu()
+        return mesh

@@ -290,4 +290,12 @@ class NeuSModel(BaseModel):
 
     @torch.no_grad()
     def export(self, export_config):
-        return self.isosurface()
+        """models/neus.py:321-329: isosurface mesh (+ per-vertex "albedo": colour seen along the normal)"""
+        mesh = self.isosurface()
+        if export_config.export_vertex_color:
+            dev = next(self.parameters()).device
+            _, sdf_grad, feature = chunk_batch(self.geometry, export_config.chunk_size, False, mesh['v_pos'].to(dev), with_grad=True,
+                                               with_feature=True)
+            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            mesh['v_rgb'] = self.texture(feature, -normal, normal).cpu()
+        return mesh

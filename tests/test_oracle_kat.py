@@ -293,3 +293,64 @@ def test_adamw_oracle_matches_torch():
     st = opt.state[pt]
     np.testing.assert_allclose(m, st['exp_avg'].numpy(), rtol=2e-6, atol=1e-7 * float(np.abs(m).max()))  # lerp cancellation near 0
     np.testing.assert_allclose(v, st['exp_avg_sq'].numpy(), rtol=2e-6, atol=1e-7 * float(v.max()))
+
+
+def _unit_grid(n, r=1.0):
+    g = np.linspace(-r, r, n, dtype=np.float32)
+    return np.meshgrid(g, g, g, indexing='ij')
+
+
+def test_marching_cubes_oracle_properties_and_product_case_table():
+    """oracle/mcubes.py (PyMCubes stand-in, parity unpinned) pinned by what a mesh consumer relies on, and the product's generated case
+    table (instant-nsr-pl_b200/mc_table.py -> csrc/mc_table.inc) checked against the oracle's independent per-cell construction."""
+    import importlib.util
+    import os
+    from oracle import mcubes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('nsr_mc_table', os.path.join(root, 'instant-nsr-pl_b200', 'mc_table.py'))
+    mt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mt)
+    table = mt.build_table()
+    assert len(table) == 256 and table[0] == [] and table[255] == [] and max(len(t) for t in table) == 5
+    for case in range(256):
+        assert mcubes.case_triangles(case) == table[case], case
+    # the committed header is the generator's output
+    inc = open(os.path.join(root, 'instant-nsr-pl_b200', 'csrc', 'mc_table.inc')).read()
+    rows = [ln for ln in inc.splitlines() if ln.startswith('    {')]
+    assert len(rows) == 256
+    for case, ln in enumerate(rows):
+        flat = [int(v) for v in ln.strip(' {},').split(',')]
+        want = [e for t in table[case] for e in t]
+        assert flat[:len(want)] == want and all(v == -1 for v in flat[len(want):]) and len(flat) == 16
+
+    # sphere: closed, outward, vertices on the iso-crossings, area / volume converge from below
+    X, Y, Z = _unit_grid(33)
+    sdf = np.sqrt(X * X + Y * Y + Z * Z) - np.float32(0.6)
+    v, f = mcubes.marching_cubes(sdf, 0.0, lo=(-1, -1, -1), hi=(1, 1, 1), negate=True)
+    assert mcubes.directed_edge_defects(f) == 0
+    assert len(v) - 3 * len(f) // 2 + len(f) == 2                      # Euler characteristic of a sphere (E = 3F/2 on a closed mesh)
+    vol, area = mcubes.signed_volume(v, f), mcubes.area(v, f)
+    assert 0.98 * (4 / 3 * np.pi * 0.6 ** 3) < vol < 4 / 3 * np.pi * 0.6 ** 3
+    assert 0.99 * (4 * np.pi * 0.36) < area < 4 * np.pi * 0.36
+    assert np.abs(np.linalg.norm(v, axis=1) - 0.6).max() < 1e-3       # linear interpolation of a distance field
+    # each vertex lies on a grid edge (two lattice coordinates) of the box
+    lat = (v + 1) / 2 * 32
+    assert ((np.abs(lat - np.round(lat)) < 1e-4).sum(axis=1) >= 2).all()
+    # flipping the sign flips the orientation (the reference negates the level for exactly this reason, geometry.py:62)
+    v2, f2 = mcubes.marching_cubes(sdf, 0.0, lo=(-1, -1, -1), hi=(1, 1, 1), negate=False)
+    assert mcubes.signed_volume(v2, f2) < 0 and len(f2) == len(f)
+    # torus: genus 1
+    q = np.sqrt(X * X + Y * Y) - np.float32(0.55)
+    tor = np.sqrt(q * q + Z * Z) - np.float32(0.22)
+    v, f = mcubes.marching_cubes(tor, 0.0, negate=True)
+    assert mcubes.directed_edge_defects(f) == 0 and len(v) - 3 * len(f) // 2 + len(f) == 0
+    # white noise (every ambiguous configuration occurs) with an outside border: still closed, and non-cubic grids work
+    rng = np.random.default_rng(0)
+    fld = rng.standard_normal((14, 15, 16)).astype(np.float32)
+    fld[0] = fld[-1] = fld[:, 0] = fld[:, -1] = -10
+    fld[:, :, 0] = fld[:, :, -1] = -10
+    v, f = mcubes.marching_cubes(fld, 0.1)
+    assert len(f) > 5000 and mcubes.directed_edge_defects(f) == 0 and mcubes.signed_volume(v, f) > 0
+    # nothing to extract
+    v, f = mcubes.marching_cubes(np.ones((4, 4, 4), np.float32), 2.0)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
