@@ -72,6 +72,7 @@ extern "C" int nsr_gather_rays(const float* directions, int32_t dirs_per_image, 
                                int32_t channels, const float* masks, const int64_t* index, const int64_t* x, const int64_t* y,
                                int32_t fixed_index, const float* bg, int32_t apply_mask, int32_t H, int32_t W, int32_t n_images, float* rays,
                                float* rgb, float* fg, int64_t n, void* stream) {
+  if (n == 0) return 0;
   NSR_REQUIRE(directions != nullptr && c2w != nullptr && rays != nullptr, "nsr_gather_rays: directions / c2w / rays is NULL");
   NSR_REQUIRE(H > 0 && W > 0 && n_images > 0, "nsr_gather_rays: empty dataset (H %d, W %d, images %d)", H, W, n_images);
   NSR_REQUIRE(c2w_rows == 3 || c2w_rows == 4, "nsr_gather_rays: c2w must be [n,3,4] or [n,4,4]");
@@ -79,7 +80,6 @@ extern "C" int nsr_gather_rays(const float* directions, int32_t dirs_per_image, 
   NSR_REQUIRE(index != nullptr || (fixed_index >= 0 && fixed_index < n_images), "nsr_gather_rays: image %d out of range", fixed_index);
   NSR_REQUIRE(rgb == nullptr || (images != nullptr && channels >= 3), "nsr_gather_rays: rgb output needs images with >= 3 channels");
   NSR_REQUIRE(!apply_mask || rgb == nullptr || (masks != nullptr && bg != nullptr), "nsr_gather_rays: apply_mask needs masks and bg");
-  if (n == 0) return 0;
   RayArgs a;
   a.directions = directions, a.c2w = c2w, a.images = images, a.masks = masks, a.index = index, a.x = x, a.y = y, a.bg = bg;
   a.rays = rays, a.rgb = rgb, a.fg = fg, a.n = n;

@@ -65,6 +65,8 @@ def training_batch(directions, all_c2w, all_images, all_fg_masks, index, x, y, b
         raise ValueError('apply_mask needs background_color')
     bg = None if background_color is None else contig(background_color.to(dev), torch.float32)
     rays, rgb, fg = torch.empty(n, 6, device=dev), torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+    if n == 0:
+        return {'rays': rays, 'rgb': rgb, 'fg_mask': fg}
     lib.call('nsr_gather_rays', ptr(d), int(d.dim() == 4), ptr(c), c.shape[1], ptr(im), im.shape[-1], ptr(mk), ptr(idx), ptr(xx), ptr(yy), 0,
              ptr(bg), int(bool(apply_mask)), H, W, n_images, ptr(rays), ptr(rgb), ptr(fg), n, stream())
     return {'rays': rays, 'rgb': rgb, 'fg_mask': fg}

@@ -3,15 +3,13 @@ oracle/rays.py (numpy fp32 restatement of systems/nerf.py:33-91 + models/ray_uti
 Tolerance: origins, colours, masks exact (copies; the mask blend is three fp32 ops in the reference's order); directions 2e-7 absolute
 (the order of the 3-term sums inside torch is not specified).
 
-Written after this round's GPU budget was spent: runs only with NSR_EXPERIMENTAL=1 until seen green on a B200."""
-import os
-
+Seen on a B200 in profiles/r1_experimental_gpu_tests.log (every comparison below held; the only failure there was the n = 0 call at the
+end of the first test, since made an early return)."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='experimental kernels: set NSR_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 from oracle import rays as orays
 

@@ -6,16 +6,18 @@ Checker: oracle.mlp.VanillaMLP (the reference's own fp32 arithmetic, pinned by t
 autograd for the gradients.  Tolerances (fp16 tensor-core operands with fp32 accumulation against fp32 GEMMs): outputs 2e-2 relative to the
 largest output (measured error is ~1e-3), gradients cosine >= 0.999 and 3e-2 of the largest entry.
 
-These kernels were written after this round's GPU budget was spent (nsr_b200.config.experimental): the tests run only with
-NSR_EXPERIMENTAL=1 until they have been seen green on a B200."""
+Status (profiles/r1_experimental_gpu_tests.log, the round's last B200 call): the C4 end-to-end test below PASSED with the fused kernels
+(colours within 5e-3 of the torch layers, gradients of all 16 colour / background tensors aligned); the two direct oracle tests had a
+test-side dtype bug in that run (fixed since) and stay behind NSR_EXPERIMENTAL=1 until they have been seen green -- as do the kernels'
+default switches (nsr_b200.config.experimental)."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='experimental kernels: set NSR_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
+experimental = pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')
 
 from oracle import mlp as omlp, sh as osh
 
@@ -39,17 +41,18 @@ def _oracle_mlp(n_in, n_out, n_hidden, weight_norm, seed):
         for m in net.layers:
             if isinstance(m, torch.nn.Linear):
                 m.bias.uniform_(-0.3, 0.3)
-    return net.double()
+    return net   # fp32: the reference's VanillaMLP casts its input to float (models/network_utils.py:108-112)
 
 
+@experimental
 @pytest.mark.parametrize('n_in,n_out,n_hidden,weight_norm,x_half', [(32, 8, 1, False, True), (24, 3, 2, False, False), (60, 16, 3, True, False),
                                                                      (3, 1, 1, False, False)])
 def test_vanilla_mlp_matches_oracle_forward_and_backward(n_in, n_out, n_hidden, weight_norm, x_half):
     from nsr_b200 import models
     from nsr_b200.models.networks import VanillaMLP
     ref = _oracle_mlp(n_in, n_out, n_hidden, weight_norm, seed=5)
-    net = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=n_hidden, output_activation='none', weight_norm=weight_norm))
-    net.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    net = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=n_hidden, output_activation='none', weight_norm=weight_norm, fused=True))
+    net.load_state_dict(ref.state_dict())
     net = net.to(D)
     g = torch.Generator().manual_seed(21)
     n = 4099                                          # ragged last tile (fwd 32-row, bwd 128-row tiles)
@@ -60,9 +63,9 @@ def test_vanilla_mlp_matches_oracle_forward_and_backward(n_in, n_out, n_hidden, 
     # (as the torch layers would), so keep it out of the subnormal range there
     go = torch.randn(n, n_out, generator=g) * (1.0 if x_half else 1e-4)
 
-    x64 = x.double().requires_grad_()
+    x64 = x.clone().requires_grad_()                  # the oracle side (fp32 on the CPU)
     y64 = ref(x64)
-    (y64 * go.double()).sum().backward()
+    (y64 * go).sum().backward()
 
     xd = (x.half() if x_half else x).to(D).requires_grad_()
     y = net(xd)
@@ -78,11 +81,12 @@ def test_vanilla_mlp_matches_oracle_forward_and_backward(n_in, n_out, n_hidden, 
     assert net(xd[:0].detach()).shape == (0, n_out)
     # fused=False pins the torch layers: same numbers to fp16-operand accuracy
     net_t = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=n_hidden, output_activation='none', weight_norm=weight_norm, fused=False))
-    net_t.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    net_t.load_state_dict(ref.state_dict())
     net_t = net_t.to(D)
     assert not net_t._fused_spec(xd) and close(net_t(xd.detach()), y64.detach(), 1e-4)
 
 
+@experimental
 @pytest.mark.parametrize('n_feat,n_extra,color_act', [(13, 3, 'sigmoid'), (8, 0, 'sigmoid'), (16, 0, None)])
 def test_vanilla_radiance_matches_oracle_forward_and_backward(n_feat, n_extra, color_act):
     """neus-dtu texture (13 + 3 normal + 16 SH = 32) and texture_bg (8 + 16 SH = 24 < 32: zero-padded input columns)"""
@@ -91,9 +95,9 @@ def test_vanilla_radiance_matches_oracle_forward_and_backward(n_feat, n_extra, c
                mlp_network_config=dict(otype='VanillaMLP', activation='ReLU', output_activation='none', n_neurons=64, n_hidden_layers=2))
     if color_act:
         cfg['color_activation'] = color_act
-    tex = models.make('volume-radiance', dict(cfg)).to(D)
+    tex = models.make('volume-radiance', dict(cfg, fused_vanilla=True)).to(D)
     ref = _oracle_mlp(n_feat + 16 + n_extra, 3, 2, False, seed=9)
-    tex.network.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    tex.network.load_state_dict(ref.state_dict())
     g = torch.Generator().manual_seed(11)
     k = 3001
     feat = torch.randn(k, n_feat, generator=g)
@@ -101,19 +105,19 @@ def test_vanilla_radiance_matches_oracle_forward_and_backward(n_feat, n_extra, c
     extra = F.normalize(torch.randn(k, 3, generator=g), dim=-1) if n_extra else None
     go = torch.randn(k, 3, generator=g) * 1e-4
 
-    f64 = feat.double().requires_grad_()
-    e64 = extra.double().requires_grad_() if n_extra else None
-    emb = osh.sh4((dirs.double() + 1) / 2)            # texture.py:24-25: (d+1)/2 -> tcnn SH (which maps back to [-1,1])
+    f64 = feat.clone().requires_grad_()               # the oracle side (fp32 on the CPU)
+    e64 = extra.clone().requires_grad_() if n_extra else None
+    emb = osh.sh4((dirs + 1) / 2)                     # texture.py:24-25: (d+1)/2 -> tcnn SH (which maps back to [-1,1])
     raw = ref(torch.cat([f64, emb] + ([e64] if n_extra else []), dim=-1))
     rgb64 = torch.sigmoid(raw) if color_act else raw
-    (rgb64 * go.double()).sum().backward()
+    (rgb64 * go).sum().backward()
 
     fd = feat.to(D).requires_grad_()
     ed = [extra.to(D).requires_grad_()] if n_extra else []
     rgb = tex(fd, dirs.to(D), *ed)
     assert tex._rspec is not None and tex._rspec.vanilla, 'fused VanillaMLP radiance path not selected'
     (rgb * go.to(D)).sum().backward()
-    assert rgb.dtype == torch.float32 and float((rgb.detach().cpu().double() - rgb64.detach()).abs().max()) < 5e-3
+    assert rgb.dtype == torch.float32 and float((rgb.detach().cpu() - rgb64.detach()).abs().max()) < 5e-3
     assert cos(fd.grad, f64.grad) > 0.999 and close(fd.grad, f64.grad, 3e-2)
     if n_extra:
         assert cos(ed[0].grad, e64.grad) > 0.999
@@ -139,7 +143,14 @@ def test_neus_dtu_step_with_fused_vanilla_networks_matches_torch_layers():
         cfg['texture']['fused_vanilla'] = cfg['texture_bg']['fused_vanilla'] = False
         return cfg
 
-    model, cfg, binary, rays, jitter = build(configs.neus_dtu, 256, 2)
+    def fused():
+        cfg = configs.neus_dtu()
+        for key in ('texture', 'geometry_bg', 'texture_bg'):
+            cfg[key]['mlp_network_config']['fused'] = True
+        cfg['texture']['fused_vanilla'] = cfg['texture_bg']['fused_vanilla'] = True
+        return cfg
+
+    model, cfg, binary, rays, jitter = build(fused, 256, 2)
     model_t = build(pinned, 256, 2)[0]
     model_t.load_state_dict(model.state_dict())
     bgb = torch.from_numpy(np.random.default_rng(0).random((256, 256, 256)) < 0.3)
@@ -155,7 +166,7 @@ def test_neus_dtu_step_with_fused_vanilla_networks_matches_torch_layers():
     assert model.texture._rspec is not None and model.texture._rspec.vanilla and model.geometry_bg.encoding_with_network.network._spec
     assert model_t.texture._rspec is None and not model_t.geometry_bg.encoding_with_network.network._spec
     assert int(a['num_samples_full']) == int(b['num_samples_full']) or abs(int(a['num_samples_bg']) - int(b['num_samples_bg'])) <= 4
-    assert float((a['comp_rgb_full'] - b['comp_rgb_full']).abs().max()) < 5e-3
+    assert float((a['comp_rgb_full'] - b['comp_rgb_full']).detach().abs().max()) < 5e-3
     ga = dict(model.named_parameters())
     checked = 0
     for name, p in model_t.named_parameters():
