@@ -96,3 +96,57 @@ def image_batch(directions, all_c2w, index, all_images=None, all_fg_masks=None, 
     if fg is not None:
         out['fg_mask'] = fg
     return out
+
+
+class RayBudget:
+    """``dynamic_ray_sampling`` of the reference's systems (systems/nerf.py:91-95, systems/neus.py:91-95): after every step
+
+        train_num_rays <- min(int(train_num_rays * 0.9 + int(train_num_rays * (train_num_samples / num_samples)) * 0.1), max_rays)
+
+    with train_num_samples = train_num_rays(0) * num_samples_per_ray.  The reference reads ``out['num_samples'].sum().item()`` -- a
+    host sync in the middle of every step.  Here ``observe()`` queues a non-blocking copy of the device-side count into pinned host
+    memory and ``update()`` folds in every observation whose copy has completed, so the controller runs one step behind the device
+    instead of stalling it (``sync=True`` restores the reference's step-exact behaviour)."""
+
+    def __init__(self, train_num_rays, num_samples_per_ray, max_train_num_rays, sync=False):
+        self.train_num_rays = int(train_num_rays)
+        self.train_num_samples = int(train_num_rays) * int(num_samples_per_ray)
+        self.max_train_num_rays = int(max_train_num_rays)
+        self.sync = bool(sync)
+        self._pending = []  # (pinned host tensor, event or None)
+
+    @staticmethod
+    def rule(train_num_rays, train_num_samples, num_samples, max_train_num_rays):
+        """one update of systems/nerf.py:93-95, literally"""
+        target = int(train_num_rays * (train_num_samples / num_samples))
+        return min(int(train_num_rays * 0.9 + target * 0.1), max_train_num_rays)
+
+    def observe(self, num_samples):
+        """num_samples: the step's sample count(s) as a tensor (out['num_samples'], or the *_full count of NeuS); any shape, summed."""
+        total = num_samples.detach().sum().reshape(1).to(torch.int64)
+        if total.is_cuda:
+            host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+            host.copy_(total, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append((host, ev))
+        else:
+            self._pending.append((total.clone(), None))
+        if self.sync:
+            return self.update(wait=True)
+        return self.train_num_rays
+
+    def update(self, wait=False):
+        """fold in the finished observations (all of them when ``wait``); returns the current train_num_rays"""
+        while self._pending:
+            host, ev = self._pending[0]
+            if ev is not None:
+                if wait:
+                    ev.synchronize()
+                elif not ev.query():
+                    break
+            self._pending.pop(0)
+            n = int(host[0])
+            if n > 0:  # the reference would divide by zero here; an empty step carries no information
+                self.train_num_rays = self.rule(self.train_num_rays, self.train_num_samples, n, self.max_train_num_rays)
+        return self.train_num_rays

@@ -189,3 +189,23 @@ def test_ray_helpers_match_golden_and_kernel_entry_refuses_cpu(golden):
         rays.training_batch(d, c2w, torch.zeros(2, 6, 8, 3), torch.zeros(2, 6, 8), z, z, z)
     with pytest.raises(NotImplementedError):
         rays.image_batch(d, c2w, 0)
+
+
+def test_ray_budget_controller_follows_the_reference_rule():
+    """dynamic_ray_sampling (systems/nerf.py:91-95): the controller applies the reference's update literally, observation by observation"""
+    from nsr_b200.rays import RayBudget
+    rng = np.random.default_rng(0)
+    b = RayBudget(256, 1024, 8192)
+    rays, target = 256, 256 * 1024
+    for step in range(200):
+        k = int(rays * rng.uniform(20, 60))          # samples the step produced
+        got = b.observe(torch.tensor([k // 2, k - k // 2], dtype=torch.int32))   # *_full counts are summed
+        got = b.update()
+        rays = min(int(rays * 0.9 + int(rays * (target / k)) * 0.1), 8192)       # systems/nerf.py:93-95
+        assert got == rays == b.train_num_rays
+    assert 256 < rays <= 8192
+    b.observe(torch.zeros(1, dtype=torch.int32))      # an empty step changes nothing (the reference would raise ZeroDivisionError)
+    assert b.update() == rays
+    s = RayBudget(256, 1024, 8192, sync=True)
+    assert s.observe(torch.tensor([1000])) == RayBudget.rule(256, 256 * 1024, 1000, 8192) == 6941   # 256 * 0.9 + 67108 * 0.1
+    assert RayBudget.rule(256, 256 * 1024, 10, 8192) == 8192                                           # capped at max_train_num_rays
