@@ -29,6 +29,16 @@ def nerf_blender(radius=1.5):
                      mlp_network_config=_ff(2, 'Sigmoid'))))
 
 
+def nerf_vanilla(radius=1.5, n_frequencies=10, n_frequencies_dir=4):
+    """config C1 (BASELINE.json configs[0]): nerf-blender with the reference's pure-torch fields -- VanillaFrequency encodings (the
+    reference gives n_frequencies no default, models/network_utils.py:17; 10 / 4 are the classic NeRF choices) + VanillaMLP networks."""
+    cfg = nerf_blender(radius)
+    cfg['geometry'].update(xyz_encoding_config=dict(otype='VanillaFrequency', n_frequencies=n_frequencies), mlp_network_config=_vanilla(1))
+    cfg['texture'].update(dir_encoding_config=dict(otype='VanillaFrequency', n_frequencies=n_frequencies_dir),
+                          mlp_network_config=_vanilla(2), color_activation='sigmoid')
+    return cfg
+
+
 def neus_blender(radius=1.5):
     return copy.deepcopy(dict(
         name='neus', radius=radius, num_samples_per_ray=1024, train_num_rays=256, max_train_num_rays=8192, grid_prune=True,
