@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 N_RAYS = 8192            # per GPU (max_train_num_rays, configs/nerf-blender.yaml:24)
 POOL = 8                 # distinct ray batches cycled through
 CPU_SAMPLE_RAYS = 1024   # rays per step of the CPU arms (bounded sample of the same workload)
+CPU_RAY_BUDGET = 90000   # rays the reference arm traces in total (steps + warm-up), so that its run time does not grow with --steps
 CPU_MAX_THREADS = 16     # the torch-CPU oracle stops scaling (and then collapses) beyond ~16 threads; `cores` reports what was used
 
 
@@ -57,6 +58,7 @@ def cpu_workload(n_rays, seed):
     dflat.requires_grad_(True)
     cflat.requires_grad_(True)
     P = om.NerfParams(cfg['geometry']['xyz_encoding_config'], dflat, cflat)
+    P.one_gather = True   # one indexing op over all corners: no table-sized autograd temporaries per corner (oracle/hashgrid.py)
     binary = synthetic.occupancy()
     step = np.float32(synthetic.render_step_size())
     tg = torch.Generator().manual_seed(seed)
@@ -94,7 +96,10 @@ def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    r = time_cpu(max(1, args.steps), max(0, args.warmup))
+    # bounded sample: ~90 k rays over the whole run (the port does ~1 k rays/s on 8 cores => the arm ends within ~2 min for any --steps / --warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    n_rays = max(64, min(CPU_SAMPLE_RAYS, CPU_RAY_BUDGET // (steps + warmup)))
+    r = time_cpu(steps, warmup, n_rays=n_rays)
     line = {
         'impl': 'reference', 'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': r['rays_per_s'], 'unit': 'rays/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
@@ -409,7 +414,7 @@ def gpu_arm(args):
         roofline['secondary'] = {'bound': 'l2_red', 'unit': 'G RED/s', 'achieved': reds / (kern[dom]['ms'] * 1e-3) / 1e9, 'peak': 140.0,
                                  'frac': reds / (kern[dom]['ms'] * 1e-3) / 1e9 / 140.0,
                                  'source': 'REDs/sample from ncu (profiles/r1_ncu_traffic.json); peak = measured scatter-only floor (profiles/r1_gather_scatter_microbench.md)'}
-    cpu = time_cpu(2, 1, n_rays=512) if world == 1 else None
+    cpu = time_cpu(8, 2, n_rays=CPU_SAMPLE_RAYS) if world == 1 else None   # ~10 s of CPU work
     line = {
         'metric': 'rays/sec fwd+bwd (NeRF-Synthetic lego shape)', 'value': N_RAYS * world * args.steps / (ms * 1e-3), 'unit': 'rays/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -428,7 +433,7 @@ def gpu_arm(args):
         line['optimizer'] = adamw
     if cpu is not None:
         line['cpu_baseline'] = {'value': cpu['rays_per_s'], 'unit': 'rays/s', 'cores': cpu['cores'], 'kind': 'port',
-                                'sample': f"2 steps x {cpu['n_rays']} rays of the C2 workload (kept {cpu['kept']:.0f} samples/step), fwd+bwd, "
+                                'sample': f"8 steps x {cpu['n_rays']} rays of the C2 workload (kept {cpu['kept']:.0f} samples/step), fwd+bwd, "
                                           f"fp32 CPU oracle, {cpu['cores']} threads"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -64,9 +64,14 @@ def corner_index(ix, iy, iz, res, size, dense):
     return idx % size
 
 
-def hashgrid_fwd(x, table, lt, compute_dtype=torch.float64):
+def hashgrid_fwd(x, table, lt, compute_dtype=torch.float64, one_gather=False):
     """x [N,3] in [0,1]; table [n_entries, F] (any float dtype; values as stored, e.g. already
-    rounded to fp16).  Returns [N, L*F] in compute_dtype (level-major, feature-minor)."""
+    rounded to fp16).  Returns [N, L*F] in compute_dtype (level-major, feature-minor).
+    one_gather=True evaluates the same expression with ONE indexing op over all L*8 corners instead of L*8 separate ones: torch's
+    autograd materialises a table-sized dense gradient per indexing op (128 x 50 MB zero-fills per backward for the 12.6 M-entry
+    table), which says nothing about the algorithm -- the timed CPU baseline (bench.py) uses this form; results agree to rounding."""
+    if one_gather:
+        return _hashgrid_fwd_one_gather(x, table, lt, compute_dtype)
     N = x.shape[0]
     L, F = lt['n_levels'], lt['n_features']
     xs = x.to(compute_dtype)
@@ -89,6 +94,28 @@ def hashgrid_fwd(x, table, lt, compute_dtype=torch.float64):
             acc = acc + w[:, None] * tab[idx]
         outs.append(acc)
     return torch.cat(outs, dim=-1)
+
+
+def _hashgrid_fwd_one_gather(x, table, lt, compute_dtype):
+    N, L, F = x.shape[0], lt['n_levels'], lt['n_features']
+    xs = x.to(compute_dtype)
+    idx_all, w_all = [], []
+    for l in range(L):
+        scale = float(lt['scale'][l])
+        pos32 = fma_f32(x.detach().float(), torch.tensor(scale, dtype=torch.float32), torch.tensor(0.5))
+        cell = torch.floor(pos32)
+        frac = xs * scale + 0.5 - cell.to(compute_dtype)
+        ci = cell.to(torch.int64)
+        res, size, dense, off = int(lt['res'][l]), int(lt['size'][l]), bool(lt['dense'][l]), int(lt['offset'][l])
+        for c in range(8):
+            bx, by, bz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+            w_all.append((frac[:, 0] if bx else 1 - frac[:, 0]) * (frac[:, 1] if by else 1 - frac[:, 1]) *
+                         (frac[:, 2] if bz else 1 - frac[:, 2]))
+            idx_all.append(corner_index(ci[:, 0] + bx, ci[:, 1] + by, ci[:, 2] + bz, res, size, dense) + off)
+    idx = torch.stack(idx_all, dim=1)                       # [N, L*8]
+    w = torch.stack(w_all, dim=1).view(N, L, 8, 1)
+    vals = table[idx].to(compute_dtype).view(N, L, 8, F)    # the one gather (its backward is one scatter-add into the table)
+    return (w * vals).sum(dim=2).reshape(N, L * F)
 
 
 def init_table(lt, seed=1337, dtype=torch.float32):

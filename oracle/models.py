@@ -31,7 +31,7 @@ def nerf_field(P, positions, dirs, radius, emulate_fp16=True, density_only=False
     x01 = contraction.contract_to_unisphere(positions, radius, ctype)
     table = P.density_flat[P.n_mlp:].view(-1, 2)
     table = q(table) if emulate_fp16 else table
-    enc = q(hashgrid.hashgrid_fwd(x01.detach(), table, P.lt, compute_dtype=torch.float32))
+    enc = q(hashgrid.hashgrid_fwd(x01.detach(), table, P.lt, compute_dtype=torch.float32, one_gather=getattr(P, 'one_gather', False)))
     out = q(mlp.ffmlp_fwd(enc, P.density_flat[:P.n_mlp], P.lt['n_output_dims'], P.feature_dim, 64, P.density_hidden, 'ReLU', 'None',
                           emulate_fp16=emulate_fp16))
     density = trunc_exp(out[:, 0] + P.density_bias)

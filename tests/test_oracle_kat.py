@@ -354,3 +354,21 @@ def test_marching_cubes_oracle_properties_and_product_case_table():
     # nothing to extract
     v, f = mcubes.marching_cubes(np.ones((4, 4, 4), np.float32), 2.0)
     assert v.shape == (0, 3) and f.shape == (0, 3)
+
+
+def test_hashgrid_one_gather_form_matches_the_per_corner_form():
+    """the timed CPU baseline evaluates the hash grid with one indexing op over all corners (bench.py): same values and gradients"""
+    cfg = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.5)
+    lt = hashgrid.level_table(cfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(257, 3, generator=g)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        t1 = (hashgrid.init_table(lt, dtype=dtype) * 1e3).requires_grad_(True)
+        t2 = t1.detach().clone().requires_grad_(True)
+        go = torch.randn(257, 32, generator=g).to(dtype)
+        a = hashgrid.hashgrid_fwd(x, t1, lt, compute_dtype=dtype)
+        b = hashgrid.hashgrid_fwd(x, t2, lt, compute_dtype=dtype, one_gather=True)
+        (a * go).sum().backward()
+        (b * go).sum().backward()
+        np.testing.assert_allclose(b.detach().numpy(), a.detach().numpy(), rtol=0, atol=tol)
+        np.testing.assert_allclose(t2.grad.numpy(), t1.grad.numpy(), rtol=0, atol=tol * 10)
