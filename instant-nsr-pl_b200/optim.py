@@ -104,3 +104,31 @@ class FusedAdamW(torch.optim.Optimizer):
                 if mod is not None:   # the fp16 copy is already up to date: re-key the module's cache to the new version
                     mod._half_key = (p._version, p.data_ptr(), p.device)
         return loss
+
+
+def _get_parameters(model, name):
+    m = model
+    for part in name.split('.'):
+        m = getattr(m, part)
+    if isinstance(m, torch.nn.Module):
+        return list(m.parameters())
+    if isinstance(m, torch.nn.Parameter):
+        return [m]
+    return []
+
+
+def parse_optimizer(config, model):
+    """systems/utils.py:314-325 (``parse_optimizer``, called from systems/base.py:119) with the same config section -- ``name``,
+    ``args`` and the optional per-submodule ``params`` (configs/neus-blender.yaml:96-102: geometry / texture / variance ...) -- but
+    ``name: AdamW`` builds the one-pass FusedAdamW (identical update rule, state_dict keys and param groups; it also keeps the fp16
+    parameter copies of the tcnn-shaped modules fresh).  Any other name resolves to ``torch.optim`` as in the reference."""
+    args = dict(config.get('args', {}) or {})
+    if 'params' in config and config['params']:
+        groups = [{'params': _get_parameters(model, name), 'name': name, **dict(group_args or {})} for name, group_args in config['params'].items()]
+    else:
+        groups = [p for p in model.parameters() if p.requires_grad]
+    if config['name'] in ('AdamW', 'FusedAdamW'):
+        args.pop('fused', None)
+        args.pop('foreach', None)
+        return FusedAdamW.for_model(model, params=groups, **args)
+    return getattr(torch.optim, config['name'])(groups, **args)

@@ -209,3 +209,24 @@ def test_ray_budget_controller_follows_the_reference_rule():
     s = RayBudget(256, 1024, 8192, sync=True)
     assert s.observe(torch.tensor([1000])) == RayBudget.rule(256, 256 * 1024, 1000, 8192) == 6941   # 256 * 0.9 + 67108 * 0.1
     assert RayBudget.rule(256, 256 * 1024, 10, 8192) == 8192                                           # capped at max_train_num_rays
+
+
+def test_parse_optimizer_builds_named_param_groups_like_the_reference():
+    """systems/utils.py:314-325 with the optimizer section of configs/neus-blender.yaml:90-102: AdamW -> FusedAdamW with one group per
+    named submodule, the reference's learning rates, and the fp16-copy owners registered for the refresh"""
+    from nsr_b200 import models, configs
+    from nsr_b200.config import Config
+    from nsr_b200.optim import parse_optimizer, FusedAdamW
+    model = models.make('neus', configs.neus_blender())
+    ocfg = Config(dict(name='AdamW', args=dict(lr=0.01, betas=[0.9, 0.99], eps=1.e-15),
+                       params=dict(geometry=dict(lr=0.01), texture=dict(lr=0.01), variance=dict(lr=0.001))))
+    opt = parse_optimizer(ocfg, model)
+    assert isinstance(opt, FusedAdamW) and [g['name'] for g in opt.param_groups] == ['geometry', 'texture', 'variance']
+    assert [g['lr'] for g in opt.param_groups] == [0.01, 0.01, 0.001] and all(g['betas'] == (0.9, 0.99) and g['eps'] == 1e-15 for g in opt.param_groups)
+    n_group = sum(p.numel() for g in opt.param_groups for p in g['params'])
+    assert n_group == sum(p.numel() for p in model.parameters())
+    assert model.geometry.encoding.encoding.params in opt._shadows and model.texture.network.params in opt._shadows
+    sgd = parse_optimizer(Config(dict(name='SGD', args=dict(lr=0.1))), model)
+    assert isinstance(sgd, torch.optim.SGD)
+    whole = parse_optimizer(Config(dict(name='AdamW', args=dict(lr=0.01))), model)
+    assert len(whole.param_groups) == 1 and whole.param_groups[0]['weight_decay'] == 1e-2      # torch.optim.AdamW's default
