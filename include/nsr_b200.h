@@ -248,6 +248,12 @@ int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const floa
                   void* enc_k_h /* fp16 [K,32] packed copy of the saved encodings, may be NULL */,
                   float* xyzdir_k /* f32 [K,6] unit-cube position + view direction per packed row, may be NULL */, int64_t n_rays,
                   void* stream);
+/* nsr_scan_counts(kept) + nsr_pack_kept in one launch: every CTA derives its packed base offset from the kept counts in front of it and
+ * writes offsets_k_out [n_rays + 1] for the kernels behind (nsr_nerf_ray_bwd_loose, nsr_nerf_field_bwd's k_dev = offsets_k_out + n_rays). */
+int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
+                       const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
+                       float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h, void* enc_k_h,
+                       float* xyzdir_k, int64_t n_rays, void* stream);
 /* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min); offsets_k != NULL
  * writes d_sraw / d_rgb in packed row order (row offsets_k[ray] + j) instead of the loose positions. */
 int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx, const float* trans,

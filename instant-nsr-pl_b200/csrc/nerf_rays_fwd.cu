@@ -255,8 +255,13 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid
   }
 }
 
-// kept prefix of every ray: loose (offsets_m) -> packed (offsets_k), for the exact-size per-sample outputs
+// kept prefix of every ray: loose (offsets_m) -> packed (offsets_k), for the exact-size per-sample outputs.
+// SCAN = true (nsr_pack_kept_scan): the packed offsets are computed HERE instead of by a one-CTA scan kernel in front: every CTA sums
+// the kept counts of the rays before its own eight (n_rays^2 / 16 ints of L2 reads in total: 17 MB at 8192 rays) and writes
+// off_k_out[ray] (+ off_k_out[n_rays] by the last CTA) for the kernels behind it.
+template <bool SCAN>
 __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restrict__ off_m, const int64_t* __restrict__ off_k,
+                                                        const int32_t* __restrict__ kept, int64_t* __restrict__ off_k_out,
                                                         const float* __restrict__ t_min, float step, const int32_t* __restrict__ kidx,
                                                         const float* __restrict__ weights, int32_t* __restrict__ ri_k,
                                                         float* __restrict__ ts_k, float* __restrict__ te_k, float* __restrict__ w_k,
@@ -265,8 +270,33 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
                                                         uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int64_t n_rays) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
-  if (ray >= n_rays) return;
-  const int64_t src = off_m[ray], dst = off_k[ray], cnt = off_k[ray + 1] - dst;
+  int64_t dst, cnt;
+  if (SCAN) {
+    __shared__ int64_t s_part[8];
+    const int64_t ray0 = blockIdx.x * 8ll;
+    int64_t sum = 0;
+    for (int64_t r = threadIdx.x; r < ray0; r += 256) sum += __ldg(kept + r);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    int64_t base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += s_part[w];
+    for (int64_t r = ray0; r < ray && r < n_rays; ++r) base += __ldg(kept + r);  // the (at most seven) rays of this CTA in front of mine
+    if (ray >= n_rays) return;
+    dst = base;
+    cnt = __ldg(kept + ray);
+    if (lane == 0) {
+      off_k_out[ray] = dst;
+      if (ray == n_rays - 1) off_k_out[n_rays] = dst + cnt;
+    }
+  } else {
+    if (ray >= n_rays) return;
+    dst = off_k[ray];
+    cnt = off_k[ray + 1] - dst;
+  }
+  const int64_t src = off_m[ray];
   const float tmin = t_min[ray];
   for (int64_t j = lane; j < cnt; j += 32) {
     const float k = (float)kidx[src + j];
@@ -391,10 +421,33 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
   nsr_nerf_t dummy;
   memset(&dummy, 0, sizeof(dummy));
   dummy.radius = 1.f;
-  pack_kept_kernel<<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, t_min, step, kidx, weights, ray_indices_k,
-                                                                            t_starts_k, t_ends_k, weights_k, loose_pos, f ? *f : dummy, rays,
-                                                                            (const uint4*)enc_loose_h, (uint4*)enc_k_h, xyzdir_k, n_rays);
+  pack_kept_kernel<false><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, nullptr, nullptr, t_min, step, kidx, weights,
+                                                                                   ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
+                                                                                   f ? *f : dummy, rays, (const uint4*)enc_loose_h,
+                                                                                   (uint4*)enc_k_h, xyzdir_k, n_rays);
   NSR_CHECK_LAUNCH("nsr_pack_kept");
+  return 0;
+}
+
+extern "C" int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
+                                  const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
+                                  float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h,
+                                  void* enc_k_h, float* xyzdir_k, int64_t n_rays, void* stream) {
+  NSR_REQUIRE(kept != nullptr && offsets_k_out != nullptr, "nsr_pack_kept_scan: kept / offsets_k_out is NULL");
+  if (n_rays == 0) {
+    cudaMemsetAsync(offsets_k_out, 0, sizeof(int64_t), (cudaStream_t)stream);
+    return 0;
+  }
+  NSR_REQUIRE(xyzdir_k == nullptr || (f != nullptr && rays != nullptr), "nsr_pack_kept_scan: xyzdir_k needs the field descriptor and the rays");
+  NSR_REQUIRE(enc_k_h == nullptr || enc_loose_h != nullptr, "nsr_pack_kept_scan: enc_k needs the loose encoding buffer");
+  nsr_nerf_t dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  dummy.radius = 1.f;
+  pack_kept_kernel<true><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, nullptr, kept, offsets_k_out, t_min, step, kidx, weights,
+                                                                                  ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
+                                                                                  f ? *f : dummy, rays, (const uint4*)enc_loose_h,
+                                                                                  (uint4*)enc_k_h, xyzdir_k, n_rays);
+  NSR_CHECK_LAUNCH("nsr_pack_kept_scan");
   return 0;
 }
 

@@ -106,7 +106,8 @@ class _NerfRenderRays(torch.autograd.Function):
         lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
                  ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, stream())
-        lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
+        if not fused.fuse_kept_scan:
+            lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
         # plus (training, tile backward) the backward's inputs in packed row order: encodings, unit-cube position + view direction
         ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
@@ -114,8 +115,12 @@ class _NerfRenderRays(torch.autograd.Function):
         # (+64 rows: the tile backward prefetches whole 64-row tiles with cp.async, the last one may reach past K)
         enc_k = torch.empty(cap + 64, 32, dtype=torch.float16, device=dev) if packed_bwd else None
         xyzdir = f32(cap + 64, 6) if packed_bwd else None
-        lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
-                 ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
+        if fused.fuse_kept_scan:   # the packed offsets are computed inside the pack kernel (one launch and a one-CTA scan less)
+            lib.call('nsr_pack_kept_scan', ptr(offsets_m), ptr(kept), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts),
+                     ptr(te), None, ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
+        else:
+            lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
+                     ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
         ctx.fused, ctx.n_rays, ctx.cap = fused, n, cap
         ctx.set_materialize_grads(False)
         if packed_bwd:
@@ -182,6 +187,8 @@ class NerfFused:
         self.mode = 'per_ray'   # 'per_ray' (persistent per-ray forward kernel) | 'two_pass' (pre-pass / compaction / sample-tile kernels)
         self.lean_static_outputs = False   # static=True: skip the per-ray outputs the fused loss op produces itself (comp_rgb, rays_valid)
         self.packed_bwd_inputs = True   # tile backward reads its inputs in packed row order (written by nsr_pack_kept)
+        from .config import experimental
+        self.fuse_kept_scan = experimental('pack_scan')   # nsr_pack_kept_scan instead of nsr_scan_counts + nsr_pack_kept (not yet timed)
         self.bwd_kernel = 'tiles'  # 'tiles' (sample-tile backward through the packed->loose index) | 'rays' (single per-ray backward kernel)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 

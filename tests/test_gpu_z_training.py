@@ -64,3 +64,23 @@ def test_short_training_run_tracks_the_oracle():
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) <= 3e-2 * b, (losses, ref_losses)
     assert losses[4] < losses[0] and losses[5] < losses[1] and ref_losses[4] < ref_losses[0] and ref_losses[5] < ref_losses[1]
+
+
+def test_pack_kept_scan_variant_is_bit_identical_to_the_two_kernel_form():
+    """nsr_pack_kept_scan (packed offsets computed inside the pack kernel) against nsr_scan_counts + nsr_pack_kept: same packed samples,
+    same per-ray outputs, and -- the backward reading the same rows in the same order -- the same MLP-input gradients up to atomics"""
+    from test_gpu_nerf import build
+    D = torch.device('cuda:0')
+    outs = []
+    for fuse in (False, True):
+        model, cfg, binary, rays, jitter, bg = build('per_ray', n_rays=601)     # not a multiple of 8: ragged last CTA
+        model._fused.fuse_kept_scan = fuse
+        out = model.forward_(torch.from_numpy(rays).to(D), jitter=torch.from_numpy(jitter))
+        (out['comp_rgb'].square().mean() + 0.1 * out['opacity'].mean()).backward()
+        outs.append((out, model.geometry.encoding_with_network.params.grad.clone(), model.texture.network.params.grad.clone()))
+    (a, gda, gca), (b, gdb, gcb) = outs
+    assert int(a['num_samples']) == int(b['num_samples']) > 1000
+    for k in ('ray_indices', 'points', 'intervals', 'weights', 'comp_rgb', 'opacity', 'depth'):
+        assert torch.equal(a[k], b[k]), k
+    assert float((gca - gcb).abs().max()) <= 1e-6 * float(gca.abs().max()) + 1e-12
+    assert float((gda - gdb).abs().max()) <= 1e-5 * float(gda.abs().max()) + 1e-12
