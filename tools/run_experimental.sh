@@ -15,3 +15,15 @@ tail -c 1500 gpurun_out/neus_times_torch_mlps.json; echo; tail -c 1500 gpurun_ou
 timeout 600 python tools/train_synthetic.py --model nerf --steps 2000 --export > gpurun_out/train_nerf.json 2> gpurun_out/train_nerf.err
 timeout 600 python tools/train_synthetic.py --model neus --steps 2000 --export > gpurun_out/train_neus.json 2> gpurun_out/train_neus.err
 tail -c 800 gpurun_out/train_nerf.json; tail -c 600 gpurun_out/train_nerf.err; tail -c 800 gpurun_out/train_neus.json; tail -c 600 gpurun_out/train_neus.err
+# A/B of the opt-in step variants on the bench workload (C2, one GPU)
+NSR_EXPERIMENTAL=0 timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+NSR_EXPERIMENTAL=pack_scan timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_pack_scan.json 2> gpurun_out/bench_pack_scan.err
+python - <<'PY'
+import json
+for name in ('default', 'pack_scan'):
+    try:
+        d = json.loads(open(f'gpurun_out/bench_{name}.json').read().strip().splitlines()[-1])
+        print(name, d['ms_per_step'], d['value'], d.get('kernels_ms'))
+    except Exception as e:
+        print(name, 'failed', e)
+PY
