@@ -135,6 +135,7 @@ class _Lib:
         self._dll = None
         self.launches = 0     # C-ABI calls that launch one of our kernels (bench.py reports it)
         self.profile = None   # dict name -> [(start_event, end_event)] when per-call CUDA-event timing is on
+        self.nvtx = os.environ.get('NSR_NVTX', '') not in ('', '0')   # NVTX range per C-ABI call (nsys / ncu --nvtx timelines)
 
     def _load(self):
         path = library_path()
@@ -164,7 +165,13 @@ class _Lib:
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = fn(*args)
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(name)
+        try:
+            rc = fn(*args)
+        finally:
+            if self.nvtx:
+                torch.cuda.nvtx.range_pop()
         if rc != 0:
             raise NsrError(f'{name} failed ({rc}): {self.dll.nsr_last_error().decode()}')
         self.launches += _KERNELS_PER_CALL.get(name, 1)
