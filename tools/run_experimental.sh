@@ -27,3 +27,9 @@ for name in ('default', 'pack_scan'):
     except Exception as e:
         print(name, 'failed', e)
 PY
+# memcheck of the kernels added at the end of round 1 (small test cases only; compute-sanitizer slows kernels down 10-100x)
+NSR_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_z_frontend.py \
+  "tests/test_gpu_z_export.py::test_marching_cubes_matches_oracle_exactly" "tests/test_gpu_z_vanilla.py::test_vanilla_mlp_matches_oracle_forward_and_backward" \
+  "tests/test_gpu_z_vanilla.py::test_vanilla_radiance_matches_oracle_forward_and_backward" -q -x -p no:cacheprovider > gpurun_out/memcheck_new_kernels.log 2>&1
+echo "memcheck exit $?" >> gpurun_out/memcheck_new_kernels.log
+tail -15 gpurun_out/memcheck_new_kernels.log
