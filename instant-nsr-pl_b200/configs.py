@@ -62,3 +62,16 @@ def neus_dtu(radius=1.0):
     cfg['texture_bg'] = dict(name='volume-radiance', input_feature_dim=8, dir_encoding_config=dict(otype='SphericalHarmonics', degree=4),
                              mlp_network_config=_vanilla(2), color_activation='sigmoid')
     return cfg
+
+
+def neuralangelo_dtu(radius=1.0):
+    """configs/neuralangelo-dtu-wmask.yaml:18-75: NeuS with a ProgressiveBandHashGrid (levels switched on every 1000 steps), finite-difference
+    normals with the progressive step, VanillaMLP colour network; no learned background."""
+    cfg = neus_blender(radius)
+    cfg.update(ray_chunk=2048)
+    cfg['geometry'].update(grad_type='finite_difference', finite_difference_eps='progressive',
+                           xyz_encoding_config=dict(_HASH_NEUS, otype='ProgressiveBandHashGrid', include_xyz=True, start_level=4, start_step=0,
+                                                    update_steps=1000))
+    cfg['texture']['mlp_network_config'] = _vanilla(2)
+    return cfg
+

@@ -230,3 +230,24 @@ def test_parse_optimizer_builds_named_param_groups_like_the_reference():
     assert isinstance(sgd, torch.optim.SGD)
     whole = parse_optimizer(Config(dict(name='AdamW', args=dict(lr=0.01))), model)
     assert len(whole.param_groups) == 1 and whole.param_groups[0]['weight_decay'] == 1e-2      # torch.optim.AdamW's default
+
+
+def test_neuralangelo_schedules_follow_the_reference():
+    """ProgressiveBandHashGrid level mask (models/network_utils.py:40-65) and the progressive finite-difference step
+    (models/geometry.py:223-238) as functions of global_step, for configs/neuralangelo-dtu-wmask.yaml"""
+    from nsr_b200 import models, configs
+    cfg = configs.neuralangelo_dtu()
+    model = models.make('neus', cfg)
+    geo = model.geometry
+    enc = geo.encoding.encoding
+    assert type(enc).__name__ == 'ProgressiveBandHashGrid' and geo.grad_type == 'finite_difference' and not geo._fused
+    hg = cfg['geometry']['xyz_encoding_config']
+    for step in (0, 1, 999, 1000, 4500, 11999, 12000, 50000):
+        geo.update_step(0, step)
+        level = min(hg['start_level'] + max(step - hg['start_step'], 0) // hg['update_steps'], hg['n_levels'])
+        assert enc.current_level == level
+        mask = enc.mask
+        assert mask.shape == (32,) and float(mask[:2 * level].min()) == 1.0 and float(mask[2 * level:].abs().sum()) == 0.0
+        eps = 2 * cfg['radius'] / (hg['base_resolution'] * hg['per_level_scale'] ** (level - 1))
+        assert geo._finite_difference_eps == pytest.approx(eps, rel=1e-12)
+    assert enc.current_level == 16 and geo._finite_difference_eps == pytest.approx(2.0 / (32 * 1.3195079107728942 ** 15))

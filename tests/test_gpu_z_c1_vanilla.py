@@ -66,3 +66,49 @@ def test_c1_vanilla_nerf_matches_oracle(fused_mlp):
             assert p.grad is not None and cos(p.grad, rg[name].grad) > ctol, name
     if fused_mlp:
         assert geo._spec and tex._spec               # 60 -> 64 -> 16 and 40 -> 64 -> 64 -> 3 on nsr_mlp_vanilla_*
+
+
+def test_neuralangelo_config_finite_difference_normals_and_laplacian():
+    """configs/neuralangelo-dtu-wmask.yaml through the drop-in 'neus' model (per-op kernels + torch: ProgressiveBandHashGrid mask,
+    finite-difference normals and laplacian, models/geometry.py:181-199): the module's normals / laplacian equal central differences of
+    its own SDF queries, masked levels contribute nothing, the step trains (finite gradients everywhere incl. the curvature term)."""
+    from nsr_b200 import models, configs
+    from test_gpu_neus import sphere_occupancy
+    cfg = configs.neuralangelo_dtu()
+    torch.manual_seed(0)
+    model = models.make('neus', cfg).to(D)
+    geo = model.geometry
+    g = torch.Generator().manual_seed(1)
+    enc = geo.encoding.encoding
+    with torch.no_grad():
+        enc.encoding.params.copy_(((torch.rand(enc.encoding.params.numel(), generator=g) * 2 - 1) * 0.02).to(D))
+        v = geo.network.layers[0].weight_v
+        v[:, 3:] = (torch.randn(v.shape[0], v.shape[1] - 3, generator=g) * 0.05).to(D)
+    model.train()
+    model.update_step(0, 2500)                          # level 6 of 16: features of levels >= 6 are masked out
+    assert enc.current_level == 6
+    eps = geo._finite_difference_eps
+    pts = ((torch.rand(2000, 3, generator=g) * 2 - 1) * 0.8).to(D)
+    sdf, grad, feat, lap = geo(pts, with_grad=True, with_feature=True, with_laplace=True)
+    e = torch.zeros(6, 3, device=D)
+    for a in range(3):
+        e[2 * a, a], e[2 * a + 1, a] = eps, -eps
+    nb = torch.stack([geo(pts + e[j], with_grad=False, with_feature=False) for j in range(6)], dim=-1)
+    assert torch.allclose(grad, 0.5 * (nb[:, 0::2] - nb[:, 1::2]) / eps, atol=1e-4)
+    assert torch.allclose(lap, (nb[:, 0::2] + nb[:, 1::2] - 2 * sdf[:, None]).sum(-1) / eps ** 2, rtol=1e-3, atol=1e-2 / eps)
+    raw = enc.encoding(((pts / cfg['radius']) + 1) / 2)
+    assert float(raw[:, 12:].abs().max()) > 0 and float(enc(((pts / cfg['radius']) + 1) / 2)[:, 12:].abs().max()) == 0.0
+    # one rendering step with the reference's loss terms incl. curvature (systems/neus.py:98-121)
+    model.occupancy_grid.set_binary(torch.from_numpy(sphere_occupancy(radius=cfg['radius'], r_in=0.3, r_out=0.7)))
+    from nsr_b200 import synthetic
+    rays = synthetic.sample_rays(256, seed=2)
+    rays[:, :3] *= cfg['radius'] / 1.5 * 0.6
+    model.background_color = torch.ones(3, device=D)
+    out = model.forward_(torch.from_numpy(rays).to(D), jitter=torch.rand(256, generator=g))
+    assert int(out['num_samples']) > 0 and 'sdf_laplace_samples' in out
+    loss = out['comp_rgb_full'].square().mean() + 0.1 * ((out['sdf_grad_samples'].norm(dim=-1) - 1) ** 2).mean() \
+        + 1e-4 * out['sdf_laplace_samples'].abs().mean()
+    loss.backward()
+    for name, p in model.named_parameters():
+        if p.requires_grad and p.numel() > 0:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
