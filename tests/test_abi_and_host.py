@@ -251,3 +251,20 @@ def test_neuralangelo_schedules_follow_the_reference():
         eps = 2 * cfg['radius'] / (hg['base_resolution'] * hg['per_level_scale'] ** (level - 1))
         assert geo._finite_difference_eps == pytest.approx(eps, rel=1e-12)
     assert enc.current_level == 16 and geo._finite_difference_eps == pytest.approx(2.0 / (32 * 1.3195079107728942 ** 15))
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/nsr_b200.h must compile as C99 (and C++17) with nothing but <stdint.h>"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    hdr = os.path.join(ROOT, 'include', 'nsr_b200.h')
+    c = tmp_path / 't.c'
+    c.write_text(f'#include "{hdr}"\nint main(void) {{ nsr_grid_t g; nsr_radiance_t r; (void)g; (void)r; return nsr_version() > 0 ? 0 : 1; }}\n')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', str(c)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp = tmp_path / 't.cpp'
+    cpp.write_text(f'#include "{hdr}"\nint main() {{ return 0; }}\n')
+    r = subprocess.run(['g++', '-std=c++17', '-Wall', '-Werror', '-fsyntax-only', str(cpp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
