@@ -268,3 +268,39 @@ def test_header_is_plain_c(tmp_path):
     cpp.write_text(f'#include "{hdr}"\nint main() {{ return 0; }}\n')
     r = subprocess.run(['g++', '-std=c++17', '-Wall', '-Werror', '-fsyntax-only', str(cpp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_struct_layouts_match_the_c_compiler(tmp_path):
+    """every struct that crosses the ABI by pointer: ctypes size / field offsets == what gcc lays out for include/nsr_b200.h"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    import importlib
+    L = importlib.import_module('nsr_b200.lib')   # (the package attribute `lib` is the loader instance, not the module)
+    pairs = [('nsr_grid_t', L.GridT, ['n_levels', 'n_features', 'scale', 'res', 'size', 'offset', 'dense_mask']),
+             ('nsr_mlp_t', L.MlpT, ['n_in', 'n_out', 'n_hidden', 'activation', 'out_activation']),
+             ('nsr_march_t', L.MarchT, ['roi', 'res', 'contraction', 'step', 'cone_angle']),
+             ('nsr_nerf_t', L.NerfT, ['grid', 'radius', 'density_bias', 'feature_dim', 'density_hidden', 'color_hidden']),
+             ('nsr_radiance_t', L.RadianceT, ['n_feat', 'n_extra', 'act_mode']),
+             ('nsr_adamw_t', L.AdamWT, ['lr', 'beta1', 'beta2', 'eps', 'weight_decay', 'step', 'inv_grad_scale']),
+             ('nsr_neus_loss_t', L.NeusLossT, ['lambda_rgb_mse', 'lambda_rgb_l1', 'lambda_eikonal', 'lambda_mask', 'lambda_opaque',
+                                              'lambda_sparsity', 'sparsity_scale'])]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "nsr_b200.h")}"', 'int main(void) {']
+    for cname, _, fields in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src, exe = tmp_path / 'layout.c', tmp_path / 'layout'
+    src.write_text('\n'.join(lines))
+    r = subprocess.run(['gcc', '-std=c99', str(src), '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line, (cname, ct, fields) in zip(out, pairs):
+        parts = line.split()
+        assert parts[0] == cname and int(parts[1]) == ctypes.sizeof(ct), (cname, parts[1], ctypes.sizeof(ct))
+        for f, off in zip(fields, parts[2:]):
+            assert getattr(ct, f).offset == int(off), (cname, f)
