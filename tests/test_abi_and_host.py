@@ -304,3 +304,59 @@ def test_ctypes_struct_layouts_match_the_c_compiler(tmp_path):
         assert parts[0] == cname and int(parts[1]) == ctypes.sizeof(ct), (cname, parts[1], ctypes.sizeof(ct))
         for f, off in zip(fields, parts[2:]):
             assert getattr(ct, f).offset == int(off), (cname, f)
+
+
+def test_python_signatures_match_the_header_prototypes():
+    """argtypes in nsr_b200/lib.py against the prototypes of include/nsr_b200.h, argument by argument (pointer / int64 / int32 / float)"""
+    import importlib
+    L = importlib.import_module('nsr_b200.lib')
+    src = open(os.path.join(ROOT, 'include', 'nsr_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
+    protos = dict(re.findall(r'\bint\s+(nsr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;', src, flags=re.S))
+    kind = {L.P: 'ptr', L.I64: 'i64', L.I32: 'i32', L.F32: 'f32'}
+
+    def classify(arg):
+        arg = ' '.join(arg.split())
+        if '*' in arg:
+            return 'ptr'
+        if arg.startswith('int64_t'):
+            return 'i64'
+        if arg.startswith(('int32_t', 'int ', 'uint32_t')):
+            return 'i32'
+        if arg.startswith('float'):
+            return 'f32'
+        raise AssertionError(f'unclassified argument {arg!r}')
+
+    checked = 0
+    for name, argtypes in L._SIGNATURES.items():
+        assert name in protos, f'{name} bound in lib.py but has no int-returning prototype in the header'
+        args = [a for a in protos[name].split(',') if a.strip() and a.strip() != 'void']
+        got = [classify(a) for a in args]
+        want = [kind[t] for t in argtypes]
+        assert got == want, f'{name}: header {got} vs lib.py {want}'
+        checked += 1
+    assert checked >= 60
+
+
+def test_every_call_site_passes_the_declared_number_of_arguments():
+    """static check of all ``lib.call('nsr_...', ...)`` sites in the package, tools and bench: ctypes would only complain on a GPU box"""
+    import ast
+    import glob
+    import importlib
+    L = importlib.import_module('nsr_b200.lib')
+    files = glob.glob(os.path.join(ROOT, 'instant-nsr-pl_b200', '**', '*.py'), recursive=True) + glob.glob(os.path.join(ROOT, 'tools', '*.py')) \
+        + [os.path.join(ROOT, 'bench.py')]
+    sites = 0
+    for path in files:
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == 'call' and node.args \
+                    and isinstance(node.args[0], ast.Constant) and isinstance(node.args[0].value, str) and node.args[0].value.startswith('nsr_'):
+                name = node.args[0].value
+                assert name in L._SIGNATURES, f'{path}:{node.lineno}: {name} is not declared in lib.py'
+                if any(isinstance(a, ast.Starred) for a in node.args):
+                    continue
+                assert len(node.args) - 1 == len(L._SIGNATURES[name]), \
+                    f'{path}:{node.lineno}: {name} called with {len(node.args) - 1} arguments, declared {len(L._SIGNATURES[name])}'
+                sites += 1
+    assert sites >= 60
