@@ -360,3 +360,18 @@ def test_every_call_site_passes_the_declared_number_of_arguments():
                     f'{path}:{node.lineno}: {name} called with {len(node.args) - 1} arguments, declared {len(L._SIGNATURES[name])}'
                 sites += 1
     assert sites >= 60
+
+
+def test_product_never_imports_the_oracle_or_reads_the_reference():
+    """the oracle is test infrastructure: nothing under instant-nsr-pl_b200/ or tools/ imports it (bench.py only inside its CPU legs,
+    __graft_entry__ only inside smoke()), and no product file opens /root/reference"""
+    import glob
+    for path in glob.glob(os.path.join(ROOT, 'instant-nsr-pl_b200', '**', '*.py'), recursive=True) + glob.glob(os.path.join(ROOT, 'tools', '*.py')):
+        text = open(path).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), path
+        assert '/root/reference' not in text, path
+    bench = open(os.path.join(ROOT, 'bench.py')).read()
+    assert not re.search(r'^(from|import)\s+oracle\b', bench, flags=re.M)          # no module-level import: only inside cpu_workload()
+    assert len(re.findall(r'^\s+from oracle import', bench, flags=re.M)) == 1 and 'def cpu_workload' in bench
+    entry = open(os.path.join(ROOT, '__graft_entry__.py')).read()
+    assert entry.index('from oracle import') > entry.index('def smoke()')
