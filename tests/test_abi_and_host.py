@@ -375,3 +375,15 @@ def test_product_never_imports_the_oracle_or_reads_the_reference():
     assert len(re.findall(r'^\s+from oracle import', bench, flags=re.M)) == 1 and 'def cpu_workload' in bench
     entry = open(os.path.join(ROOT, '__graft_entry__.py')).read()
     assert entry.index('from oracle import') > entry.index('def smoke()')
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """no silent fallback: without libnsr_b200.so the first call raises NsrError naming the build command"""
+    import importlib
+    L = importlib.import_module('nsr_b200.lib')
+    fresh = L._Lib()
+    monkeypatch.setattr(L, 'library_path', lambda: str(tmp_path / 'libnsr_b200.so'))
+    with pytest.raises(L.NsrError, match='build'):
+        fresh.call('nsr_version')
+    with pytest.raises(L.NsrError):
+        _ = fresh.dll
