@@ -32,3 +32,25 @@ def test_reference_models_build_on_our_modules():
     assert nerf['tcnn_modules'] == ['Encoding', 'Network', 'NetworkWithInputEncoding']
     assert neus['tcnn_modules'] == ['Encoding', 'Network']
     assert dtu['n_params'] == dtu['n_params_ours'] and dtu['tcnn_modules'] == ['Encoding']  # neus-dtu: VanillaMLPs everywhere
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='/root/reference is not mounted here')
+def test_oracle_orchestration_is_pinned_to_the_reference_forward():
+    """oracle/models.py (nerf_render, neus_render) restates models/nerf.py:61-127 and models/neus.py:205-287.  Here the reference's
+    OWN forward_ runs on the CPU -- tinycudann / nerfacc replaced by per-op stand-ins built from the oracle's primitives
+    (tests/helpers/cpu_thirdparty.py), fp32 throughout -- and every output and parameter gradient (incl. the double backward of the
+    eikonal term through the reference's VolumeSDF) must equal the oracle's: the glue is pinned, the third-party arithmetic stays ours
+    on both sides."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'reference_forward.py')], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
+    nerf, neus = res['nerf'], res['neus']
+    assert nerf['keys'] == ['comp_rgb', 'depth', 'intervals', 'num_samples', 'opacity', 'points', 'ray_indices', 'rays_valid', 'weights']
+    assert nerf['num_samples'] == nerf['num_samples_oracle'] and 0.3 * nerf['num_marched'] < nerf['num_samples'] < 0.9 * nerf['num_marched']
+    assert nerf['rays_valid_equal'] and max(nerf['diff'].values()) < 1e-6 and max(nerf['grad_diff']) < 1e-5
+    assert set(neus['keys']) >= {'comp_rgb', 'comp_normal', 'opacity', 'depth', 'rays_valid', 'num_samples', 'sdf_samples', 'sdf_grad_samples',
+                                 'weights', 'points', 'intervals', 'ray_indices', 'comp_rgb_bg', 'num_samples_bg', 'rays_valid_bg',
+                                 'comp_rgb_full', 'num_samples_full', 'rays_valid_full'}
+    assert neus['num_samples'] == neus['num_samples_oracle'] > 5000 and neus['cos_anneal_ratio'] == 0.25
+    assert max(neus['diff'].values()) < 5e-6 and neus['inv_s_diff'] == 0.0 and max(neus['grad_diff'].values()) < 1e-5
