@@ -164,8 +164,11 @@ def neus_render(P, rays, binary, radius, step, bg_color, cos_anneal_ratio, jitte
     inv_s = neus.inv_s_from_variance(P.variance)
     alpha = neus.get_alpha(sdf, normal, t_dirs, dists, inv_s, cos_anneal_ratio)[:, None]
     shv = q(sh.sh4((t_dirs + 1.) / 2.))
-    rgb = torch.sigmoid(mlp.ffmlp_fwd(torch.cat([feature, shv, normal], dim=-1), P.color_flat, P.feature_dim + 16 + 3, 3, 64, P.color_hidden,
-                                      'ReLU', 'None', emulate_fp16=emulate_fp16))
+    if getattr(P, 'color_mlp', None) is not None:   # neus-dtu.yaml:58-70: the colour network is the reference's VanillaMLP (fp32, biases)
+        rgb = torch.sigmoid(P.color_mlp(torch.cat([feature, shv, normal], dim=-1)))
+    else:
+        rgb = torch.sigmoid(mlp.ffmlp_fwd(torch.cat([feature, shv, normal], dim=-1), P.color_flat, P.feature_dim + 16 + 3, 3, 64, P.color_hidden,
+                                          'ReLU', 'None', emulate_fp16=emulate_fp16))
     w = render.render_weight_from_alpha(alpha, ri_t, n_rays)
     opacity = render.accumulate_along_rays(w, ri_t, None, n_rays)
     depth = render.accumulate_along_rays(w, ri_t, mid, n_rays)
@@ -175,3 +178,74 @@ def neus_render(P, rays, binary, radius, step, bg_color, cos_anneal_ratio, jitte
             'num_samples': torch.tensor([len(ts_t)], dtype=torch.int32), 'sdf_samples': sdf, 'sdf_grad_samples': grad,
             'weights': w.view(-1), 'points': mid.view(-1), 'intervals': dists.view(-1), 'ray_indices': ri_t,
             'comp_rgb_full': comp + bg_color * (1.0 - opacity), 'inv_s': torch.exp(P.variance * 10.0), 'alpha': alpha.view(-1), 'rgb': rgb}
+
+
+# --------------------------------------------------------------------------------------------------
+# NeuS with learned background (config C4: neus-dtu.yaml)
+# --------------------------------------------------------------------------------------------------
+class NeusBgParams:
+    """background fields of neus-dtu.yaml:72-105: hash table + VanillaMLP density network (32 -> 64 -> 8) and VanillaMLP colour network
+    ([feature 8 | SH4 16] -> 64 -> 64 -> 3), both passed as modules (the reference's own arithmetic, pinned by the golden vectors)."""
+
+    def __init__(self, grid_cfg, table_flat, density_mlp, color_mlp, density_bias=-1.0):
+        self.lt = hashgrid.level_table(grid_cfg)
+        self.table_flat, self.density_mlp, self.color_mlp, self.density_bias = table_flat, density_mlp, color_mlp, density_bias
+
+
+def neus_bg_field(P, positions, dirs, radius, emulate_fp16=True, density_only=False):
+    """VolumeDensity (UN_BOUNDED_SPHERE contraction) + VolumeRadiance with VanillaMLPs (geometry.py:122-130, texture.py:23-30)"""
+    q = (lambda t: t.half().float()) if emulate_fp16 else (lambda t: t)
+    x01 = contraction.contract_to_unisphere(positions, radius, contraction.UN_BOUNDED_SPHERE)
+    table = P.table_flat.view(-1, 2)
+    table = q(table) if emulate_fp16 else table
+    enc = q(hashgrid.hashgrid_fwd(x01.detach(), table, P.lt, compute_dtype=torch.float32, one_gather=True))
+    out = P.density_mlp(enc).float()
+    density = trunc_exp(out[:, 0] + P.density_bias)
+    if density_only:
+        return density, None
+    shv = q(sh.sh4((dirs + 1.) / 2.))
+    return density, torch.sigmoid(P.color_mlp(torch.cat([out, shv], dim=-1)))
+
+
+def neus_bg_render(P, rays, binary_bg, radius, step, cone_angle, near_plane, far_plane, bg_color, emulate_fp16=True, early_stop_eps=1e-4):
+    """NeuSModel.forward_bg_ (models/neus.py:141-203): start where the ray leaves the foreground box (or at near_plane when it misses
+    it), blind cone stepping through the contracted 256^3 grid, sigma_fn visibility pre-pass, NeRF-style compositing."""
+    rays = np.asarray(rays, np.float32)
+    o, d = rays[:, :3], rays[:, 3:6]
+    n_rays = len(rays)
+    aabb = np.array([-radius] * 3 + [radius] * 3, np.float32)
+    _, t_box = march.ray_aabb_intersect(o, d, aabb)
+    near = np.where(t_box > 1e9, np.float32(near_plane), t_box).astype(np.float32)   # neus.py:157
+    t0, t1 = march.ray_interval(o, d, None, near, far_plane, step, None)
+    ri, ts, te, _ = march.march_sequential(o, d, aabb, binary_bg, step, cone_angle, t0, t1, march.UN_BOUNDED_SPHERE)
+    ri_t, ts_t, te_t = torch.from_numpy(ri).long(), _t(ts)[:, None], _t(te)[:, None]
+    ot, dt = _t(o), _t(d)
+    with torch.no_grad():
+        sig, _ = neus_bg_field(P, ot[ri_t] + dt[ri_t] * (ts_t + te_t) / 2., None, radius, emulate_fp16, density_only=True)
+        keep, _ = render.render_visibility((1.0 - torch.exp(-sig[:, None] * (te_t - ts_t))).view(-1), ri_t, n_rays, early_stop_eps, 0.0)
+    n_marched = len(ri)
+    ri_t, ts_t, te_t = ri_t[keep], ts_t[keep], te_t[keep]
+    mid = (ts_t + te_t) / 2.
+    density, rgb = neus_bg_field(P, ot[ri_t] + dt[ri_t] * mid, dt[ri_t], radius, emulate_fp16)
+    w = render.render_weight_from_density(ts_t, te_t, density[:, None], ri_t, n_rays)
+    opacity = render.accumulate_along_rays(w, ri_t, None, n_rays)
+    depth = render.accumulate_along_rays(w, ri_t, mid, n_rays)
+    comp = render.accumulate_along_rays(w, ri_t, rgb, n_rays) + bg_color * (1.0 - opacity)
+    return {'comp_rgb': comp, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
+            'num_samples': torch.tensor([len(ts_t)], dtype=torch.int32), 'num_marched': n_marched,
+            'weights': w.view(-1), 'points': mid.view(-1), 'intervals': (te_t - ts_t).view(-1), 'ray_indices': ri_t.view(-1)}
+
+
+def neus_dtu_render(P, Pbg, rays, binary, binary_bg, radius, step, bg_step, bg_cone_angle, bg_near, bg_far, bg_color, cos_anneal_ratio,
+                    emulate_fp16=True):
+    """NeuSModel.forward_ with learned_background (models/neus.py:205-287): foreground NeuS pass, background pass, composition
+    ``comp_rgb_full = comp_rgb + comp_rgb_bg * (1 - opacity)`` and the *_bg / *_full dictionary keys."""
+    fg = neus_render(P, rays, binary, radius, step, bg_color, cos_anneal_ratio, jitter=None, emulate_fp16=emulate_fp16)
+    bg = neus_bg_render(Pbg, rays, binary_bg, radius, bg_step, bg_cone_angle, bg_near, bg_far, bg_color, emulate_fp16=emulate_fp16)
+    out = {k: v for k, v in fg.items() if k not in ('comp_rgb_full', 'alpha', 'rgb', 'inv_s')}
+    out.update({k + '_bg': v for k, v in bg.items() if k != 'num_marched'})
+    out['comp_rgb_full'] = fg['comp_rgb'] + bg['comp_rgb'] * (1.0 - fg['opacity'])
+    out['num_samples_full'] = fg['num_samples'] + bg['num_samples']
+    out['rays_valid_full'] = fg['rays_valid'] | bg['rays_valid']
+    return out
+

@@ -92,12 +92,19 @@ class OccupancyGrid(nn.Module):
 @torch.no_grad()
 def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=None, sigma_fn=None, alpha_fn=None, early_stop_eps=1e-4,
                  alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3, stratified=False, cone_angle=0.0):
-    assert not stratified and cone_angle == 0.0 and alpha_fn is None and scene_aabb is not None and grid is not None
+    """nerfacc 0.3.3 ray_marching semantics from the oracle's marchers: the step lattice for AABB grids with
+    cone_angle 0, blind cone stepping through the grid's own (contracted) region otherwise; then the sigma_fn visibility filter"""
+    assert not stratified and alpha_fn is None and grid is not None
     o, d = rays_o.numpy().astype(np.float32), rays_d.numpy().astype(np.float32)
-    aabb = scene_aabb.numpy().astype(np.float32)
     step = np.float32(render_step_size)
-    t0, t1 = march.ray_interval(o, d, aabb, near_plane, far_plane, step, None)
-    ri, ts, te, _ = march.march_lattice(o, d, aabb, grid.binary.numpy(), step, t0, t1)
+    near = near_plane.numpy().astype(np.float32) if torch.is_tensor(near_plane) else near_plane
+    box = None if scene_aabb is None else scene_aabb.numpy().astype(np.float32)
+    t0, t1 = march.ray_interval(o, d, box, near, far_plane, step, None)
+    roi = grid._roi_aabb.numpy().astype(np.float32)
+    if grid.contraction_type == ContractionType.AABB and cone_angle == 0.0:
+        ri, ts, te, _ = march.march_lattice(o, d, roi, grid.binary.numpy(), step, t0, t1)
+    else:
+        ri, ts, te, _ = march.march_sequential(o, d, roi, grid.binary.numpy(), step, cone_angle, t0, t1, grid.contraction_type.value)
     ri_t, ts_t, te_t = torch.from_numpy(ri).long(), torch.from_numpy(ts)[:, None], torch.from_numpy(te)[:, None]
     if sigma_fn is not None:
         sig = sigma_fn(ts_t, te_t, ri_t)

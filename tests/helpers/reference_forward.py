@@ -132,6 +132,54 @@ def main():
                                                             'weights', 'points', 'intervals', 'ray_indices', 'comp_rgb_full')},
                    'inv_s_diff': diff(model.variance.inv_s, o['inv_s']),
                    'grad_diff': {k: diff(g_ref[k], params[k].grad) / (float(params[k].grad.abs().max()) + 1e-30) for k in names}}
+    # ---- NeuS with learned background (neus-dtu.yaml: config C4)
+    cfg = configs.neus_dtu()
+    cfg['randomized'] = False
+    torch.manual_seed(2)
+    model = ref_models.make('neus', Config(cfg))
+    r = cfg['radius']
+    with torch.no_grad():
+        v = model.geometry.network.layers[0].weight_v
+        v[:, 3:] = torch.randn(v.shape[0], v.shape[1] - 3) * 0.05
+        model.geometry_bg.encoding_with_network.network.layers[-1].bias[0] = 2.5      # background densities ~ exp(1.5): visibly opaque
+    g = (np.arange(128) + 0.5) / 128 * 2 * r - r
+    X, Y, Z = np.meshgrid(g, g, g, indexing='ij')
+    dist = np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+    shell = (dist > 0.35 * r) & (dist < 0.65 * r)
+    bgb = np.random.default_rng(0).random((256, 256, 256)) < 0.3
+    model.occupancy_grid._binary.copy_(torch.from_numpy(shell))
+    model.occupancy_grid_bg._binary.copy_(torch.from_numpy(bgb))
+    model.train()
+    model.update_step(0, 5000)
+    model.background_color = bg
+    rays_c4 = rays.copy()
+    rays_c4[:, :3] *= r / 1.5 * 0.6
+    out = model.forward_(torch.from_numpy(rays_c4))
+    eik = ((torch.linalg.norm(out['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+    (torch.nn.functional.l1_loss(out['comp_rgb_full'], torch.full_like(out['comp_rgb_full'], 0.5)) + 0.1 * eik).backward()
+    params = dict(model.named_parameters())
+    g_ref = {k: p.grad.clone() for k, p in params.items() if p.grad is not None}
+    for p in model.parameters():
+        p.grad = None
+    P = om.NeusParams(cfg['geometry']['xyz_encoding_config'], params['geometry.encoding.encoding.params'], model.geometry.network, None,
+                      params['variance.variance'])
+    P.color_mlp = model.texture.network
+    ewn = model.geometry_bg.encoding_with_network
+    Pbg = om.NeusBgParams(cfg['geometry_bg']['xyz_encoding_config'], ewn.encoding.encoding.params, ewn.network, model.texture_bg.network)
+    o = om.neus_dtu_render(P, Pbg, rays_c4, shell, bgb, r, np.float32(model.render_step_size), model.render_step_size_bg,
+                           model.cone_angle_bg, model.near_plane_bg, model.far_plane_bg, bg, model.cos_anneal_ratio, emulate_fp16=False)
+    eik = ((torch.linalg.norm(o['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+    (torch.nn.functional.l1_loss(o['comp_rgb_full'], torch.full_like(o['comp_rgb_full'], 0.5)) + 0.1 * eik).backward()
+    keys = ['comp_rgb', 'opacity', 'sdf_samples', 'sdf_grad_samples', 'weights', 'ray_indices', 'comp_rgb_bg', 'opacity_bg', 'depth_bg',
+            'weights_bg', 'points_bg', 'intervals_bg', 'ray_indices_bg', 'comp_rgb_full']
+    res['neus_dtu'] = {'keys': sorted(out), 'oracle_keys_missing': sorted(set(out) - set(o)),
+                       'num_samples': int(out['num_samples']), 'num_samples_bg': int(out['num_samples_bg']),
+                       'num_samples_bg_oracle': int(o['num_samples_bg']), 'num_marched_bg': int(o['num_marched_bg']) if 'num_marched_bg' in o else -1,
+                       'num_samples_full_equal': int(out['num_samples_full']) == int(o['num_samples_full']),
+                       'rays_valid_full_equal': bool(torch.equal(out['rays_valid_full'], o['rays_valid_full'])),
+                       'diff': {k: diff(out[k], o[k]) for k in keys},
+                       'grad_diff': {k: diff(gr, params[k].grad) / (float(params[k].grad.abs().max()) + 1e-30) for k, gr in g_ref.items()},
+                       'n_grads': len(g_ref)}
     print('RESULT ' + json.dumps(res))
 
 

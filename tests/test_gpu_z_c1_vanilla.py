@@ -112,3 +112,69 @@ def test_neuralangelo_config_finite_difference_normals_and_laplacian():
     for name, p in model.named_parameters():
         if p.requires_grad and p.numel() > 0:
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+@pytest.mark.parametrize('fused_mlps', [False, True])
+def test_c4_neus_dtu_matches_oracle(fused_mlps):
+    """Config C4 (neus-dtu.yaml: NeuS foreground + learned NeRF++ background, VanillaMLP colour / background networks) through the drop-in
+    model against oracle.models.neus_dtu_render, whose orchestration is pinned to the reference's own forward_ (tests/test_reference_dropin.py).
+    Tolerances as for C3 (tests/test_gpu_neus.py): sample sets exact, sdf 2e-3, per-ray colour 6e-3, gradients cosine >= 0.99 (0.98 with the
+    fp16-operand VanillaMLP kernels)."""
+    from test_gpu_neus import build
+    from nsr_b200 import configs
+    from oracle import mlp as omlp
+
+    def cfg_fn():
+        cfg = configs.neus_dtu()
+        for key in ('texture', 'geometry_bg', 'texture_bg'):
+            cfg[key]['mlp_network_config']['fused'] = fused_mlps
+        cfg['texture']['fused_vanilla'] = cfg['texture_bg']['fused_vanilla'] = fused_mlps
+        return cfg
+
+    model, cfg, binary, rays, jitter = build(cfg_fn, 256, 2)
+    model.randomized = False                                                   # lattice / cone marching without jitter on both sides
+    bgb = np.random.default_rng(0).random((256, 256, 256)) < 0.3
+    model.occupancy_grid.set_binary(torch.from_numpy(binary))
+    model.occupancy_grid_bg.set_binary(torch.from_numpy(bgb))
+    with torch.no_grad():
+        model.geometry_bg.encoding_with_network.network.layers[-1].bias[0] = 2.5   # background densities ~ exp(1.5)
+    r = cfg['radius']
+    out = model.forward_(torch.from_numpy(rays).to(D))
+    eik = ((torch.linalg.norm(out['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+    (torch.nn.functional.l1_loss(out['comp_rgb_full'], torch.full_like(out['comp_rgb_full'], 0.5)) + 0.1 * eik).backward()
+
+    def cpu_mlp(module, n_in, n_out, mcfg):
+        m = omlp.VanillaMLP(n_in, n_out, dict(mcfg))
+        m.load_state_dict({k: v.detach().cpu() for k, v in module.state_dict().items()})
+        return m
+
+    geo = model.geometry
+    sdf_mlp = cpu_mlp(geo.network, 35, 13, cfg['geometry']['mlp_network_config'])
+    tex_mlp = cpu_mlp(model.texture.network, 32, 3, cfg['texture']['mlp_network_config'])
+    ewn = model.geometry_bg.encoding_with_network
+    bg_mlp = cpu_mlp(ewn.network, 32, 8, cfg['geometry_bg']['mlp_network_config'])
+    bgtex_mlp = cpu_mlp(model.texture_bg.network, 24, 3, cfg['texture_bg']['mlp_network_config'])
+    table = geo.encoding.encoding.params.detach().cpu().clone().requires_grad_(True)
+    table_bg = ewn.encoding.encoding.params.detach().cpu().clone().requires_grad_(True)
+    var = model.variance.variance.detach().cpu().clone().requires_grad_(True)
+    P = omodels.NeusParams(cfg['geometry']['xyz_encoding_config'], table, sdf_mlp, None, var)
+    P.color_mlp = tex_mlp
+    Pbg = omodels.NeusBgParams(cfg['geometry_bg']['xyz_encoding_config'], table_bg, bg_mlp, bgtex_mlp)
+    bgc = model.background_color.detach().cpu()
+    ref = omodels.neus_dtu_render(P, Pbg, rays, binary, bgb, r, np.float32(model.render_step_size), model.render_step_size_bg,
+                                  model.cone_angle_bg, model.near_plane_bg, model.far_plane_bg, bgc, model.cos_anneal_ratio)
+    eik = ((torch.linalg.norm(ref['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
+    (torch.nn.functional.l1_loss(ref['comp_rgb_full'], torch.full_like(ref['comp_rgb_full'], 0.5)) + 0.1 * eik).backward()
+
+    assert int(out['num_samples']) == len(ref['ray_indices']) > 3000 and torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
+    assert abs(int(out['num_samples_bg']) - int(ref['num_samples_bg'])) <= 3 and int(ref['num_samples_bg']) > 100
+    assert float((out['sdf_samples'].detach().cpu() - ref['sdf_samples'].detach()).abs().max()) <= 2e-3
+    for k in ('comp_rgb', 'comp_rgb_bg', 'comp_rgb_full', 'opacity', 'opacity_bg'):
+        assert float((out[k].detach().cpu() - ref[k].detach()).abs().max()) <= 6e-3, k
+    ctol = 0.98 if fused_mlps else 0.99
+    assert cos(geo.encoding.encoding.params.grad, table.grad) >= 0.99 and cos(ewn.encoding.encoding.params.grad, table_bg.grad) >= ctol
+    for mine, theirs in ((geo.network, sdf_mlp), (model.texture.network, tex_mlp), (ewn.network, bg_mlp), (model.texture_bg.network, bgtex_mlp)):
+        rg = dict(theirs.named_parameters())
+        for name, p in mine.named_parameters():
+            assert cos(p.grad, rg[name].grad) >= ctol, name
+    assert abs(float(model.variance.variance.grad) - float(var.grad)) <= 3e-2 * abs(float(var.grad)) + 1e-6

@@ -36,7 +36,7 @@ def test_reference_models_build_on_our_modules():
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='/root/reference is not mounted here')
 def test_oracle_orchestration_is_pinned_to_the_reference_forward():
-    """oracle/models.py (nerf_render, neus_render) restates models/nerf.py:61-127 and models/neus.py:205-287.  Here the reference's
+    """oracle/models.py (nerf_render, neus_render, neus_bg_render, neus_dtu_render) restates models/nerf.py:61-127 and models/neus.py:141-287.  Here the reference's
     OWN forward_ runs on the CPU -- tinycudann / nerfacc replaced by per-op stand-ins built from the oracle's primitives
     (tests/helpers/cpu_thirdparty.py), fp32 throughout -- and every output and parameter gradient (incl. the double backward of the
     eikonal term through the reference's VolumeSDF) must equal the oracle's: the glue is pinned, the third-party arithmetic stays ours
@@ -54,3 +54,9 @@ def test_oracle_orchestration_is_pinned_to_the_reference_forward():
                                  'comp_rgb_full', 'num_samples_full', 'rays_valid_full'}
     assert neus['num_samples'] == neus['num_samples_oracle'] > 5000 and neus['cos_anneal_ratio'] == 0.25
     assert max(neus['diff'].values()) < 5e-6 and neus['inv_s_diff'] == 0.0 and max(neus['grad_diff'].values()) < 1e-5
+    # config C4 (neus-dtu.yaml): learned background = forward_bg_ (models/neus.py:141-203) + the *_bg / *_full composition (:268-281)
+    dtu = res['neus_dtu']
+    assert not dtu['oracle_keys_missing'] and dtu['num_samples'] > 5000
+    assert dtu['num_samples_bg'] == dtu['num_samples_bg_oracle'] > 300 and dtu['num_samples_full_equal'] and dtu['rays_valid_full_equal']
+    assert max(dtu['diff'].values()) < 5e-6
+    assert dtu['n_grads'] == 25 and max(dtu['grad_diff'].values()) < 2e-4     # every trainable tensor of all five submodules
