@@ -60,3 +60,22 @@ def test_oracle_orchestration_is_pinned_to_the_reference_forward():
     assert dtu['num_samples_bg'] == dtu['num_samples_bg_oracle'] > 300 and dtu['num_samples_full_equal'] and dtu['rays_valid_full_equal']
     assert max(dtu['diff'].values()) < 5e-6
     assert dtu['n_grads'] == 25 and max(dtu['grad_diff'].values()) < 2e-4     # every trainable tensor of all five submodules
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/systems'), reason='/root/reference is not mounted here')
+def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step():
+    """The reference's OWN systems/nerf.py / systems/neus.py ``preprocess_data`` and ``training_step`` run on the CPU (tiny in-memory
+    dataset, fake model; tests/helpers/reference_system.py): the batch they assemble equals oracle.rays.training_batch / image_batch (the
+    checker of nsr_gather_rays), their losses and gradients equal oracle.losses (the restatement the fused loss kernels are tested
+    against), and their dynamic ray count equals the rule RayBudget applies."""
+    from nsr_b200.rays import RayBudget
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'reference_system.py')], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
+    nerf, neus = res['nerf'], res['neus']
+    assert nerf['rays'] < 3e-7 and nerf['image_rays'] < 3e-7 and nerf['rgb'] == 0.0 and nerf['fg_mask'] == 0.0 and nerf['bg_equal']
+    assert abs(nerf['loss'] - nerf['loss_oracle']) < 1e-7 and nerf['grad'] < 1e-8
+    assert nerf['train_num_rays'] == nerf['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 9000, 1024)
+    assert abs(neus['loss'] - neus['loss_oracle']) < 1e-6 and max(neus['grad'].values()) < 1e-7
+    assert neus['train_num_rays'] == neus['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 5000, 1024)
