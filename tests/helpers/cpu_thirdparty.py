@@ -86,7 +86,8 @@ class OccupancyGrid(nn.Module):
         return self._binary
 
     def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):
-        pass   # the grid is set by the test
+        # the grid itself is set by the test; keep what the reference handed over so its occupancy functions can be checked
+        self.last_call = dict(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre)
 
 
 @torch.no_grad()

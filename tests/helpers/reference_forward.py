@@ -98,6 +98,15 @@ def main():
                    'grad_diff': [diff(g_ref[0], dflat.grad) / (float(dflat.grad.abs().max()) + 1e-30),
                                  diff(g_ref[1], cflat.grad) / (float(cflat.grad.abs().max()) + 1e-30)]}
 
+    from oracle import neus as oneus
+    pts = (torch.rand(300, 3, generator=torch.Generator().manual_seed(9)) * 2 - 1) * 1.2
+    model.update_step(0, 16)                                    # models/nerf.py:45-55: occ = density * render_step_size
+    call = model.occupancy_grid.last_call
+    with torch.no_grad():
+        dens, _ = om.nerf_field(P, pts, None, 1.5, emulate_fp16=False, density_only=True)
+        res['nerf']['occ_fn'] = diff(call['occ_eval_fn'](pts), dens[:, None] * model.render_step_size)
+    res['nerf']['occ_thre'] = call['occ_thre']
+
     # ---- NeuS (neus-blender.yaml)
     cfg = configs.neus_blender()
     cfg['randomized'] = False
@@ -132,6 +141,13 @@ def main():
                                                             'weights', 'points', 'intervals', 'ray_indices', 'comp_rgb_full')},
                    'inv_s_diff': diff(model.variance.inv_s, o['inv_s']),
                    'grad_diff': {k: diff(g_ref[k], params[k].grad) / (float(params[k].grad.abs().max()) + 1e-30) for k in names}}
+    call = model.occupancy_grid.last_call                       # models/neus.py:90-111 handed over by update_step(0, 5000) above
+    with torch.no_grad():
+        sdf = model.geometry(pts * 0.6, with_grad=False, with_feature=False)
+        res['neus']['occ_fn'] = diff(call['occ_eval_fn'](pts * 0.6), oneus.occ_alpha(sdf, oneus.inv_s_from_variance(params[names[2]]),
+                                                                                     model.render_step_size))
+    res['neus']['occ_thre'] = call['occ_thre']
+
     # ---- NeuS with learned background (neus-dtu.yaml: config C4)
     cfg = configs.neus_dtu()
     cfg['randomized'] = False
@@ -180,6 +196,11 @@ def main():
                        'diff': {k: diff(out[k], o[k]) for k in keys},
                        'grad_diff': {k: diff(gr, params[k].grad) / (float(params[k].grad.abs().max()) + 1e-30) for k, gr in g_ref.items()},
                        'n_grads': len(g_ref)}
+    call_bg = model.occupancy_grid_bg.last_call                 # models/neus.py:103-111: density * render_step_size_bg, its own threshold key
+    with torch.no_grad():
+        dens, _ = om.neus_bg_field(Pbg, pts * 3.0, None, r, emulate_fp16=False, density_only=True)
+        res['neus_dtu']['occ_fn_bg'] = diff(call_bg['occ_eval_fn'](pts * 3.0), dens[:, None] * model.render_step_size_bg)
+    res['neus_dtu']['occ_thre'] = [model.occupancy_grid.last_call['occ_thre'], call_bg['occ_thre']]
     print('RESULT ' + json.dumps(res))
 
 

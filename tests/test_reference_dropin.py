@@ -60,6 +60,10 @@ def test_oracle_orchestration_is_pinned_to_the_reference_forward():
     assert dtu['num_samples_bg'] == dtu['num_samples_bg_oracle'] > 300 and dtu['num_samples_full_equal'] and dtu['rays_valid_full_equal']
     assert max(dtu['diff'].values()) < 5e-6
     assert dtu['n_grads'] == 25 and max(dtu['grad_diff'].values()) < 2e-4     # every trainable tensor of all five submodules
+    # the occupancy functions update_step hands to OccupancyGrid.every_n_step (models/nerf.py:45-55, models/neus.py:90-111) and their thresholds
+    assert nerf['occ_fn'] < 1e-7 and nerf['occ_thre'] == 0.01
+    assert neus['occ_fn'] < 1e-6 and neus['occ_thre'] == 0.001                # grid_prune_occ_thre of neus-blender.yaml
+    assert dtu['occ_fn_bg'] < 1e-6 and dtu['occ_thre'] == [0.001, 0.01]       # the background grid keeps the default threshold
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/systems'), reason='/root/reference is not mounted here')
