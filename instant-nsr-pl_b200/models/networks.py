@@ -149,11 +149,13 @@ class VanillaMLP(nn.Module):
             elif is_last:
                 lin.bias.fill_(-self.sphere_init_radius)
                 lin.weight.normal_(mean=math.sqrt(math.pi) / math.sqrt(dim_in), std=0.0001)
+            elif is_first:   # only the xyz columns are drawn (same random draws as the reference for a given seed)
+                lin.bias.zero_()
+                lin.weight[:, 3:].zero_()
+                lin.weight[:, :3].normal_(0.0, math.sqrt(2) / math.sqrt(dim_out))
             else:
                 lin.bias.zero_()
                 lin.weight.normal_(0.0, math.sqrt(2) / math.sqrt(dim_out))
-                if is_first:
-                    lin.weight[:, 3:].zero_()
         return nn.utils.weight_norm(lin) if self.weight_norm else lin
 
     def make_activation(self):

@@ -83,3 +83,24 @@ def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step()
     assert nerf['train_num_rays'] == nerf['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 9000, 1024)
     assert abs(neus['loss'] - neus['loss_oracle']) < 1e-6 and max(neus['grad'].values()) < 1e-7
     assert neus['train_num_rays'] == neus['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 5000, 1024)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='/root/reference is not mounted here')
+def test_product_torch_side_equals_the_reference_functions():
+    """every pure-torch piece of the drop-in models compared DIRECTLY with the reference's own (tests/helpers/reference_torch_parts.py):
+    activations (value + gradient), scale_anything, contraction, chunk_batch, VanillaFrequency mask schedule, VanillaMLP / tcnn sphere
+    initialisation (same seed => the same parameters, draw for draw), VarianceNetwork modulation, NeuSModel.get_alpha with cos annealing,
+    the render constants (step sizes, cone angle, planes, boxes).  The bar is bit equality."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'reference_torch_parts.py')], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
+
+    def worst(v):
+        if isinstance(v, dict):
+            return max(worst(x) for x in v.values())
+        return float(v) if not isinstance(v, bool) else (0.0 if v else 1.0)
+
+    assert len(res['activations']) == 15 and len(res['chunk_batch']) == 8 and len(res['vanilla_mlp']) == 4
+    for name, section in res.items():
+        assert worst(section) == 0.0, (name, section)
