@@ -153,6 +153,23 @@ def main():
                    'grad': {n: float((g_ref[n] - out[n].grad).abs().max()) for n in names},
                    'train_num_rays': s.train_num_rays,
                    'train_num_rays_oracle': olosses.next_train_num_rays(n_rays, n_rays * 64, 5000, 1024)}
+    # ---- parse_optimizer (systems/utils.py:314-325) on the same model and config section: param groups of the reference vs ours
+    from systems.utils import parse_optimizer as ref_parse_optimizer
+    from nsr_b200 import models as our_models, configs
+    from nsr_b200.optim import parse_optimizer
+    m = our_models.make('neus', configs.neus_dtu())
+    ocfg = dict(name='AdamW', args=dict(lr=0.01, betas=[0.9, 0.99], eps=1.e-15),
+                params=dict(geometry=dict(lr=0.01), texture=dict(lr=0.01), geometry_bg=dict(lr=0.01), texture_bg=dict(lr=0.01), variance=dict(lr=0.001)))
+    ro, oo = ref_parse_optimizer(Config(ocfg), m), parse_optimizer(Config(ocfg), m)
+    keys = ('lr', 'betas', 'eps', 'weight_decay')
+    res['optimizer'] = {
+        'ref_class': type(ro).__name__, 'our_class': type(oo).__name__,
+        'names_equal': [g_['name'] for g_ in ro.param_groups] == [g_['name'] for g_ in oo.param_groups],
+        'hyper_equal': all(tuple(a[k]) == tuple(b[k]) if isinstance(a[k], (list, tuple)) else a[k] == b[k]
+                           for a, b in zip(ro.param_groups, oo.param_groups) for k in keys),
+        'same_tensors': all(len(a['params']) == len(b['params']) and all(x is y for x, y in zip(a['params'], b['params']))
+                            for a, b in zip(ro.param_groups, oo.param_groups)),
+        'n_groups': len(oo.param_groups)}
     print('RESULT ' + json.dumps(res))
 
 

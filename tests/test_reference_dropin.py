@@ -83,6 +83,10 @@ def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step()
     assert nerf['train_num_rays'] == nerf['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 9000, 1024)
     assert abs(neus['loss'] - neus['loss_oracle']) < 1e-6 and max(neus['grad'].values()) < 1e-7
     assert neus['train_num_rays'] == neus['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 5000, 1024)
+    # optim.parse_optimizer builds the reference's param groups (same tensors, names, hyper-parameters) around FusedAdamW
+    opt = res['optimizer']
+    assert opt['ref_class'] == 'AdamW' and opt['our_class'] == 'FusedAdamW' and opt['n_groups'] == 5
+    assert opt['names_equal'] and opt['hyper_equal'] and opt['same_tensors']
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='/root/reference is not mounted here')
