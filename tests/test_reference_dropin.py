@@ -108,3 +108,23 @@ def test_product_torch_side_equals_the_reference_functions():
     assert len(res['activations']) == 15 and len(res['chunk_batch']) == 8 and len(res['vanilla_mlp']) == 4
     for name, section in res.items():
         assert worst(section) == 0.0, (name, section)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='/root/reference is not mounted here')
+def test_product_volume_sdf_torch_paths_equal_the_reference():
+    """VolumeSDF paths of the product that are torch code rather than kernels -- finite-difference normals + laplacian under the
+    ProgressiveBandHashGrid schedule (configs/neuralangelo-dtu-wmask.yaml), fixed-eps finite differences, the autograd fallback of the
+    analytic normal -- run on the CPU with the hash grid swapped for the oracle-backed stand-in, against the reference's VolumeSDF with the
+    same weights (tests/helpers/reference_sdf_paths.py): values, level function, train / eval detaching, parameter gradients through an
+    eikonal-style loss."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'reference_sdf_paths.py')], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
+    assert set(res) == {'finite_difference_progressive', 'analytic_fallback', 'finite_difference_fixed_eps'}
+    assert len(res['finite_difference_progressive']) == 6
+    for section, cases in res.items():
+        for case, d in cases.items():
+            for name, v in d.items():
+                tol = 1e-5 if name == 'param_grad' else (2e-6 if name == 'grad' else 0.0)
+                assert v <= tol, (section, case, name, v)
