@@ -78,7 +78,9 @@ class OccupancyGrid(nn.Module):
     def __init__(self, roi_aabb, resolution=128, contraction_type=ContractionType.AABB):
         super().__init__()
         self.register_buffer('_roi_aabb', torch.as_tensor(roi_aabb, dtype=torch.float32))
-        self.resolution, self.contraction_type = resolution, contraction_type
+        self.contraction_type = contraction_type
+        self.register_buffer('resolution', torch.tensor([resolution] * 3, dtype=torch.int32))     # nerfacc 0.3.3's checkpointed state
+        self.register_buffer('occs', torch.zeros(resolution ** 3))
         self.register_buffer('_binary', torch.zeros([resolution] * 3, dtype=torch.bool))
 
     @property
@@ -92,17 +94,17 @@ class OccupancyGrid(nn.Module):
 
 @torch.no_grad()
 def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=None, sigma_fn=None, alpha_fn=None, early_stop_eps=1e-4,
-                 alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3, stratified=False, cone_angle=0.0):
+                 alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3, stratified=False, cone_angle=0.0, jitter=None):
     """nerfacc 0.3.3 ray_marching semantics from the oracle's marchers: the step lattice for AABB grids with
     cone_angle 0, blind cone stepping through the grid's own (contracted) region otherwise; then the sigma_fn visibility filter"""
-    assert not stratified and alpha_fn is None and grid is not None
+    assert not stratified and jitter is None and alpha_fn is None and grid is not None
     o, d = rays_o.numpy().astype(np.float32), rays_d.numpy().astype(np.float32)
     step = np.float32(render_step_size)
     near = near_plane.numpy().astype(np.float32) if torch.is_tensor(near_plane) else near_plane
     box = None if scene_aabb is None else scene_aabb.numpy().astype(np.float32)
     t0, t1 = march.ray_interval(o, d, box, near, far_plane, step, None)
     roi = grid._roi_aabb.numpy().astype(np.float32)
-    if grid.contraction_type == ContractionType.AABB and cone_angle == 0.0:
+    if grid.contraction_type.value == ContractionType.AABB.value and cone_angle == 0.0:   # (by value: the product has its own enum class)
         ri, ts, te, _ = march.march_lattice(o, d, roi, grid.binary.numpy(), step, t0, t1)
     else:
         ri, ts, te, _ = march.march_sequential(o, d, roi, grid.binary.numpy(), step, cone_angle, t0, t1, grid.contraction_type.value)
