@@ -151,7 +151,7 @@ def train(args):
         sched.step()
         n_rays_total += n
         if step % 250 == 0 or step == args.steps - 1:
-            last_loss = float(loss)
+            last_loss = float(loss.detach())
             print(f'step {step:5d}  loss {last_loss:.5f}  rays/step {n}', file=sys.stderr)
     torch.cuda.synchronize()
     secs = time.time() - t_start
