@@ -132,9 +132,7 @@ class RayBudget:
             self._pending.append((host, ev))
         else:
             self._pending.append((total.clone(), None))
-        if self.sync:
-            return self.update(wait=True)
-        return self.train_num_rays
+        return self.update(wait=self.sync)   # folds in whatever has arrived (everything when sync): the value for the NEXT step
 
     def update(self, wait=False):
         """fold in the finished observations (all of them when ``wait``); returns the current train_num_rays"""

@@ -401,4 +401,5 @@ def test_train_synthetic_tool_logic_runs_on_cpu_standins():
     lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith('{"tool"')]
     assert [ln['model'] for ln in lines] == ['nerf', 'neus']
     for ln in lines:
-        assert ln['steps'] == 3 and ln['psnr_after'] > ln['psnr_before'] and ln['final_rays_per_step'] <= 64 and ln['steps_per_s'] > 0
+        assert ln['steps'] == 3 and ln['psnr_after'] > ln['psnr_before'] and ln['steps_per_s'] > 0
+        assert ln['final_rays_per_step'] <= 64 and ln['final_rays_per_step'] != 48     # the ray budget reacted to the sample counts
