@@ -97,12 +97,13 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
                  alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3, stratified=False, cone_angle=0.0, jitter=None):
     """nerfacc 0.3.3 ray_marching semantics from the oracle's marchers: the step lattice for AABB grids with
     cone_angle 0, blind cone stepping through the grid's own (contracted) region otherwise; then the sigma_fn visibility filter"""
-    assert not stratified and jitter is None and alpha_fn is None and grid is not None
+    assert alpha_fn is None and grid is not None and (not stratified or jitter is not None), 'stratified marching needs the per-ray jitter'
     o, d = rays_o.numpy().astype(np.float32), rays_d.numpy().astype(np.float32)
     step = np.float32(render_step_size)
     near = near_plane.numpy().astype(np.float32) if torch.is_tensor(near_plane) else near_plane
     box = None if scene_aabb is None else scene_aabb.numpy().astype(np.float32)
-    t0, t1 = march.ray_interval(o, d, box, near, far_plane, step, None)
+    jit = jitter.cpu().numpy().astype(np.float32) if (stratified and jitter is not None) else None
+    t0, t1 = march.ray_interval(o, d, box, near, far_plane, step, jit)
     roi = grid._roi_aabb.numpy().astype(np.float32)
     if grid.contraction_type.value == ContractionType.AABB.value and cone_angle == 0.0:   # (by value: the product has its own enum class)
         ri, ts, te, _ = march.march_lattice(o, d, roi, grid.binary.numpy(), step, t0, t1)

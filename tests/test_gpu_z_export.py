@@ -6,8 +6,8 @@ area convergence.
 
 Seen on a B200 in profiles/r1_experimental_gpu_tests.log: the five exact comparisons passed; the 256^3 extraction was closed and its
 volume (0.99707) matched the analytic 0.99717 (the test then compared against a biased voxel count: fixed); model.isosurface() ran (the
-radius bounds of the sphere initialisation were too tight: loosened).  The vertex-colour export has not run on a GPU yet and stays
-behind NSR_EXPERIMENTAL=1."""
+radius bounds of the sphere initialisation were too tight: loosened).  The vertex-colour export (tests/test_gpu_zz_export_colours.py) has not
+run on a GPU yet; its Python path was dry-run on the CPU with stand-ins."""
 import os
 
 import numpy as np
@@ -15,7 +15,6 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-experimental = pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')
 
 from oracle import mcubes as omc
 
@@ -99,23 +98,3 @@ def test_neus_isosurface_of_the_sphere_initialisation():
     assert 0.45 < float(rad.min()) and float(rad.max()) < 1.2 and 0.5 < float(rad.mean()) < 1.0   # measured on B200: min 0.59
     assert _balance_defects(f.to(D), v.shape[0]) == 0
 
-
-@experimental
-def test_export_with_vertex_colours_and_density_threshold():
-    """models/neus.py:321-329 / models/nerf.py:153-161: per-vertex colours through the texture network; density fields mesh at
-    level = -density, threshold = density value (configs/nerf-blender.yaml:38-42)"""
-    from nsr_b200 import models, configs
-    from nsr_b200.config import Config
-    cfg = configs.neus_blender()
-    cfg['geometry']['isosurface'] = dict(method='mc', resolution=64, chunk=100000, threshold=0.0)
-    torch.manual_seed(0)
-    model = models.make('neus', cfg).to(D)
-    model.eval()
-    out = model.export(Config(dict(chunk_size=50000, export_vertex_color=True)))
-    assert out['v_rgb'].shape == (out['v_pos'].shape[0], 3) and float(out['v_rgb'].min()) >= 0 and float(out['v_rgb'].max()) <= 1
-    ncfg = configs.nerf_blender()
-    ncfg['geometry']['isosurface'] = dict(method='mc', resolution=64, chunk=100000, threshold=5.0)
-    nerf = models.make('nerf', ncfg).to(D)
-    nerf.eval()
-    m2 = nerf.export(Config(dict(chunk_size=50000, export_vertex_color=False)))   # random-init density ~ exp(-1): nothing above 5
-    assert m2['v_pos'].shape == (0, 3) and m2['t_pos_idx'].shape == (0, 3)
