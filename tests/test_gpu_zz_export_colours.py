@@ -1,11 +1,14 @@
 """Vertex-colour export (models/neus.py:321-329, models/nerf.py:153-161) through the drop-in models on the GPU: isosurface by the GPU
 marching cubes, per-vertex features through the fused SDF field / colour kernels.  Every kernel on this path has its own parity test; the
 Python path (chunk_batch keyword arguments, eval-mode detaching, the texture call with the normal as view direction) was dry-run on the
-CPU with the oracle-backed stand-ins.  Sorted last on purpose: it is the one un-gated test that has not been seen on a B200 yet."""
+CPU with the oracle-backed stand-ins (tests/test_dryrun.py).  Not yet seen on a B200: NSR_EXPERIMENTAL=1 (tools/run_experimental.sh) runs it."""
+import os
+
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')]
 
 D = torch.device('cuda:0')
 

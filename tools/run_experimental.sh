@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/run_experimental.sh'
 mkdir -p gpurun_out
 export NSR_EXPERIMENTAL=1
-python -u -m pytest tests/test_gpu_z_frontend.py tests/test_gpu_z_vanilla.py tests/test_gpu_z_export.py tests/test_gpu_zy_configs.py tests/test_gpu_z_training.py -q -rA --timeout 120 \
+python -u -m pytest tests/test_gpu_z_frontend.py tests/test_gpu_z_vanilla.py tests/test_gpu_z_export.py tests/test_gpu_zy_configs.py tests/test_gpu_z_training.py tests/test_gpu_zz_export_colours.py -q -rA --timeout 120 \
   -p no:cacheprovider > gpurun_out/exp_tests.log 2>&1
 echo "pytest exit $?" >> gpurun_out/exp_tests.log
 tail -40 gpurun_out/exp_tests.log
