@@ -97,7 +97,9 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
                  alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3, stratified=False, cone_angle=0.0, jitter=None):
     """nerfacc 0.3.3 ray_marching semantics from the oracle's marchers: the step lattice for AABB grids with
     cone_angle 0, blind cone stepping through the grid's own (contracted) region otherwise; then the sigma_fn visibility filter"""
-    assert alpha_fn is None and grid is not None and (not stratified or jitter is not None), 'stratified marching needs the per-ray jitter'
+    assert alpha_fn is None and grid is not None
+    if stratified and jitter is None:   # nerfacc draws one U[0,1) offset per ray
+        jitter = torch.rand(rays_o.shape[0])
     o, d = rays_o.numpy().astype(np.float32), rays_d.numpy().astype(np.float32)
     step = np.float32(render_step_size)
     near = near_plane.numpy().astype(np.float32) if torch.is_tensor(near_plane) else near_plane

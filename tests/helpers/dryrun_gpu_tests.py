@@ -47,6 +47,7 @@ def run(name, fn, *a):
         getattr(fn, '__wrapped__', fn)(*a); print(name, 'PASSED', round(time.time()-t0,1))
     except Exception as e:
         tb = traceback.format_exc().splitlines(); print(name, 'FAILED', type(e).__name__, str(e)[:300]); print('   ', '\n    '.join(tb[-6:]))
+run('c3_parity', neus_t.test_neus_blender_forward_backward_parity)          # established C3 test: guards the models' Python side
 run('c1[False]', c1.test_c1_vanilla_nerf_matches_oracle, False)
 run('c4[False]', c1.test_c4_neus_dtu_matches_oracle, False)
 run('neuralangelo', c1.test_neuralangelo_config_finite_difference_normals_and_laplacian)
