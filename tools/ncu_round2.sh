@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"nerf_bwd_kernel|nerf_rays_fwd_kernel|march_rays_mask_kernel|scan_counts_kernel|pack_kept_kernel|ray_bwd_loose_kernel" \
     -s 12 -c 8 -o gpurun_out/r2_c2 -f python tools/ncu_target.py 5 > gpurun_out/r2_c2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"neus_field_fwd_kernel|neus_field_bwd_kernel|radiance_bwd_kernel" \
-    -s 4 -c 6 -o gpurun_out/r2_c3 -f python tools/neus_profile.py > gpurun_out/r2_c3.log 2>&1
+    -s 4 -c 6 -o gpurun_out/r2_c3 -f python tools/neus_times.py > gpurun_out/r2_c3.log 2>&1
 NSR_EXPERIMENTAL=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r2_c4_launches_fused_mlps.csv \
     python tools/neus_times.py > gpurun_out/r2_c4_launches_fused_mlps.log 2>&1
 ls -la gpurun_out | tail -12
