@@ -11,6 +11,7 @@
 // expand kernels.  Per-ray outputs are plain stores (no atomics: bit-reproducible); kept samples of ray r land at
 // offsets_m[r] + j (j < kept[r]) in the per-sample buffers ("loose" layout: a kept prefix per ray).
 // The kept set is identical to the two-pass path: same density code, same 32-sample chunking of the scan.
+#include <stdlib.h>
 #include "nerf_fused.cuh"
 
 namespace {
@@ -60,7 +61,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) nerf_rays_fwd_kernel(const __grid_constant__ nsr_nerf_t P, const RaysFwdArgs a) {
+// MINB = resident CTAs per SM the register allocation is sized for: 2 (default: 128 registers, no spills) or 3 (80 registers, ~0.5 KB of
+// spills per thread, 24 instead of 16 warps per SM to hide the gather latency; opt-in through NSR_FWD_CTAS=3 until it has been timed)
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __grid_constant__ nsr_nerf_t P, const RaysFwdArgs a) {
   extern __shared__ __align__(16) __half smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   __half* At = smem + NF_W_TOTAL + warp * kWarpHalves;
@@ -389,9 +393,14 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
   NSR_REQUIRE(words >= 1 && words <= kMaxWords, "nsr_nerf_rays_fwd: words must be in [1,%d]", kMaxWords);
   NSR_REQUIRE(ticket != nullptr && kept != nullptr, "nsr_nerf_rays_fwd: ticket / kept are required");
   if (n_rays == 0) return 0;
+  static const int ctas_per_sm = [] {
+    const char* v = getenv("NSR_FWD_CTAS");
+    return (v != nullptr && v[0] == '3') ? 3 : 2;
+  }();
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nerf_rays_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = ctas_per_sm == 3 ? cudaFuncSetAttribute(nerf_rays_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)
+                                     : cudaFuncSetAttribute(nerf_rays_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
       nsr_set_error("nsr_nerf_rays_fwd: cannot reserve %zu B shared memory: %s", kSmemBytes, cudaGetErrorString(e));
       return 2;
@@ -405,8 +414,11 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
   a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.ticket = ticket;
   a.step = step; a.early_stop_eps = early_stop_eps; a.words = words; a.n_rays = n_rays;
   const int64_t want = (n_rays + kWarps - 1) / kWarps;
-  int grid = (int)min((int64_t)nsr_sm_count() * 2, want > 0 ? want : (int64_t)1);
-  nerf_rays_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
+  int grid = (int)min((int64_t)nsr_sm_count() * ctas_per_sm, want > 0 ? want : (int64_t)1);
+  if (ctas_per_sm == 3)
+    nerf_rays_fwd_kernel<3><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
+  else
+    nerf_rays_fwd_kernel<2><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
   NSR_CHECK_LAUNCH("nsr_nerf_rays_fwd");
   return 0;
 }

@@ -33,3 +33,8 @@ NSR_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcod
   "tests/test_gpu_z_vanilla.py::test_vanilla_radiance_matches_oracle_forward_and_backward" -q -x -p no:cacheprovider > gpurun_out/memcheck_new_kernels.log 2>&1
 echo "memcheck exit $?" >> gpurun_out/memcheck_new_kernels.log
 tail -15 gpurun_out/memcheck_new_kernels.log
+# forward kernel sized for three CTAs per SM (80 registers, some spills, 24 warps/SM): parity of the NeRF model tests, then the bench A/B
+NSR_FWD_CTAS=3 timeout 600 python -m pytest tests/test_gpu_nerf.py -q -x -p no:cacheprovider > gpurun_out/fwd_ctas3_tests.log 2>&1; echo "exit $?" >> gpurun_out/fwd_ctas3_tests.log
+NSR_FWD_CTAS=3 NSR_EXPERIMENTAL=0 timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_fwd_ctas3.json 2> gpurun_out/bench_fwd_ctas3.err
+tail -3 gpurun_out/fwd_ctas3_tests.log; python -c "
+import json; d=json.loads(open('gpurun_out/bench_fwd_ctas3.json').read().strip().splitlines()[-1]); print('fwd_ctas3', d['ms_per_step'], d['value'], d.get('kernels_ms'))"
