@@ -8,6 +8,7 @@
 //     barrier  -> all chunks have landed everywhere
 // Chunks are disjoint, so the in-place update is race free.  Barriers are monotonically increasing epochs in a peer-mapped flag
 // array (st.release.sys / ld.acquire.sys), with a bounded spin so that a lost peer sets an error flag instead of hanging the GPU.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -125,7 +126,12 @@ extern "C" int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* mult
   if (n == 0 || world == 1) return 0;
   const int64_t n4 = n / 4, chunk = (n4 + world - 1) / world;
   constexpr int kU = 4;
-  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * 4, (chunk + 256 * kU - 1) / (256 * kU)));
+  static const int ctas_per_sm = [] {   // tuning knob (default 4): NSR_P2P_CTAS_PER_SM=1..16
+    const char* v = getenv("NSR_P2P_CTAS_PER_SM");
+    const int n = v ? atoi(v) : 4;
+    return n >= 1 && n <= 16 ? n : 4;
+  }();
+  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * ctas_per_sm, (chunk + 256 * kU - 1) / (256 * kU)));
   const float inv = 1.f / (float)world;
   if (multicast_ptr != nullptr) {
     p2p_allreduce_mean_multimem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)multicast_ptr, rank, world, n4, inv);
