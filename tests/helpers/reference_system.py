@@ -153,9 +153,58 @@ def main():
                    'grad': {n: float((g_ref[n] - out[n].grad).abs().max()) for n in names},
                    'train_num_rays': s.train_num_rays,
                    'train_num_rays_oracle': olosses.next_train_num_rays(n_rays, n_rays * 64, 5000, 1024)}
+    # ---- the reference's systems driving the DROP-IN models (INTEGRATION.md level 2), a few real training steps on the CPU: the models'
+    # CUDA modules swapped for the stand-ins, everything else -- preprocess_data, update_module_step, training_step, the optimizer built by
+    # the reference's parse_optimizer -- is the reference's own code calling our model classes
+    from systems.utils import parse_optimizer as ref_parse_optimizer, update_module_step as ref_update_module_step
+    from nsr_b200 import models as our_models, configs, tcnn as our_tcnn, nerfacc as our_nerfacc
+    from nsr_b200.models import nerf_model, neus_model
+    for mod in (nerf_model, neus_model):
+        for fn in ('ray_marching', 'render_weight_from_density', 'render_weight_from_alpha', 'accumulate_along_rays'):
+            if hasattr(mod, fn):
+                setattr(mod, fn, getattr(tp, fn))
+
+    def swap_tcnn(module):
+        for name, child in list(module.named_children()):
+            if isinstance(child, our_tcnn.NetworkWithInputEncoding):
+                setattr(module, name, tp.NetworkWithInputEncoding(child.n_input_dims, child.n_output_dims, child.encoding_config, child.network_config))
+            elif isinstance(child, our_tcnn.Encoding):
+                setattr(module, name, tp.Encoding(child.n_input_dims, child.encoding_config))
+            elif isinstance(child, our_tcnn.Network):
+                setattr(module, name, tp.Network(child.n_input_dims, child.n_output_dims, child.network_config))
+            else:
+                swap_tcnn(child)
+    our_nerfacc.OccupancyGrid.every_n_step = lambda self, step, occ_eval_fn, **k: setattr(self, '_binary', torch.ones_like(self._binary))
+    res['integration'] = {}
+    for kind, sysname, cfg_fn, lam_cfg in (('nerf', 'nerf-system', configs.nerf_blender, dict(lambda_rgb=1.0, lambda_distortion=0.0)),
+                                           ('neus', 'neus-system', configs.neus_blender, lam)):
+        mcfg = cfg_fn()
+        mcfg.update(fused=False, train_num_rays=64, max_train_num_rays=128, num_samples_per_ray=1024, dynamic_ray_sampling=True,
+                    batch_image_sampling=True, background_color='random')
+        mcfg['geometry']['fused'] = False
+        s = make_system(ref_systems.systems[sysname], mcfg, lam_cfg)
+        s.train_num_samples = 64 * 40                      # a sample budget this tiny scene can meet
+        torch.manual_seed(5)
+        s.model = our_models.make(kind, mcfg)
+        swap_tcnn(s.model)
+        s.model.train()
+        opt = ref_parse_optimizer(Config(dict(name='AdamW', args=dict(lr=0.01, betas=[0.9, 0.99], eps=1.e-15))), s.model)
+        losses_, rays_ = [], []
+        for step in range(4):
+            s.global_step = step
+            batch = {}
+            torch.manual_seed(100)                         # the same pixels every step: the loss on them must go down
+            s.preprocess_data(batch, 'train')
+            ref_update_module_step(s.model, 0, step)       # BaseSystem.on_train_batch_start
+            loss = s.training_step(batch, step)['loss']
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            losses_.append(float(loss.detach()))
+            rays_.append(int(s.train_num_rays))
+        res['integration'][kind] = {'losses': losses_, 'train_num_rays': rays_, 'model_class': type(s.model).__module__}
+
     # ---- parse_optimizer (systems/utils.py:314-325) on the same model and config section: param groups of the reference vs ours
-    from systems.utils import parse_optimizer as ref_parse_optimizer
-    from nsr_b200 import models as our_models, configs
     from nsr_b200.optim import parse_optimizer
     m = our_models.make('neus', configs.neus_dtu())
     ocfg = dict(name='AdamW', args=dict(lr=0.01, betas=[0.9, 0.99], eps=1.e-15),

@@ -83,6 +83,13 @@ def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step()
     assert nerf['train_num_rays'] == nerf['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 9000, 1024)
     assert abs(neus['loss'] - neus['loss_oracle']) < 1e-6 and max(neus['grad'].values()) < 1e-7
     assert neus['train_num_rays'] == neus['train_num_rays_oracle'] == RayBudget.rule(257, 257 * 64, 5000, 1024)
+    # level 2: the reference's systems (preprocess_data, update_module_step, training_step, parse_optimizer) drive OUR model classes for a
+    # few real optimizer steps on the CPU (CUDA modules swapped for the stand-ins): it trains, and the ray budget reacts
+    for kind in ('nerf', 'neus'):
+        e = res['integration'][kind]
+        assert e['model_class'] == f'nsr_b200.models.{kind}_model' and len(e['losses']) == 4
+        assert e['losses'][-1] < e['losses'][0] and all(v == v for v in e['losses'])
+        assert e['train_num_rays'][-1] != 64 and all(1 <= v <= 128 for v in e['train_num_rays'])
     # optim.parse_optimizer builds the reference's param groups (same tensors, names, hyper-parameters) around FusedAdamW
     opt = res['optimizer']
     assert opt['ref_class'] == 'AdamW' and opt['our_class'] == 'FusedAdamW' and opt['n_groups'] == 5
