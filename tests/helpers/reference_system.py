@@ -202,7 +202,18 @@ def main():
             opt.step()
             losses_.append(float(loss.detach()))
             rays_.append(int(s.train_num_rays))
-        res['integration'][kind] = {'losses': losses_, 'train_num_rays': rays_, 'model_class': type(s.model).__module__}
+        # validation_step (systems/nerf.py:136-149 / systems/neus.py:171-190): whole-image eval through model.eval() + chunk_batch
+        s.model.eval()
+        dataset.img_wh = (W, H)
+        grids = []
+        s.save_image_grid = lambda name, imgs: grids.append((name, [tuple(i['img'].shape) for i in imgs]))
+        vb = {'index': torch.tensor([1])}
+        s.preprocess_data(vb, 'validation')
+        with torch.no_grad():
+            vout = s.validation_step(vb, 0)
+        s.model.train()
+        res['integration'][kind] = {'losses': losses_, 'train_num_rays': rays_, 'model_class': type(s.model).__module__,
+                                    'val_psnr': float(vout['psnr']), 'val_index': int(vout['index'][0]), 'val_grid': grids[0][1]}
 
     # ---- parse_optimizer (systems/utils.py:314-325) on the same model and config section: param groups of the reference vs ours
     from nsr_b200.optim import parse_optimizer

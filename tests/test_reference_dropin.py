@@ -90,6 +90,8 @@ def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step()
         assert e['model_class'] == f'nsr_b200.models.{kind}_model' and len(e['losses']) == 4
         assert e['losses'][-1] < e['losses'][0] and all(v == v for v in e['losses'])
         assert e['train_num_rays'][-1] != 64 and all(1 <= v <= 128 for v in e['train_num_rays'])
+        # ... and their validation_step renders a whole image through model.eval() / chunk_batch and lays the outputs out as H x W images
+        assert 0 < e['val_psnr'] < 60 and e['val_index'] == 1 and e['val_grid'][:2] == [[24, 32, 3], [24, 32, 3]]
     # optim.parse_optimizer builds the reference's param groups (same tensors, names, hyper-parameters) around FusedAdamW
     opt = res['optimizer']
     assert opt['ref_class'] == 'AdamW' and opt['our_class'] == 'FusedAdamW' and opt['n_groups'] == 5
