@@ -136,7 +136,9 @@ class NeRFModel(BaseModel):
     def export(self, export_config):
         """models/nerf.py:153-161: isosurface mesh (+ per-vertex colour seen from above)"""
         mesh = self.isosurface()
-        if export_config.export_vertex_color:
+        if export_config.export_vertex_color and mesh['v_pos'].shape[0] == 0:
+            mesh['v_rgb'] = torch.zeros(0, 3)        # nothing crossed the threshold (the reference would fail on the empty chunk list)
+        elif export_config.export_vertex_color:
             dev = next(self.parameters()).device
             _, feature = chunk_batch(self.geometry, export_config.chunk_size, False, mesh['v_pos'].to(dev))
             viewdirs = torch.zeros(feature.shape[0], 3).to(feature)

@@ -292,7 +292,9 @@ class NeuSModel(BaseModel):
     def export(self, export_config):
         """models/neus.py:321-329: isosurface mesh (+ per-vertex "albedo": colour seen along the normal)"""
         mesh = self.isosurface()
-        if export_config.export_vertex_color:
+        if export_config.export_vertex_color and mesh['v_pos'].shape[0] == 0:
+            mesh['v_rgb'] = torch.zeros(0, 3)        # nothing crossed the threshold (the reference would fail on the empty chunk list)
+        elif export_config.export_vertex_color:
             dev = next(self.parameters()).device
             _, sdf_grad, feature = chunk_batch(self.geometry, export_config.chunk_size, False, mesh['v_pos'].to(dev), with_grad=True,
                                                with_feature=True)

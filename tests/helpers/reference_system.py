@@ -211,9 +211,31 @@ def main():
         s.preprocess_data(vb, 'validation')
         with torch.no_grad():
             vout = s.validation_step(vb, 0)
+        # export() (systems/nerf.py:213-218): model.export(config.export) -> save_mesh(name, **mesh); the GPU marching cubes replaced by the
+        # oracle's inside this process
+        from nsr_b200 import mcubes as nmc
+        from oracle import mcubes as omc
+        nmc.marching_cubes = lambda level, threshold=0.0, lo=(0., 0., 0.), hi=(1., 1., 1.), negate=True: tuple(
+            torch.from_numpy(a) for a in omc.marching_cubes(level.detach().cpu().numpy(), threshold, lo=lo, hi=hi, negate=negate))
+        nmc.check_cuda = lambda *a, **k: None
+        if kind == 'nerf':   # give the density field a surface to extract: the bench's density bump (a ball of high density)
+            from nsr_b200 import ops, synthetic
+            net = s.model.geometry.encoding_with_network
+            with torch.no_grad():
+                flat = net.params.detach().clone()
+                synthetic.shape_density(flat, ops.GridSpec(mcfg['geometry']['xyz_encoding_config']), net.n_mlp)
+                net.params.copy_(flat)
+        iso = dict(method='mc', resolution=20, chunk=4096, threshold=0.0 if kind == 'neus' else 5.0)
+        s.model.geometry.config['isosurface'] = Config(iso)
+        s.config['model']['geometry']['isosurface'] = Config(iso)
+        s.config['export'] = Config(dict(chunk_size=4096, export_vertex_color=True))
+        meshes = []
+        s.save_mesh = lambda name, **mesh: meshes.append((name, {k: tuple(v.shape) for k, v in mesh.items()}))
+        s.export()
         s.model.train()
         res['integration'][kind] = {'losses': losses_, 'train_num_rays': rays_, 'model_class': type(s.model).__module__,
-                                    'val_psnr': float(vout['psnr']), 'val_index': int(vout['index'][0]), 'val_grid': grids[0][1]}
+                                    'val_psnr': float(vout['psnr']), 'val_index': int(vout['index'][0]), 'val_grid': grids[0][1],
+                                    'mesh_name': meshes[0][0], 'mesh': meshes[0][1]}
 
     # ---- parse_optimizer (systems/utils.py:314-325) on the same model and config section: param groups of the reference vs ours
     from nsr_b200.optim import parse_optimizer

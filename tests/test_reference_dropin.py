@@ -92,6 +92,10 @@ def test_oracle_front_end_and_losses_are_pinned_to_the_reference_training_step()
         assert e['train_num_rays'][-1] != 64 and all(1 <= v <= 128 for v in e['train_num_rays'])
         # ... and their validation_step renders a whole image through model.eval() / chunk_batch and lays the outputs out as H x W images
         assert 0 < e['val_psnr'] < 60 and e['val_index'] == 1 and e['val_grid'][:2] == [[24, 32, 3], [24, 32, 3]]
+        # ... and their export() receives the mesh dictionary save_mesh expects (marching cubes: the oracle's, in that process)
+        m = e['mesh']
+        assert e['mesh_name'] == 'it3-mc20.obj' and set(m) == {'v_pos', 't_pos_idx', 'v_rgb'}
+        assert m['v_pos'][0] > 500 and m['v_pos'] == m['v_rgb'] and m['t_pos_idx'][1] == 3
     # optim.parse_optimizer builds the reference's param groups (same tensors, names, hyper-parameters) around FusedAdamW
     opt = res['optimizer']
     assert opt['ref_class'] == 'AdamW' and opt['our_class'] == 'FusedAdamW' and opt['n_groups'] == 5
