@@ -22,19 +22,6 @@ class ContractionType(enum.Enum):
     UN_BOUNDED_SPHERE = 2
 
 
-def _contract_inv(x, roi, ctype):
-    """unit cube -> world (nerfacc contract_inv)."""
-    lo, hi = roi[:3], roi[3:]
-    if ctype == ContractionType.AABB:
-        return x * (hi - lo) + lo
-    if ctype == ContractionType.UN_BOUNDED_SPHERE:
-        u = (x - 0.5) * 4
-        mag = u.norm(dim=-1, keepdim=True)
-        u = torch.where(mag > 1, u * (1 / (2 - mag) / mag), u)
-        return (u + 1) / 2 * (hi - lo) + lo
-    raise NotImplementedError(f'contraction type {ctype} not implemented')
-
-
 def pack_binary(binary):
     """bool [R,R,R] -> int32 words; bit (idx & 31) of word (idx >> 5), idx = ix*R*R + iy*R + iz."""
     flat = binary.reshape(-1)
@@ -128,26 +115,11 @@ class OccupancyGrid(nn.Module):
 
     @torch.no_grad()
     def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256):
-        """nerfacc OccupancyGrid._update.  CUDA grids run the three refresh kernels of csrc/occgrid.cu (points, EMA-max
-        update with deterministic duplicate handling, threshold + bit packing); the torch path below is the same rule for CPU grids."""
-        if self.occs.is_cuda:
-            return self._update_cuda(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps)
-        dev = self.occs.device
-        R = self._res
-        if step < warmup_steps:
-            indices = torch.arange(self.num_cells, device=dev)
-        else:
-            indices = self._sample_uniform_and_occupied_cells(self.num_cells // 4)
-        coords = torch.stack([indices // (R * R), (indices // R) % R, indices % R], dim=-1).float()
-        x = (coords + torch.rand_like(coords)) / R
-        if self._contraction_type == ContractionType.UN_BOUNDED_SPHERE:
-            mask = (x - 0.5).norm(dim=1) < 0.5
-            x, indices = x[mask], indices[mask]
-        x = _contract_inv(x, self._roi_aabb, self._contraction_type)
-        occ = occ_eval_fn(x).squeeze(-1).float()
-        self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
-        self._binary = (self.occs > torch.clamp(self.occs.mean(), max=occ_thre)).view(R, R, R)
-        self._bits_key = None
+        """nerfacc OccupancyGrid._update as the three refresh kernels of csrc/occgrid.cu (cell points, EMA-max update with
+        deterministic duplicate handling, threshold + bit packing).  CUDA only, like nerfacc 0.3.3 itself: there is no CPU path."""
+        if not self.occs.is_cuda:
+            raise NotImplementedError('OccupancyGrid._update: only CUDA grids are supported; there is no CPU path')
+        return self._update_cuda(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps)
 
     def _update_cuda(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, cells=None, jitter=None):
         """``cells`` / ``jitter`` (our extension) fix the random draws so tests can compare with the oracle."""

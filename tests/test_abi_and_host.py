@@ -85,6 +85,10 @@ def test_cpu_tensors_are_rejected_loudly():
         nerfacc.ray_marching(torch.zeros(2, 3), torch.ones(2, 3), render_step_size=0.1)
     with pytest.raises(NotImplementedError):
         nerfacc.render_weight_from_alpha(torch.rand(4, 1), ray_indices=torch.zeros(4, dtype=torch.long), n_rays=1)
+    grid = nerfacc.OccupancyGrid(torch.tensor([-1., -1., -1., 1., 1., 1.]), 16)
+    grid.train()
+    with pytest.raises(NotImplementedError):
+        grid.every_n_step(step=0, occ_eval_fn=lambda x: x[:, :1])
     net = tcnn.NetworkWithInputEncoding(3, 16, dict(otype='HashGrid', n_levels=4, n_features_per_level=2, log2_hashmap_size=8,
                                                     base_resolution=4, per_level_scale=1.5),
                                         dict(otype='FullyFusedMLP', activation='ReLU', output_activation='None', n_neurons=64,
