@@ -39,6 +39,14 @@ def nerf_vanilla(radius=1.5, n_frequencies=10, n_frequencies_dir=4):
     return cfg
 
 
+def nerf_colmap(radius=1.0):
+    """configs/nerf-colmap.yaml:13-63: unbounded scene -- NeRF with the mip-360 style sphere contraction, a 256^3 occupancy grid and cone
+    marching between near 0.2 and far 1e4 (models/nerf.py:21-27), 2048 nominal samples per ray"""
+    cfg = nerf_blender(radius)
+    cfg.update(num_samples_per_ray=2048, train_num_rays=128, ray_chunk=16384, learned_background=True)
+    return cfg
+
+
 def neus_blender(radius=1.5):
     return copy.deepcopy(dict(
         name='neus', radius=radius, num_samples_per_ray=1024, train_num_rays=256, max_train_num_rays=8192, grid_prune=True,

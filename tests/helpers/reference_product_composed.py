@@ -159,6 +159,17 @@ def main():
         return out['comp_rgb_full'].square().mean() + 0.1 * eik + 0.05 * out['opacity'].mean()
 
     run('nerf', configs.nerf_blender, prep_nerf, lambda out: out['comp_rgb'].square().mean() + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean())
+    def prep_colmap(m):
+        from nsr_b200 import ops
+        net = m.geometry.encoding_with_network
+        with torch.no_grad():
+            flat = net.params.detach().clone()
+            synthetic.shape_density(flat, ops.GridSpec(configs.nerf_colmap()['geometry']['xyz_encoding_config']), net.n_mlp, radius=1.0)
+            net.params.copy_(flat)
+            m.occupancy_grid._binary.copy_(torch.from_numpy(np.random.default_rng(1).random((256, 256, 256)) < 0.3))
+
+    run('nerf', configs.nerf_colmap, prep_colmap, lambda out: out['comp_rgb'].square().mean() + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean(),
+        ray_scale=1.0 / 1.5 * 0.4)
     run('neus', configs.neus_blender, prep_neus, neus_loss)
     run('neus', configs.neus_dtu, prep_dtu, neus_loss, ray_scale=1.0 / 1.5 * 0.6)
     print('RESULT ' + json.dumps(res))
