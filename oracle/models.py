@@ -75,6 +75,34 @@ def nerf_render(P, rays, binary, radius, step, bg_color, jitter=None, emulate_fp
     return out
 
 
+def nerf_unbounded_render(P, rays, binary, radius, step, cone_angle, near_plane, far_plane, bg_color, emulate_fp16=True, early_stop_eps=1e-4):
+    """NeRFModel.forward_ with learned_background (models/nerf.py:21-27,61-127; configs/nerf-colmap.yaml): no scene box, near / far planes,
+    blind cone stepping through the 256^3 grid under the UN_BOUNDED_SPHERE contraction, fields evaluated on contracted positions."""
+    rays = np.asarray(rays, np.float32)
+    o, d = rays[:, :3], rays[:, 3:6]
+    n_rays = len(rays)
+    roi = np.array([-radius] * 3 + [radius] * 3, np.float32)
+    t0, t1 = march.ray_interval(o, d, None, near_plane, far_plane, step, None)
+    ri, ts, te, _ = march.march_sequential(o, d, roi, binary, step, cone_angle, t0, t1, march.UN_BOUNDED_SPHERE)
+    ri_t, ts_t, te_t = torch.from_numpy(ri).long(), _t(ts)[:, None], _t(te)[:, None]
+    ot, dt = _t(o), _t(d)
+    S = contraction.UN_BOUNDED_SPHERE
+    with torch.no_grad():
+        sig, _ = nerf_field(P, ot[ri_t] + dt[ri_t] * (ts_t + te_t) / 2., None, radius, emulate_fp16, density_only=True, ctype=S)
+        keep, _ = render.render_visibility((1.0 - torch.exp(-sig[:, None] * (te_t - ts_t))).view(-1), ri_t, n_rays, early_stop_eps, 0.0)
+    n_marched = len(ri)
+    ri_t, ts_t, te_t = ri_t[keep], ts_t[keep], te_t[keep]
+    mid = (ts_t + te_t) / 2.
+    density, rgb = nerf_field(P, ot[ri_t] + dt[ri_t] * mid, dt[ri_t], radius, emulate_fp16, ctype=S)
+    w = render.render_weight_from_density(ts_t, te_t, density[:, None], ri_t, n_rays)
+    opacity = render.accumulate_along_rays(w, ri_t, None, n_rays)
+    depth = render.accumulate_along_rays(w, ri_t, mid, n_rays)
+    comp = render.accumulate_along_rays(w, ri_t, rgb, n_rays) + bg_color * (1.0 - opacity)
+    return {'comp_rgb': comp, 'opacity': opacity, 'depth': depth, 'rays_valid': opacity > 0,
+            'num_samples': torch.tensor([len(ts_t)], dtype=torch.int32), 'num_marched': n_marched,
+            'weights': w.view(-1), 'points': mid.view(-1), 'intervals': (te_t - ts_t).view(-1), 'ray_indices': ri_t.view(-1)}
+
+
 def smooth_l1_masked(comp_rgb, target, valid):
     """systems/nerf.py:97."""
     v = valid.view(-1)

@@ -51,6 +51,7 @@ run('c3_parity', neus_t.test_neus_blender_forward_backward_parity)          # es
 run('c1[False]', c1.test_c1_vanilla_nerf_matches_oracle, False)
 run('c4[False]', c1.test_c4_neus_dtu_matches_oracle, False)
 run('neuralangelo', c1.test_neuralangelo_config_finite_difference_normals_and_laplacian)
+run('nerf_colmap', c1.test_nerf_colmap_unbounded_matches_oracle)
 # ---- export tests: GPU marching cubes replaced by the oracle's
 from nsr_b200 import mcubes as nmc
 from oracle import mcubes as omc

@@ -99,6 +99,7 @@ def main():
                                  diff(g_ref[1], cflat.grad) / (float(cflat.grad.abs().max()) + 1e-30)]}
 
     from oracle import neus as oneus
+    from nsr_b200 import ops
     pts = (torch.rand(300, 3, generator=torch.Generator().manual_seed(9)) * 2 - 1) * 1.2
     model.update_step(0, 16)                                    # models/nerf.py:45-55: occ = density * render_step_size
     call = model.occupancy_grid.last_call
@@ -106,6 +107,38 @@ def main():
         dens, _ = om.nerf_field(P, pts, None, 1.5, emulate_fp16=False, density_only=True)
         res['nerf']['occ_fn'] = diff(call['occ_eval_fn'](pts), dens[:, None] * model.render_step_size)
     res['nerf']['occ_thre'] = call['occ_thre']
+
+    # ---- unbounded NeRF (nerf-colmap.yaml): sphere contraction, 256^3 grid, cone marching between the near and far planes
+    cfg = configs.nerf_colmap()
+    cfg['randomized'] = False
+    torch.manual_seed(3)
+    model = ref_models.make('nerf', Config(cfg))
+    bgb_nerf = np.random.default_rng(1).random((256, 256, 256)) < 0.3
+    with torch.no_grad():
+        net = model.geometry.encoding_with_network
+        flat = net.params.detach().clone()
+        synthetic.shape_density(flat, ops.GridSpec(cfg['geometry']['xyz_encoding_config']), net.n_mlp, radius=1.0)
+        net.params.copy_(flat)
+        model.occupancy_grid._binary.copy_(torch.from_numpy(bgb_nerf))
+    model.train()
+    model.background_color = bg
+    rays_u = rays.copy()
+    rays_u[:, :3] *= 1.0 / 1.5 * 0.4
+    out = model.forward_(torch.from_numpy(rays_u))
+    (out['comp_rgb'].square().mean() + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean()).backward()
+    g_ref = [p.grad.clone() for p in (model.geometry.encoding_with_network.params, model.texture.network.params)]
+    dflat = model.geometry.encoding_with_network.params.detach().clone().requires_grad_(True)
+    cflat = model.texture.network.params.detach().clone().requires_grad_(True)
+    P = om.NerfParams(cfg['geometry']['xyz_encoding_config'], dflat, cflat)
+    P.one_gather = True
+    o = om.nerf_unbounded_render(P, rays_u, bgb_nerf, 1.0, model.render_step_size, model.cone_angle, model.near_plane, model.far_plane, bg,
+                                 emulate_fp16=False)
+    (o['comp_rgb'].square().mean() + 0.1 * o['opacity'].mean() + 0.05 * o['depth'].mean()).backward()
+    res['nerf_colmap'] = {'num_samples': int(out['num_samples']), 'num_samples_oracle': int(o['num_samples']), 'num_marched': int(o['num_marched']),
+                          'diff': {k: diff(out[k], o[k]) for k in ('comp_rgb', 'opacity', 'depth', 'weights', 'points', 'intervals', 'ray_indices')},
+                          'grad_diff': [diff(g_ref[0], dflat.grad) / (float(dflat.grad.abs().max()) + 1e-30),
+                                        diff(g_ref[1], cflat.grad) / (float(cflat.grad.abs().max()) + 1e-30)],
+                          'constants': [float(model.render_step_size), float(model.cone_angle), float(model.near_plane), float(model.far_plane)]}
 
     # ---- NeuS (neus-blender.yaml)
     cfg = configs.neus_blender()

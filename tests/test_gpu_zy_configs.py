@@ -183,3 +183,43 @@ def test_c4_neus_dtu_matches_oracle(fused_mlps):
         for name, p in mine.named_parameters():
             assert cos(p.grad, rg[name].grad) >= ctol, name
     assert abs(float(model.variance.variance.grad) - float(var.grad)) <= 3e-2 * abs(float(var.grad)) + 1e-6
+
+
+@experimental
+def test_nerf_colmap_unbounded_matches_oracle():
+    """configs/nerf-colmap.yaml (unbounded NeRF: mip-360 sphere contraction, 256^3 occupancy grid, cone marching between near 0.2 and far 1e4)
+    through the drop-in model's per-op path against oracle.models.nerf_unbounded_render (pinned to the reference's forward_ by
+    tests/test_reference_dropin.py).  Sample sets up to the visibility threshold, per-ray colour 5e-3, gradients cosine >= 0.99."""
+    from nsr_b200 import models, configs, synthetic
+    cfg = configs.nerf_colmap()
+    cfg['randomized'] = False
+    torch.manual_seed(3)
+    model = models.make('nerf', cfg).to(D)
+    assert model._fused is None                                 # not the AABB shape: composed path (contracted cone marcher + per-op fields)
+    net, cnet = model.geometry.encoding_with_network, model.texture.network
+    with torch.no_grad():
+        from nsr_b200 import ops
+        grid_spec = ops.GridSpec(cfg['geometry']['xyz_encoding_config'])
+        p = net.params.detach().cpu().clone()
+        synthetic.shape_density(p, grid_spec, p.numel() - grid_spec.n_params, radius=1.0)   # flat vector: MLP first, then the table
+        net.params.copy_(p.to(D))
+    binary = np.random.default_rng(1).random((256, 256, 256)) < 0.3
+    model.occupancy_grid.set_binary(torch.from_numpy(binary))
+    rays = synthetic.sample_rays(192, seed=21)
+    rays[:, :3] *= 1.0 / 1.5 * 0.4
+    bg = torch.tensor([0.3, 0.6, 0.9])
+    model.background_color = bg.to(D)
+    model.train()
+    model.randomized = False
+    out = model.forward_(torch.from_numpy(rays).to(D))
+    (out['comp_rgb'].square().mean() + 0.1 * out['opacity'].mean() + 0.05 * out['depth'].mean()).backward()
+    dflat = net.params.detach().cpu().clone().requires_grad_(True)
+    cflat = cnet.params.detach().cpu().clone().requires_grad_(True)
+    P = omodels.NerfParams(cfg['geometry']['xyz_encoding_config'], dflat, cflat)
+    P.one_gather = True
+    ref = omodels.nerf_unbounded_render(P, rays, binary, 1.0, model.render_step_size, model.cone_angle, model.near_plane, model.far_plane, bg)
+    (ref['comp_rgb'].square().mean() + 0.1 * ref['opacity'].mean() + 0.05 * ref['depth'].mean()).backward()
+    assert int(ref['num_samples']) > 1000 and abs(int(out['num_samples']) - int(ref['num_samples'])) <= 6
+    assert float((out['comp_rgb'].detach().cpu() - ref['comp_rgb'].detach()).abs().max()) <= 5e-3
+    assert float((out['opacity'].detach().cpu() - ref['opacity'].detach()).abs().max()) <= 5e-3
+    assert cos(cnet.params.grad, cflat.grad) >= 0.99 and cos(net.params.grad, dflat.grad) >= 0.99

@@ -49,6 +49,10 @@ def test_oracle_orchestration_is_pinned_to_the_reference_forward():
     assert nerf['keys'] == ['comp_rgb', 'depth', 'intervals', 'num_samples', 'opacity', 'points', 'ray_indices', 'rays_valid', 'weights']
     assert nerf['num_samples'] == nerf['num_samples_oracle'] and 0.3 * nerf['num_marched'] < nerf['num_samples'] < 0.9 * nerf['num_marched']
     assert nerf['rays_valid_equal'] and max(nerf['diff'].values()) < 1e-6 and max(nerf['grad_diff']) < 1e-5
+    colmap = res['nerf_colmap']                      # unbounded NeRF (nerf-colmap.yaml): sphere contraction + cone marching + planes
+    assert colmap['num_samples'] == colmap['num_samples_oracle'] > 1000 and colmap['num_marched'] > 10 * colmap['num_samples']
+    assert max(colmap['diff'].values()) < 1e-6 and max(colmap['grad_diff']) < 1e-5
+    assert colmap['constants'] == [0.01, pytest.approx(10 ** (4 / 2048) - 1, rel=1e-12), 0.2, 1e4]
     assert set(neus['keys']) >= {'comp_rgb', 'comp_normal', 'opacity', 'depth', 'rays_valid', 'num_samples', 'sdf_samples', 'sdf_grad_samples',
                                  'weights', 'points', 'intervals', 'ray_indices', 'comp_rgb_bg', 'num_samples_bg', 'rays_valid_bg',
                                  'comp_rgb_full', 'num_samples_full', 'rays_valid_full'}
