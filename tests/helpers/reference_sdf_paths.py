@@ -118,6 +118,9 @@ def main():
     res['analytic_fallback'] = pair(an, (0,))
     fixed = dict(configs.neus_blender()['geometry'], grad_type='finite_difference', finite_difference_eps=0.01)
     res['finite_difference_fixed_eps'] = pair(fixed, (0,))
+    colmap = dict(configs.neuralangelo_dtu()['geometry'], grad_type='analytic', radius=0.6)   # neus-colmap.yaml: progressive grid + analytic normals
+    colmap.pop('finite_difference_eps', None)
+    res['analytic_progressive'] = pair(colmap, (0, 3500))
     print('RESULT ' + json.dumps(res))
 
 

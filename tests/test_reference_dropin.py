@@ -131,14 +131,14 @@ def test_product_torch_side_equals_the_reference_functions():
 def test_product_volume_sdf_torch_paths_equal_the_reference():
     """VolumeSDF paths of the product that are torch code rather than kernels -- finite-difference normals + laplacian under the
     ProgressiveBandHashGrid schedule (configs/neuralangelo-dtu-wmask.yaml), fixed-eps finite differences, the autograd fallback of the
-    analytic normal -- run on the CPU with the hash grid swapped for the oracle-backed stand-in, against the reference's VolumeSDF with the
+    analytic normal (plain grid, and the progressive grid of configs/neus-colmap.yaml) -- run on the CPU with the hash grid swapped for the oracle-backed stand-in, against the reference's VolumeSDF with the
     same weights (tests/helpers/reference_sdf_paths.py): values, level function, train / eval detaching, parameter gradients through an
     eikonal-style loss."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'reference_sdf_paths.py')], capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
-    assert set(res) == {'finite_difference_progressive', 'analytic_fallback', 'finite_difference_fixed_eps'}
+    assert set(res) == {'finite_difference_progressive', 'analytic_fallback', 'finite_difference_fixed_eps', 'analytic_progressive'}
     assert len(res['finite_difference_progressive']) == 6
     for section, cases in res.items():
         for case, d in cases.items():
