@@ -12,8 +12,8 @@ NSR_EXPERIMENTAL=0 timeout 300 python tools/neus_times.py > gpurun_out/neus_time
 NSR_EXPERIMENTAL=1 timeout 300 python tools/neus_times.py > gpurun_out/neus_times_fused_mlps.json 2> gpurun_out/neus_times_fused_mlps.err
 tail -c 1500 gpurun_out/neus_times_torch_mlps.json; echo; tail -c 1500 gpurun_out/neus_times_fused_mlps.json
 # end-to-end training on the analytic scene (PSNR before / after, steps/s): NeRF then NeuS
-timeout 600 python tools/train_synthetic.py --model nerf --steps 2000 --export > gpurun_out/train_nerf.json 2> gpurun_out/train_nerf.err
-timeout 600 python tools/train_synthetic.py --model neus --steps 2000 --export > gpurun_out/train_neus.json 2> gpurun_out/train_neus.err
+NSR_EXPERIMENTAL=0 timeout 600 python tools/train_synthetic.py --model nerf --steps 2000 --export > gpurun_out/train_nerf.json 2> gpurun_out/train_nerf.err
+NSR_EXPERIMENTAL=0 timeout 600 python tools/train_synthetic.py --model neus --steps 2000 --export > gpurun_out/train_neus.json 2> gpurun_out/train_neus.err
 tail -c 800 gpurun_out/train_nerf.json; tail -c 600 gpurun_out/train_nerf.err; tail -c 800 gpurun_out/train_neus.json; tail -c 600 gpurun_out/train_neus.err
 # A/B of the opt-in step variants on the bench workload (C2, one GPU)
 NSR_EXPERIMENTAL=0 timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
