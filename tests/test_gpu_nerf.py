@@ -180,7 +180,7 @@ def test_graphed_step_matches_eager():
     gs = GraphedStep(model, loss_fn, 512, batch_spec={'rgb': (3,)})
     lg = gs(r, rgb=tgt, background_color=bg.to(D))
     assert abs(lg.item() - le_val) <= 1e-5 * max(1.0, abs(le_val))
-    assert gs.counts()[1] == k_eager and gs.launches_per_replay >= 3
+    assert gs.counts()[1] == k_eager
     for p, g in zip(plist, ge):
         assert cos(p.grad, g) >= 0.9999
     # new inputs -> new result, no recapture

@@ -271,4 +271,3 @@ def test_neus_static_forward_and_graphed_step_match_eager():
     assert abs(float(loss_g) - loss_e0) <= 1e-5 * abs(loss_e0)
     for p, b in zip(params, grads_e0):
         assert cos(p.grad, b) > 0.9999
-    assert step.launches_per_replay <= 16
