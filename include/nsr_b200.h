@@ -294,11 +294,13 @@ int nsr_sample_points(const float* rays, const int32_t* ray_indices, const float
 /* ---- NeuS shading pieces (models/neus.py:117-139, 225, 237-243) --------------------------------------------------------------
  * (n, n_dev) / (k, k_dev) follow the convention above: non-NULL device count => n is the buffer capacity (CUDA-graph capture).
  * nsr_neus_alpha_fwd: normal = normalize(sdf_grad) and alpha = get_alpha(sdf, normal, dirs, dists) with the cos-anneal ratio;
- * dirs f32 [K,3] per-sample view directions, dists f32 [K] = t_ends - t_starts, inv_s: DEVICE scalar (already clipped to [1e-6, 1e6]).
+ * dirs f32 [K,3] per-sample view directions, dists f32 [K] = t_ends - t_starts, inv_s: DEVICE scalar (already clipped to [1e-6, 1e6]);
+ * cos_anneal_dev (may be NULL): DEVICE scalar that replaces cos_anneal_ratio, so that a captured graph follows the schedule of
+ * models/neus.py:113-115 without re-capture.
  * nsr_neus_alpha_bwd: d_alpha [K], d_normal [K,3] (may be NULL) -> d_sdf [K], d_sdf_grad [K,3], d_inv_s (+=, device scalar). */
-int nsr_neus_alpha_fwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, float* alpha, float* normal, int64_t n,
+int nsr_neus_alpha_fwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, const float* cos_anneal_dev, float* alpha, float* normal, int64_t n,
                        const int64_t* n_dev, void* stream);
-int nsr_neus_alpha_bwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, const float* d_alpha, const float* d_normal,
+int nsr_neus_alpha_bwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists, const float* inv_s, float cos_anneal_ratio, const float* cos_anneal_dev, const float* d_alpha, const float* d_normal,
                        float* d_sdf, float* d_sdf_grad, float* d_inv_s, int64_t n, const int64_t* n_dev, void* stream);
 /* render_weight_from_alpha + accumulate_along_rays x4 (opacity, depth at the sample midpoints, rgb, normal) in one pass per
  * direction.  offsets int64 [n_rays+1]; comp_normal is the un-normalised weighted sum.  Backward: any of the g_* may be NULL. */
@@ -412,10 +414,6 @@ int nsr_neus_loss_bwd(const nsr_neus_loss_t* p, const float* comp_rgb, const uin
                       const float* fg_mask, const float* sdf_grad, const float* sdf, const float* accum8, const float* g_loss,
                       float* g_comp_rgb, float* g_opacity, float* g_sdf_grad, float* g_sdf, int64_t n_rays, int64_t k, const int64_t* k_dev,
                       void* stream);
-/* development micro-benchmark of gather strategies (tools/gather_bench.py); not used by the product path */
-int nsr_dbg_gather(const nsr_grid_t* g, const float* pos, const void* table_h, void* out_h, int64_t n, int variant, int ctas_per_sm,
-                   void* stream);
-int nsr_dbg_scatter(const nsr_grid_t* g, const float* pos, const void* denc_h, float* grad, int64_t n, int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,5 +65,28 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+TOOLS = os.path.join(HERE, '..', 'tools')
+TOOLS_LIB = os.path.join(TOOLS, 'libnsr_tools.so')
+
+
+def build_tools(verbose=False):
+    """development micro-benchmarks (tools/csrc/*.cu: gather / scatter strategy kernels) as their OWN library, tools/libnsr_tools.so --
+    nothing of it is linked into the product library.  Rebuilt when a source or a product header is newer."""
+    srcs = sorted(os.path.join(TOOLS, 'csrc', f) for f in os.listdir(os.path.join(TOOLS, 'csrc')) if f.endswith('.cu'))
+    srcs.append(os.path.join(CSRC, 'api.cu'))   # nsr_set_error / nsr_sm_count
+    newest = max([os.path.getmtime(s) for s in srcs] + [_deps_mtime()])
+    if os.path.exists(TOOLS_LIB) and os.path.getmtime(TOOLS_LIB) >= newest:
+        return TOOLS_LIB
+    cmd = [NVCC] + ARCH + COMMON + (['-Xptxas', '-v'] if verbose else []) + ['-shared', '-o', TOOLS_LIB] + srcs + ['-lcudart']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed (tools)')
+    return TOOLS_LIB
+
+
 if __name__ == '__main__':
     print(build_lib(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    if '--tools' in sys.argv:
+        print(build_tools(verbose='--verbose' in sys.argv))

@@ -45,11 +45,19 @@ def to_primitive(c):
     return c
 
 
+# kernel paths seen green (parity + timing) on a B200: on by default, NSR_DISABLE=name[,name] switches one off again
+VALIDATED = {'mlp_vanilla', 'radiance_vanilla', 'pack_scan'}   # round 2: profiles/r2_gputest_first.log
+
+
 def experimental(name):
-    """True when the kernel path ``name`` is switched on.  Paths listed here were written after this round's GPU budget was spent: they
-    compile for sm_100a and have oracle-backed tests, but have not run on a B200 yet, so they stay off unless the environment asks
-    for them: NSR_EXPERIMENTAL=1 (all) or a comma-separated list of names."""
+    """True when the kernel path ``name`` is switched on.  Paths in VALIDATED are on unless NSR_DISABLE lists them; any other name is a
+    path that has not run on a B200 yet and stays off unless the environment asks for it: NSR_EXPERIMENTAL=1 (all) or a comma-separated
+    list of names."""
     import os
+    if name in [x.strip() for x in os.environ.get('NSR_DISABLE', '').split(',') if x.strip()]:
+        return False
+    if name in VALIDATED:
+        return True
     v = os.environ.get('NSR_EXPERIMENTAL', '').strip()
     if v in ('', '0'):
         return False

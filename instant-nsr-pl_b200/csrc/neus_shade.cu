@@ -38,9 +38,11 @@ __device__ __forceinline__ AlphaTerms alpha_terms(float sdf, float gx, float gy,
 
 __global__ void __launch_bounds__(256) neus_alpha_fwd_kernel(const float* __restrict__ sdf, const float* __restrict__ sdf_grad,
                                                              const float* __restrict__ dirs, const float* __restrict__ dists,
-                                                             const float* __restrict__ inv_s, float cos_anneal, float* __restrict__ alpha,
-                                                             float* __restrict__ normal, int64_t n_cap, const int64_t* __restrict__ n_dev) {
+                                                             const float* __restrict__ inv_s, float cos_anneal, const float* __restrict__ cos_dev,
+                                                             float* __restrict__ alpha, float* __restrict__ normal, int64_t n_cap,
+                                                             const int64_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  if (cos_dev) cos_anneal = __ldg(cos_dev);  // schedule value kept on the device: a captured graph follows update_step()
   const int64_t i = blockIdx.x * 256ll + threadIdx.x;
   if (i >= n) return;
   const AlphaTerms t = alpha_terms(sdf[i], sdf_grad[i * 3], sdf_grad[i * 3 + 1], sdf_grad[i * 3 + 2], dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2],
@@ -55,11 +57,12 @@ __global__ void __launch_bounds__(256) neus_alpha_fwd_kernel(const float* __rest
 // outputs: d sdf [K], d sdf_grad [K,3], d inv_s (one atomicAdd per block).
 __global__ void __launch_bounds__(256) neus_alpha_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ sdf_grad,
                                                              const float* __restrict__ dirs, const float* __restrict__ dists,
-                                                             const float* __restrict__ inv_s, float cos_anneal,
+                                                             const float* __restrict__ inv_s, float cos_anneal, const float* __restrict__ cos_dev,
                                                              const float* __restrict__ d_alpha, const float* __restrict__ d_normal,
                                                              float* __restrict__ d_sdf, float* __restrict__ d_sdf_grad,
                                                              float* __restrict__ d_inv_s, int64_t n_cap, const int64_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  if (cos_dev) cos_anneal = __ldg(cos_dev);
   const int64_t i = blockIdx.x * 256ll + threadIdx.x;
   float ds_part = 0.f;
   if (i < n) {
@@ -105,24 +108,24 @@ __global__ void __launch_bounds__(256) neus_alpha_bwd_kernel(const float* __rest
 }  // namespace
 
 extern "C" int nsr_neus_alpha_fwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists,
-                                  const float* inv_s, float cos_anneal_ratio, float* alpha,
+                                  const float* inv_s, float cos_anneal_ratio, const float* cos_anneal_dev, float* alpha,
                                   float* normal, int64_t n, const int64_t* n_dev, void* stream) {
   NSR_REQUIRE(inv_s != nullptr, "nsr_neus_alpha_fwd: inv_s (device scalar) is NULL");
   if (n == 0) return 0;
   neus_alpha_fwd_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(sdf, sdf_grad, dirs, dists, inv_s,
-                                                                               cos_anneal_ratio, alpha, normal, n, n_dev);
+                                                                               cos_anneal_ratio, cos_anneal_dev, alpha, normal, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_neus_alpha_fwd");
   return 0;
 }
 
 extern "C" int nsr_neus_alpha_bwd(const float* sdf, const float* sdf_grad, const float* dirs, const float* dists,
-                                  const float* inv_s, float cos_anneal_ratio,
+                                  const float* inv_s, float cos_anneal_ratio, const float* cos_anneal_dev,
                                   const float* d_alpha, const float* d_normal, float* d_sdf, float* d_sdf_grad, float* d_inv_s, int64_t n,
                                   const int64_t* n_dev, void* stream) {
   NSR_REQUIRE(inv_s != nullptr && d_inv_s != nullptr, "nsr_neus_alpha_bwd: inv_s / d_inv_s is NULL");
   if (n == 0) return 0;
   neus_alpha_bwd_kernel<<<nsr_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(sdf, sdf_grad, dirs, dists, inv_s,
-                                                                               cos_anneal_ratio, d_alpha, d_normal, d_sdf, d_sdf_grad, d_inv_s, n, n_dev);
+                                                                               cos_anneal_ratio, cos_anneal_dev, d_alpha, d_normal, d_sdf, d_sdf_grad, d_inv_s, n, n_dev);
   NSR_CHECK_LAUNCH("nsr_neus_alpha_bwd");
   return 0;
 }

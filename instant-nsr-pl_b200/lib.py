@@ -85,8 +85,6 @@ _SIGNATURES = {
     'nsr_weight_from_alpha_fwd': [P, P, P, P, I64, P],
     'nsr_weight_from_alpha_bwd': [P, P, P, P, P, P, I64, P],
     'nsr_accumulate': [P, P, P, P, I32, I64, P],
-    'nsr_dbg_gather': [P, P, P, P, I64, I32, I32, P],
-    'nsr_dbg_scatter': [P, P, P, P, I64, I32, P],
     'nsr_march_rays_mask': [P, P, P, P, P, P, I32, P, P, I64, P],
     'nsr_scan_counts_order': [P, P, P, I64, P],
     'nsr_march_rays_expand': [P, P, I32, P, P, P, P, P, I64, P],
@@ -99,8 +97,8 @@ _SIGNATURES = {
     'nsr_neus_field_bwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, P, P, P, P, P, P, I64, P, P],
     'nsr_absmax3': [P, I64, P, I64, P, I64, P, I64, P, P],
     'nsr_sample_points': [P, P, P, P, P, P, P, I64, P, P],
-    'nsr_neus_alpha_fwd': [P, P, P, P, P, F32, P, P, I64, P, P],
-    'nsr_neus_alpha_bwd': [P, P, P, P, P, F32, P, P, P, P, P, I64, P, P],
+    'nsr_neus_alpha_fwd': [P, P, P, P, P, F32, P, P, P, I64, P, P],
+    'nsr_neus_alpha_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, I64, P, P],
     'nsr_neus_composite_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_neus_composite_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_radiance_fwd': [P, P, P, P, P, P, I64, P, P],

@@ -28,12 +28,19 @@ class VarianceNetwork(nn.Module):
             self.reach_max_steps = self.config.reach_max_steps
             self.max_inv_s = self.config.max_inv_s
             self.do_mod = False
+            self.mod_val = float(self.max_inv_s)
+            self._mod_dev = None   # device copy of mod_val (graph-safe: update_step refreshes it in place)
 
     @property
     def inv_s(self):
         val = torch.exp(self.variance * 10.0)
         if self.modulate and self.do_mod:
-            val = val.clamp_max(self.mod_val)
+            if val.is_cuda:   # the cap lives on the device so that a captured CUDA graph follows the schedule (nsr_b200.graph.GraphedStep)
+                if self._mod_dev is None or self._mod_dev.device != val.device:
+                    self._mod_dev = torch.full((), float(self.mod_val), device=val.device)
+                val = torch.minimum(val, self._mod_dev)
+            else:
+                val = val.clamp_max(self.mod_val)
         return val
 
     def forward(self, x):
@@ -48,6 +55,8 @@ class VarianceNetwork(nn.Module):
         else:
             ramp = (global_step / self.reach_max_steps) * (self.max_inv_s - self.prev_inv_s) + self.prev_inv_s
             self.mod_val = min(ramp, self.max_inv_s)
+            if self._mod_dev is not None:
+                self._mod_dev.fill_(float(self.mod_val))
 
 
 def _long_keep_offsets(ray_indices):
@@ -90,6 +99,7 @@ class NeuSModel(BaseModel):
         self.background_color = None
         self.render_step_size = 1.732 * 2 * r / cfg.num_samples_per_ray
         self.cos_anneal_ratio = 1.0
+        self._cos_dev = None        # device copy of cos_anneal_ratio for the static (CUDA-graph) path
         self._march_static = None
 
     def _inv_s(self, n):
@@ -104,6 +114,8 @@ class NeuSModel(BaseModel):
         update_module_step(self.variance, epoch, global_step)
         anneal_end = self.config.get('cos_anneal_end', 0)
         self.cos_anneal_ratio = 1.0 if anneal_end == 0 else min(1.0, global_step / anneal_end)
+        if self._cos_dev is not None:
+            self._cos_dev.fill_(float(self.cos_anneal_ratio))
         if not (self.training and self.config.grid_prune):
             return
         half = self.render_step_size * 0.5
@@ -192,7 +204,9 @@ class NeuSModel(BaseModel):
             positions, t_dirs, dists = ops.sample_points(rays, ri32, t_starts, t_ends)
             sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
             inv_s = self.variance.inv_s.clip(1e-6, 1e6).reshape(1)
-            alpha, normal = ops.neus_alpha(sdf, sdf_grad, inv_s, t_dirs, dists, self.cos_anneal_ratio)
+            if self._cos_dev is None or self._cos_dev.device != dev:
+                self._cos_dev = torch.full((1,), float(self.cos_anneal_ratio), device=dev)
+            alpha, normal = ops.neus_alpha(sdf, sdf_grad, inv_s, t_dirs, dists, self._cos_dev)
             rgb = self.texture(feature, t_dirs, normal)
         weights, opacity, depth, comp_rgb, comp_normal = ops.neus_composite(alpha, rgb, normal, t_starts, t_ends, offsets)
         comp_normal = F.normalize(comp_normal, p=2, dim=-1)

@@ -85,14 +85,23 @@ class OccupancyGrid(nn.Module):
     def contraction_type(self):
         return self._contraction_type
 
+    @staticmethod
+    def _keep_storage(old, new):
+        """the packed fields keep their device storage across refreshes: kernels captured in a CUDA graph hold these pointers"""
+        if old is not None and old.shape == new.shape and old.device == new.device and old.dtype == new.dtype:
+            old.copy_(new)
+            return old
+        return new
+
     def bits(self):
         key = (self._binary._version, self._binary.data_ptr())
         if self._bits_key != key:
-            self._bits = pack_binary(self._binary)
+            self._bits = self._keep_storage(self._bits, pack_binary(self._binary))
             R = self._res
-            self._coarse = None
             if R % 4 == 0 and R <= 128:  # "any bit in the 4^3 block": lets the marcher skip empty space without a global load
-                self._coarse = pack_binary(self._binary.view(R // 4, 4, R // 4, 4, R // 4, 4).any(dim=5).any(dim=3).any(dim=1))
+                self._coarse = self._keep_storage(self._coarse, pack_binary(self._binary.view(R // 4, 4, R // 4, 4, R // 4, 4).any(dim=5).any(dim=3).any(dim=1)))
+            else:
+                self._coarse = None
             self._bits_key = key
         return self._bits
 
@@ -101,7 +110,7 @@ class OccupancyGrid(nn.Module):
         return self._coarse
 
     def set_binary(self, binary):
-        self._binary = binary.to(device=self._binary.device, dtype=torch.bool).view_as(self._binary).clone()
+        self._binary.copy_(binary.to(device=self._binary.device, dtype=torch.bool).view_as(self._binary))   # in place: pointer stays
         self._bits_key = None
 
     @torch.no_grad()
@@ -146,14 +155,23 @@ class OccupancyGrid(nn.Module):
             self._work = (torch.empty(C, device=dev), torch.empty(1024, dtype=torch.float64, device=dev))
         scratch, partial = self._work
         lib.call('nsr_occgrid_update', ptr(self.occs), ptr(cells), ptr(occ), ptr(scratch), float(ema_decay), ptr(partial), n, C, stream())
-        binary = torch.empty(C, dtype=torch.uint8, device=dev)
-        bits = torch.empty((C + 31) // 32, dtype=torch.int32, device=dev)
+        # the kernel writes INTO the persistent buffers (bool grid, packed bits, coarse field): their device pointers never change, so a
+        # CUDA graph captured before this refresh (nsr_b200.graph.GraphedStep) marches against the new field on its next replay
+        if not self._binary.is_contiguous():
+            self._binary = self._binary.contiguous()
+        n_bits = (C + 31) // 32
+        if self._bits is None or self._bits.device != dev or self._bits.numel() != n_bits:
+            self._bits = torch.empty(n_bits, dtype=torch.int32, device=dev)
         coarse = None
         if R % 4 == 0 and R <= 128:
-            coarse = torch.empty(((R // 4) ** 3 + 31) // 32, dtype=torch.int32, device=dev)
-        lib.call('nsr_occgrid_binarize', ptr(self.occs), ptr(partial), float(occ_thre), ptr(binary), ptr(bits), ptr(coarse), R, C, stream())
-        self._binary = binary.view(torch.bool).view(R, R, R)
-        self._bits, self._coarse = bits, coarse
+            n_coarse = ((R // 4) ** 3 + 31) // 32
+            if self._coarse is None or self._coarse.device != dev or self._coarse.numel() != n_coarse:
+                self._coarse = torch.empty(n_coarse, dtype=torch.int32, device=dev)
+            coarse = self._coarse
+        else:
+            self._coarse = None
+        lib.call('nsr_occgrid_binarize', ptr(self.occs), ptr(partial), float(occ_thre), ptr(self._binary.view(torch.uint8)), ptr(self._bits), ptr(coarse),
+                 R, C, stream())
         self._bits_key = (self._binary._version, self._binary.data_ptr())   # packed by the kernel: bits() must not re-pack
 
     @torch.no_grad()

@@ -532,9 +532,12 @@ class _NeusAlpha(torch.autograd.Function):
         n = sdf.shape[0]
         alpha = torch.empty(n, device=sdf.device)
         normal = torch.empty(n, 3, device=sdf.device)
-        lib.call('nsr_neus_alpha_fwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), float(cos_anneal), ptr(alpha), ptr(normal),
+        # cos_anneal: python float, or a 1-element CUDA tensor (the model's device copy of the schedule value: graph-safe)
+        cos_dev = cos_anneal if torch.is_tensor(cos_anneal) else None
+        cos_val = 0.0 if cos_dev is not None else float(cos_anneal)
+        lib.call('nsr_neus_alpha_fwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), cos_val, ptr(cos_dev), ptr(alpha), ptr(normal),
                  n, ptr(_LIVE_ROWS), stream())
-        ctx.cos_anneal, ctx.k_dev = float(cos_anneal), _LIVE_ROWS
+        ctx.cos_anneal, ctx.cos_dev, ctx.k_dev = cos_val, cos_dev, _LIVE_ROWS
         ctx.save_for_backward(sdf, sdf_grad, inv_s, dirs, dists)
         return alpha, normal
 
@@ -546,7 +549,7 @@ class _NeusAlpha(torch.autograd.Function):
         d_sdf = torch.empty(n, device=sdf.device)
         d_grad = torch.empty(n, 3, device=sdf.device)
         d_inv_s = torch.zeros_like(inv_s)
-        lib.call('nsr_neus_alpha_bwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), ctx.cos_anneal, ptr(g_alpha),
+        lib.call('nsr_neus_alpha_bwd', ptr(sdf), ptr(sdf_grad), ptr(dirs), ptr(dists), ptr(inv_s), ctx.cos_anneal, ptr(ctx.cos_dev), ptr(g_alpha),
                  ptr(contig(g_normal, torch.float32)), ptr(d_sdf), ptr(d_grad), ptr(d_inv_s), n, ptr(ctx.k_dev), stream())
         return d_sdf, d_grad, d_inv_s, None, None, None
 

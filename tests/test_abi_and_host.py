@@ -168,9 +168,13 @@ def test_experimental_switch_and_vanilla_mlp_stays_on_torch_for_cpu(monkeypatch)
     from nsr_b200.config import experimental
     from nsr_b200.models.networks import VanillaMLP
     monkeypatch.delenv('NSR_EXPERIMENTAL', raising=False)
-    assert not experimental('mlp_vanilla')
-    monkeypatch.setenv('NSR_EXPERIMENTAL', 'mlp_vanilla, other')
-    assert experimental('mlp_vanilla') and experimental('other') and not experimental('radiance_vanilla')
+    monkeypatch.delenv('NSR_DISABLE', raising=False)
+    assert experimental('mlp_vanilla') and experimental('radiance_vanilla') and not experimental('something_new')   # validated paths: on
+    monkeypatch.setenv('NSR_DISABLE', 'mlp_vanilla, other')
+    assert not experimental('mlp_vanilla') and experimental('radiance_vanilla')
+    monkeypatch.delenv('NSR_DISABLE')
+    monkeypatch.setenv('NSR_EXPERIMENTAL', 'new_a, new_b')
+    assert experimental('new_a') and experimental('new_b') and not experimental('new_c')
     monkeypatch.setenv('NSR_EXPERIMENTAL', '1')
     assert experimental('anything')
     net = VanillaMLP(8, 3, dict(n_neurons=64, n_hidden_layers=2, output_activation='none'))

@@ -19,6 +19,7 @@ def cos(a, b):
 
 
 def build(fused, n_rays=600, seed=0, peak=10.0):
+    """peak=None: synthetic.shape_density's default = the bench workload"""
     from nsr_b200 import models, configs, synthetic
     D = torch.device('cuda:0')
     cfg = configs.nerf_blender()
@@ -35,7 +36,7 @@ def build(fused, n_rays=600, seed=0, peak=10.0):
         p = net.params.detach().cpu().clone()
         # a rougher table than tcnn's 1e-4 init so every level matters, then the density bump
         p[net.mlp.n_params:] = ((torch.rand(net.grid.n_params, generator=g) * 2 - 1) * 0.1)
-        synthetic.shape_density(p, net.grid, net.mlp.n_params, peak_logit=peak)
+        synthetic.shape_density(p, net.grid, net.mlp.n_params, **({} if peak is None else {'peak_logit': peak}))
         net.params.copy_(p.to(D))
     binary = synthetic.occupancy()
     model.occupancy_grid.set_binary(torch.from_numpy(binary))
@@ -63,7 +64,18 @@ def oracle_run(model, binary, rays, jitter, bg, target):
 def test_nerf_model_forward_backward_parity(fused):
     """per_ray: per-ray forward kernel + tile backward (default); per_ray_bwd: per-ray forward AND backward kernels;
     two_pass: pre-pass + sample-tile kernels; False: per-op composition"""
-    model, cfg, binary, rays, jitter, bg = build(fused)
+    check_parity(fused, 600)
+
+
+def test_nerf_full_size_c2_8192_rays_parity():
+    """BASELINE.json config 2 at its full size (8192 rays, ~440 k marched / ~270 k kept samples: the bench workload's density peak): the
+    persistent per-ray kernel's longest-first ticket order, the 64-word lattice masks and the tile backward's grid-stride loop are only
+    exercised at this size.  Same tolerances as the 600-ray cases."""
+    check_parity('per_ray', 8192, seed=11, peak=None, min_marched=300000)
+
+
+def check_parity(fused, n_rays, seed=0, peak=10.0, min_marched=10000):
+    model, cfg, binary, rays, jitter, bg = build(fused, n_rays=n_rays, seed=seed, **({} if peak is None else {'peak': peak}))
     assert (model._fused is not None) == bool(fused)
     D = torch.device('cuda:0')
     target = torch.rand(len(rays), 3, generator=torch.Generator().manual_seed(3))
@@ -78,7 +90,7 @@ def test_nerf_model_forward_backward_parity(fused):
     # ---- sample sets
     k, k_r = int(out['num_samples'].item()), int(ref['num_samples'].item())
     ambiguous = int(((ref['trans_pre'] / 1e-4 - 1).abs() < 1e-3).sum())
-    assert ref['num_marched'] > 10000 and 0.2 * ref['num_marched'] < k_r < ref['num_marched']
+    assert ref['num_marched'] > min_marched and 0.2 * ref['num_marched'] < k_r < ref['num_marched']
     assert abs(k - k_r) <= ambiguous
     if k == k_r:
         assert torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
@@ -190,6 +202,28 @@ def test_graphed_step_matches_eager():
     assert abs(l2.item() - loss_fn(out2, {'rgb': tgt}).item()) <= 1e-5
     # static outputs: capacity-length per-sample buffers + device-side count
     assert gs.out['weights'].shape[0] == 512 * model._fused.cap_per_ray and gs.out['num_samples'].dtype == torch.int32
+    # an occupancy refresh between replays (models/nerf.py:45-55 every 16 steps) is picked up WITHOUT re-capture: the refresh kernels
+    # write into the same device buffers the captured marcher reads
+    og = model.occupancy_grid
+    ptrs = (og.bits().data_ptr(), og.coarse_bits().data_ptr(), og.binary.data_ptr())
+    model.update_step(0, 0)              # step 0 < warm-up: every cell is re-evaluated from the current density field
+    assert ptrs == (og.bits().data_ptr(), og.coarse_bits().data_ptr(), og.binary.data_ptr())
+    assert float((og.binary.cpu() != torch.from_numpy(binary)).float().mean()) > 0.01   # the refreshed field really differs
+    l3 = gs(r2, rgb=tgt, background_color=bg.to(D))
+    k3 = gs.counts()[1]
+    out3 = model.forward_(r2)
+    assert k3 == int(out3['num_samples']) and abs(l3.item() - loss_fn(out3, {'rgb': tgt}).item()) <= 1e-5
+    # an occupancy refresh between replays (models/nerf.py:45-55 every 16 steps) is picked up WITHOUT re-capture: the refresh kernels
+    # write into the same device buffers the captured marcher reads
+    ptrs = (model.occupancy_grid.bits().data_ptr(), model.occupancy_grid.coarse_bits().data_ptr(), model.occupancy_grid.binary.data_ptr())
+    model.update_step(0, 0)              # step 0 < warm-up: every cell is re-evaluated from the current density field
+    assert ptrs == (model.occupancy_grid.bits().data_ptr(), model.occupancy_grid.coarse_bits().data_ptr(), model.occupancy_grid.binary.data_ptr())
+    changed = float((model.occupancy_grid.binary.cpu() != torch.from_numpy(binary)).float().mean())
+    assert changed > 0.01                # the refreshed field really differs from the synthetic one
+    l3 = gs(r2, rgb=tgt, background_color=bg.to(D))
+    k3 = gs.counts()[1]
+    out3 = model.forward_(r2)
+    assert k3 == int(out3['num_samples']) and abs(l3.item() - loss_fn(out3, {'rgb': tgt}).item()) <= 1e-5
     assert {'offsets_loose', 'offsets_packed', 'loose_pos', 't_starts'} <= set(gs.out)
 
 

@@ -52,8 +52,17 @@ def build(cfg_fn, n_rays, seed):
 
 
 def test_neus_blender_forward_backward_parity():
+    check_neus_blender(300, 0, 5000)
+
+
+def test_neus_full_size_c3_8192_rays_parity():
+    """BASELINE.json config 3 at its full size (neus-blender with mask, 8192 rays, ~300 k samples): same tolerances as the 300-ray case."""
+    check_neus_blender(8192, 7, 250000)
+
+
+def check_neus_blender(n_rays, seed, min_samples):
     from nsr_b200 import configs
-    model, cfg, binary, rays, jitter = build(configs.neus_blender, 300, 0)
+    model, cfg, binary, rays, jitter = build(configs.neus_blender, n_rays, seed)
     # update_step(0, 5000) is not a multiple of 16 -> grid untouched; restore binary in case
     model.occupancy_grid.set_binary(torch.from_numpy(binary))
     assert abs(model.cos_anneal_ratio - 0.25) < 1e-9
@@ -90,7 +99,7 @@ def test_neus_blender_forward_backward_parity():
     loss_r = losses(ref, target, mask)
     loss_r.backward()
 
-    assert int(out['num_samples']) == len(ref['ray_indices']) > 5000
+    assert int(out['num_samples']) == len(ref['ray_indices']) > min_samples
     assert torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
     assert (out['sdf_samples'].detach().cpu() - ref['sdf_samples'].detach()).abs().max().item() <= 2e-3
     # the analytic normal of a trilinear interpolant jumps across cell faces (fine levels: scale 2047 x table step), so a sample
@@ -271,3 +280,16 @@ def test_neus_static_forward_and_graphed_step_match_eager():
     assert abs(float(loss_g) - loss_e0) <= 1e-5 * abs(loss_e0)
     for p, b in zip(params, grads_e0):
         assert cos(p.grad, b) > 0.9999
+    # the schedule moves between replays (models/neus.py:113-115 cos annealing; occupancy refresh every 16 steps): the captured graph
+    # reads both from device memory that update_step() refreshes in place -- same result as a fresh eager step, no re-capture
+    ptrs = (model.occupancy_grid.bits().data_ptr(), model.occupancy_grid.coarse_bits().data_ptr())
+    model.update_step(0, 12000)          # 12000 % 16 == 0: grid refresh; cos_anneal_ratio 0.25 -> 0.6
+    assert abs(model.cos_anneal_ratio - 0.6) < 1e-9 and ptrs == (model.occupancy_grid.bits().data_ptr(), model.occupancy_grid.coarse_bits().data_ptr())
+    loss_g2 = float(step(rays_d, rgb=target, fg_mask=mask, background_color=bg))
+    grads_g2 = [p.grad.clone() for p in params]
+    model.background_color = bg
+    _, loss_e2, _, grads_e2 = run(False)
+    assert abs(loss_e2 - loss_e0) > 1e-4 * abs(loss_e0)         # the step really changed ...
+    assert abs(loss_g2 - loss_e2) <= 1e-5 * abs(loss_e2)        # ... and the replay followed it
+    for a, b in zip(grads_g2, grads_e2):
+        assert cos(a, b) > 0.9999

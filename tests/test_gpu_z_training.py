@@ -3,15 +3,14 @@ oracle's render + torch.optim.AdamW (the reference's optimizer, systems/utils.py
 targets.  Adam normalises every gradient entry, so table entries whose gradient is rounding noise may step differently; the loss is what
 must agree.  Tolerance: per-step loss within 3 % of the oracle's for six steps, and the loss must go down on both sides.
 
-Not yet seen green on a B200 (written after the round's GPU budget was spent): NSR_EXPERIMENTAL=1 runs it."""
+First seen green on a B200 in round 2 (profiles/r2_gputest_first.log)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 from oracle import models as omodels
 

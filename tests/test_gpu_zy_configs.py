@@ -5,9 +5,7 @@ reference's own torch fields (optionally on the fused VanillaMLP kernels), again
 Tolerances: kept-sample counts equal up to samples whose transmittance sits at early_stop_eps (<= 3), per-ray colour 2e-3 (5e-3 with the
 fp16-operand VanillaMLP kernels), network gradients cosine >= 0.999 (0.99).
 
-Not yet seen on a B200 (written after the round's GPU budget was spent).  The whole test logic was dry-run on the CPU with the oracle-backed
-stand-ins (tests/test_dryrun.py).  C1 with the torch VanillaMLP layers touches only the marching / compositing kernels (green parity
-tests of their own) and runs; everything else here waits behind NSR_EXPERIMENTAL=1 for its first B200 run (tools/run_experimental.sh)."""
+First seen green on a B200 in round 2 (profiles/r2_gputest_first.log); runs un-gated."""
 import os
 
 import numpy as np
@@ -15,8 +13,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-experimental = pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')
-TORCH_AND_FUSED_MLPS = [False, pytest.param(True, marks=experimental)]   # the fused VanillaMLP kernels stay opt-in until their own tests are green
+TORCH_AND_FUSED_MLPS = [False, True]   # torch (cuBLAS) layers pinned by `fused: False`, and the fused VanillaMLP kernels (the default)
 
 from oracle import models as omodels
 
@@ -71,7 +68,6 @@ def test_c1_vanilla_nerf_matches_oracle(fused_mlp):
         assert geo._spec and tex._spec               # 60 -> 64 -> 16 and 40 -> 64 -> 64 -> 3 on nsr_mlp_vanilla_*
 
 
-@experimental
 def test_neuralangelo_config_finite_difference_normals_and_laplacian():
     """configs/neuralangelo-dtu-wmask.yaml through the drop-in 'neus' model (per-op kernels + torch: ProgressiveBandHashGrid mask,
     finite-difference normals and laplacian, models/geometry.py:181-199): the module's normals / laplacian equal central differences of
@@ -118,9 +114,13 @@ def test_neuralangelo_config_finite_difference_normals_and_laplacian():
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
 
 
-@experimental
+def test_c4_full_size_4096_rays_matches_oracle():
+    """BASELINE.json config 4 at its full size (neus-dtu, learned background, 4096 rays) on the default (fused VanillaMLP) kernels."""
+    test_c4_neus_dtu_matches_oracle(True, n_rays=4096, min_fg=40000)
+
+
 @pytest.mark.parametrize('fused_mlps', [False, True])
-def test_c4_neus_dtu_matches_oracle(fused_mlps):
+def test_c4_neus_dtu_matches_oracle(fused_mlps, n_rays=256, min_fg=3000):
     """Config C4 (neus-dtu.yaml: NeuS foreground + learned NeRF++ background, VanillaMLP colour / background networks) through the drop-in
     model against oracle.models.neus_dtu_render, whose orchestration is pinned to the reference's own forward_ (tests/test_reference_dropin.py).
     Tolerances as for C3 (tests/test_gpu_neus.py): sample sets exact, sdf 2e-3, per-ray colour 6e-3, gradients cosine >= 0.99 (0.98 with the
@@ -136,7 +136,7 @@ def test_c4_neus_dtu_matches_oracle(fused_mlps):
         cfg['texture']['fused_vanilla'] = cfg['texture_bg']['fused_vanilla'] = fused_mlps
         return cfg
 
-    model, cfg, binary, rays, jitter = build(cfg_fn, 256, 2)
+    model, cfg, binary, rays, jitter = build(cfg_fn, n_rays, 2)
     model.randomized = False                                                   # lattice / cone marching without jitter on both sides
     bgb = np.random.default_rng(0).random((256, 256, 256)) < 0.3
     model.occupancy_grid.set_binary(torch.from_numpy(binary))
@@ -171,7 +171,7 @@ def test_c4_neus_dtu_matches_oracle(fused_mlps):
     eik = ((torch.linalg.norm(ref['sdf_grad_samples'], ord=2, dim=-1) - 1.) ** 2).mean()
     (torch.nn.functional.l1_loss(ref['comp_rgb_full'], torch.full_like(ref['comp_rgb_full'], 0.5)) + 0.1 * eik).backward()
 
-    assert int(out['num_samples']) == len(ref['ray_indices']) > 3000 and torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
+    assert int(out['num_samples']) == len(ref['ray_indices']) > min_fg and torch.equal(out['ray_indices'].cpu(), ref['ray_indices'])
     assert abs(int(out['num_samples_bg']) - int(ref['num_samples_bg'])) <= 3 and int(ref['num_samples_bg']) > 100
     assert float((out['sdf_samples'].detach().cpu() - ref['sdf_samples'].detach()).abs().max()) <= 2e-3
     for k in ('comp_rgb', 'comp_rgb_bg', 'comp_rgb_full', 'opacity', 'opacity_bg'):
@@ -185,7 +185,6 @@ def test_c4_neus_dtu_matches_oracle(fused_mlps):
     assert abs(float(model.variance.variance.grad) - float(var.grad)) <= 3e-2 * abs(float(var.grad)) + 1e-6
 
 
-@experimental
 def test_nerf_colmap_unbounded_matches_oracle():
     """configs/nerf-colmap.yaml (unbounded NeRF: mip-360 sphere contraction, 256^3 occupancy grid, cone marching between near 0.2 and far 1e4)
     through the drop-in model's per-op path against oracle.models.nerf_unbounded_render (pinned to the reference's forward_ by

@@ -1,14 +1,13 @@
 """Vertex-colour export (models/neus.py:321-329, models/nerf.py:153-161) through the drop-in models on the GPU: isosurface by the GPU
 marching cubes, per-vertex features through the fused SDF field / colour kernels.  Every kernel on this path has its own parity test; the
 Python path (chunk_batch keyword arguments, eval-mode detaching, the texture call with the normal as view direction) was dry-run on the
-CPU with the oracle-backed stand-ins (tests/test_dryrun.py).  Not yet seen on a B200: NSR_EXPERIMENTAL=1 (tools/run_experimental.sh) runs it."""
+CPU with the oracle-backed stand-ins (tests/test_dryrun.py).  First seen green on a B200 in round 2 (profiles/r2_gputest_first.log)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NSR_EXPERIMENTAL', '') in ('', '0'), reason='not yet seen green on a B200: set NSR_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 D = torch.device('cuda:0')
 

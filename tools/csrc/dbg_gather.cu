@@ -1,6 +1,6 @@
 // Development micro-benchmark (not part of the product path): gather-only variants of the 16-level hash
 // encode, to pick the load strategy used by nf_gather.  positions [n,3] in [0,1] -> enc fp16 [n,32].
-#include "nerf_fused.cuh"
+#include "../../instant-nsr-pl_b200/csrc/nerf_fused.cuh"
 
 namespace {
 

@@ -5,6 +5,16 @@ import torch
 import bench
 from nsr_b200 import synthetic
 from nsr_b200.lib import lib, ptr, stream
+import ctypes
+
+_tools = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libnsr_tools.so'))   # python instant-nsr-pl_b200/build.py --tools
+
+
+def tools_call(name, *args):
+    conv = [a if not isinstance(a, int) else ctypes.c_int64(a) for a in args]
+    rc = getattr(_tools, name)(*conv)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed: {rc}')
 
 dev = torch.device('cuda:0')
 model = bench.build_model(dev)
@@ -31,7 +41,7 @@ ref = None
 for variant in (0,):
     for occ in (8,):
         def run():
-            lib.call('nsr_dbg_gather', f.grid.ref(), ptr(pos), ptr(table), ptr(out), n, variant, occ, stream())
+            tools_call('nsr_dbg_gather', f.grid.ref(), ptr(pos), ptr(table), ptr(out), n, ctypes.c_int(variant), ctypes.c_int(occ), stream())
         for _ in range(3):
             run()
         ts_ = []
@@ -56,7 +66,7 @@ grad = torch.zeros(f.grid.n_params, device=dev)
 sres = {'k': k}
 for variant in (0, 1, 2, 3, 4, 5):
     def run():
-        lib.call('nsr_dbg_scatter', f.grid.ref(), ptr(pos), ptr(denc), ptr(grad), k, variant, stream())
+        tools_call('nsr_dbg_scatter', f.grid.ref(), ptr(pos), ptr(denc), ptr(grad), k, ctypes.c_int(variant), stream())
     for _ in range(3):
         run()
     ts_ = []
