@@ -66,6 +66,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.out, self.loss = self._run()
         self.launches_per_replay = lib.launches - before  # our kernels inside the graph (torch's own nodes not counted)
+        fused = getattr(m, '_fused', None)   # the captured step's device-side sample counts (an eager forward later replaces last_stats)
+        self._counts = fused.last_stats.get('counts_dev') if fused is not None and isinstance(getattr(fused, 'last_stats', None), dict) else None
         torch.cuda.synchronize()
 
     def __call__(self, rays, background_color=None, **batch):
@@ -81,5 +83,7 @@ class GraphedStep:
 
     def counts(self):
         """(n_marched, n_kept) of the last replay -- one device->host read."""
-        c = self.model._fused.last_stats['counts_dev']
+        c = self._counts
+        if c is None:
+            raise RuntimeError('GraphedStep.counts(): the captured model exposes no device-side sample counts')
         return tuple((torch.cat(list(c)) if isinstance(c, (tuple, list)) else c).tolist())

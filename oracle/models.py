@@ -27,7 +27,7 @@ class NerfParams:
 
 def nerf_field(P, positions, dirs, radius, emulate_fp16=True, density_only=False, ctype=contraction.AABB):
     """VolumeDensity.forward + VolumeRadiance.forward (geometry.py:122-130, texture.py:23-30)."""
-    q = (lambda t: t.half().float()) if emulate_fp16 else (lambda t: t)
+    q = mlp.round_half if emulate_fp16 else (lambda t: t)   # values only: see oracle.mlp._RoundHalf
     x01 = contraction.contract_to_unisphere(positions, radius, ctype)
     table = P.density_flat[P.n_mlp:].view(-1, 2)
     table = q(table) if emulate_fp16 else table
@@ -168,7 +168,7 @@ class NeusParams:
 
 def neus_render(P, rays, binary, radius, step, bg_color, cos_anneal_ratio, jitter=None, emulate_fp16=True):
     """NeuSModel.forward_ without learned background (models/neus.py:205-287)."""
-    q = (lambda t: t.half().float()) if emulate_fp16 else (lambda t: t)
+    q = mlp.round_half if emulate_fp16 else (lambda t: t)   # values only: see oracle.mlp._RoundHalf
     rays = np.asarray(rays, np.float32)
     o, d = rays[:, :3], rays[:, 3:6]
     n_rays = len(rays)
@@ -222,7 +222,7 @@ class NeusBgParams:
 
 def neus_bg_field(P, positions, dirs, radius, emulate_fp16=True, density_only=False):
     """VolumeDensity (UN_BOUNDED_SPHERE contraction) + VolumeRadiance with VanillaMLPs (geometry.py:122-130, texture.py:23-30)"""
-    q = (lambda t: t.half().float()) if emulate_fp16 else (lambda t: t)
+    q = mlp.round_half if emulate_fp16 else (lambda t: t)   # values only: see oracle.mlp._RoundHalf
     x01 = contraction.contract_to_unisphere(positions, radius, contraction.UN_BOUNDED_SPHERE)
     table = P.table_flat.view(-1, 2)
     table = q(table) if emulate_fp16 else table

@@ -163,6 +163,91 @@ __global__ void __launch_bounds__(256) dbg_scatter_kernel(const __grid_constant_
   }
 }
 
+
+// ---- round 2: warp-wide run merging + paired 16-byte REDs, thread per sample (what the scatter warps of the tcgen05 backward do) -------
+// lanes = 32 consecutive samples (ray-major order); on levels < MERGE_LEVELS runs of equal cells are summed with a segmented shuffle
+// scan over the WHOLE warp (round 1 merged over 8 lanes) and only the run's last lane issues REDs; x-adjacent corners that are
+// neighbours in memory go out as one red.v4.f32.  PAIR = 0: 8-byte REDs only.
+template <int MERGE_LEVELS, int PAIR>
+__global__ void __launch_bounds__(256) dbg_scatter_merged_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ pos,
+                                                                 const __half2* __restrict__ denc, float* __restrict__ grad, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n32 = (n + 31) & ~31ll;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n32; i += (int64_t)gridDim.x * 256) {
+    const bool ok = i < n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (ok) {
+      x = pos[i * 3];
+      y = pos[i * 3 + 1];
+      z = pos[i * 3 + 2];
+    }
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) {
+      float2 d = make_float2(0.f, 0.f);
+      if (ok) d = __half22float2(denc[i * 16 + l]);
+      const LevelInfo li = nsr_level(g, l);
+      uint32_t cx, cy, cz, idx[8];
+      float fx, fy, fz;
+      nsr_pos_fract(x, li.scale, cx, fx);
+      nsr_pos_fract(y, li.scale, cy, fy);
+      nsr_pos_fract(z, li.scale, cz, fz);
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float w = nsr_corner_weight(c, fx, fy, fz);
+        v[2 * c] = w * d.x;
+        v[2 * c + 1] = w * d.y;
+      }
+      bool issue = ok;
+      if (l < MERGE_LEVELS) {
+        const uint32_t key = ok ? (cx + li.res * (cy + li.res * cz)) : (0xFFFFFF00u + lane);
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || prev != key;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // start lane of my run
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        // longest run in the warp bounds the number of scan steps (warp-uniform)
+        const int run_len = lane - my_head + 1;
+        int maxrun = run_len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxrun = max(maxrun, __shfl_xor_sync(0xffffffffu, maxrun, o));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          if (o < maxrun) {
+            const bool take = lane - o >= my_head;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float u = __shfl_up_sync(0xffffffffu, v[e], o);
+              if (take) v[e] += u;
+            }
+          }
+        }
+        issue = ok && tail;
+      }
+      if (issue) {
+        nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          if (PAIR)
+            nsr_red_corner_pair(grad, idx[c], idx[c + 1], v[2 * c], v[2 * c + 1], v[2 * c + 2], v[2 * c + 3]);
+          else {
+            nsr_red_add_f32x2(grad + 2 * (size_t)idx[c], v[2 * c], v[2 * c + 1]);
+            nsr_red_add_f32x2(grad + 2 * (size_t)idx[c + 1], v[2 * c + 2], v[2 * c + 3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int ML, int PAIR>
+int launch_scatter_merged(const nsr_grid_t* g, const float* pos, const void* denc, float* grad, int64_t n, int ctas_per_sm, cudaStream_t st) {
+  const int grid = (int)min((int64_t)nsr_sm_count() * ctas_per_sm, (n + 255) / 256);
+  dbg_scatter_merged_kernel<ML, PAIR><<<grid, 256, 0, st>>>(*g, pos, (const __half2*)denc, grad, n);
+  NSR_CHECK_LAUNCH("nsr_dbg_scatter_merged");
+  return 0;
+}
+
 template <int V>
 int launch_scatter(const nsr_grid_t* g, const float* pos, const void* denc, float* grad, int64_t n, cudaStream_t st) {
   const int64_t total = V >= 3 ? n * 16 : n;
@@ -186,4 +271,19 @@ extern "C" int nsr_dbg_scatter(const nsr_grid_t* g, const float* pos, const void
     case 5: return launch_scatter<5>(g, pos, denc_h, grad, n, st);
   }
   NSR_REQUIRE(false, "nsr_dbg_scatter: unknown variant %d", variant);
+}
+
+// variant = merge_levels * 2 + pair; ctas_per_sm x 256 threads resident per SM (occupancy sweep: how many scatter warps saturate the RED path)
+extern "C" int nsr_dbg_scatter_merged(const nsr_grid_t* g, const float* pos, const void* denc_h, float* grad, int64_t n, int merge_levels,
+                                      int pair, int ctas_per_sm, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define NSR_SM(ML)                                                                                   \
+  case ML:                                                                                           \
+    return pair ? launch_scatter_merged<ML, 1>(g, pos, denc_h, grad, n, ctas_per_sm, st)             \
+                : launch_scatter_merged<ML, 0>(g, pos, denc_h, grad, n, ctas_per_sm, st);
+  switch (merge_levels) {
+    NSR_SM(0) NSR_SM(6) NSR_SM(8) NSR_SM(10)
+  }
+#undef NSR_SM
+  NSR_REQUIRE(false, "nsr_dbg_scatter_merged: merge_levels must be 0, 6, 8 or 10 (got %d)", merge_levels);
 }

@@ -83,3 +83,25 @@ for variant in (0, 1, 2, 3, 4, 5):
         grad.zero_(); run(); torch.cuda.synchronize()
         assert (grad - ref_grad).abs().max().item() <= 1e-3 * ref_grad.abs().max().item(), 'v5 mismatch'
 print(json.dumps(sres))
+
+# ---- round 2: warp-wide run merging (+ paired 16-byte REDs), thread per sample, occupancy sweep
+mres = {'k': k}
+for ml in (0, 6, 8, 10):
+    for pair in (0, 1):
+        for occ in (2, 4, 8):
+            def run():
+                tools_call('nsr_dbg_scatter_merged', f.grid.ref(), ptr(pos), ptr(denc), ptr(grad), k, ctypes.c_int(ml), ctypes.c_int(pair), ctypes.c_int(occ), stream())
+            for _ in range(2):
+                run()
+            ts_ = []
+            for _ in range(7):
+                flush.fill_(0.0)
+                grad.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(); e1.record(); torch.cuda.synchronize()
+                ts_.append(e0.elapsed_time(e1))
+            mres[f'merge{ml}_pair{pair}_occ{occ}'] = round(sorted(ts_)[len(ts_) // 2] * 1e3, 1)
+            grad.zero_(); run(); torch.cuda.synchronize()
+            err = (grad - ref_grad).abs().max().item() / ref_grad.abs().max().item()
+            assert err <= 2e-3, (ml, pair, occ, err)
+print(json.dumps(mres))
