@@ -228,6 +228,22 @@ int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ra
                        const float* xyzdir /* optional f32 [k,6]: unit-cube position + view direction per row (nsr_pack_kept); then rays,
                                               ray_indices, t_starts, t_ends are not read and every load of a tile is independent */,
                        void* stream);
+/* the same backward as TWO launches over the packed inputs (enc_k / d_sraw / d_rgb / xyzdir in packed row order, nsr_pack_kept):
+ * (1) network half: recompute + dgrad + wgrad on tensor cores, d(encoding) -> denc_h (f16 [k,32] workspace, still multiplied by the loss
+ * scale); (2) table half: a high-occupancy scatter kernel over the same rows -- runs of consecutive samples that share a cell on the
+ * coarse levels are summed across the warp before one lane issues the REDs, and x-adjacent corners that are neighbours in memory
+ * leave as one 16-byte RED (autograd of tcnn's HashGrid, models/geometry.py:122-130).  Same results as nsr_nerf_field_bwd up to the fp16
+ * rounding of d(encoding) and the summation order. */
+/* Blackwell-native form of the same backward (csrc/nerf_bwd_tc.cu): tcgen05.mma with the accumulators in tensor memory, tile inputs
+ * staged by cp.async.bulk (TMA) + mbarrier, warp-specialised producer / MMA issuer / epilogue / scatter roles, weight gradients kept in
+ * TMEM for the whole kernel.  enc_tiles_h = nsr_pack_kept(..., enc_tiled = 1); xyzdir / d_sraw / d_rgb in packed row order; all four
+ * buffers readable up to the end of the last 128-row tile.  status (device int, may be NULL): non-zero if a barrier wait timed out. */
+int nsr_nerf_field_bwd_tc(const nsr_nerf_t* f, const void* enc_tiles_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
+                          const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
+                          const int64_t* k_dev, const float* xyzdir, int* status, void* stream);
+int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
+                             const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
+                             const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream);
 
 /* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
  * nsr_nerf_rays_fwd: masks (nsr_march_rays_mask) -> per-ray colour in ONE kernel: a warp owns a ray (atomic ticket queue),
@@ -246,14 +262,16 @@ int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const floa
                   int64_t* loose_pos /* packed row -> loose position, may be NULL */,
                   const nsr_nerf_t* f, const float* rays, const void* enc_loose_h /* inputs of the optional outputs below */,
                   void* enc_k_h /* fp16 [K,32] packed copy of the saved encodings, may be NULL */,
-                  float* xyzdir_k /* f32 [K,6] unit-cube position + view direction per packed row, may be NULL */, int64_t n_rays,
-                  void* stream);
+                  float* xyzdir_k /* f32 [K,6] unit-cube position + view direction per packed row, may be NULL */,
+                  int32_t enc_tiled /* 0: enc_k row-major [K,32]; 1: canonical UMMA tiles of 128 rows (8 KB each; chunk (r, kc) at
+                                       ((r/8)*4 + kc)*128 + (r%8)*16 bytes) for nsr_nerf_field_bwd_tc -- enc_k then needs ceil(K/128)*128 rows */,
+                  int64_t n_rays, void* stream);
 /* nsr_scan_counts(kept) + nsr_pack_kept in one launch: every CTA derives its packed base offset from the kept counts in front of it and
  * writes offsets_k_out [n_rays + 1] for the kernels behind (nsr_nerf_ray_bwd_loose, nsr_nerf_field_bwd's k_dev = offsets_k_out + n_rays). */
 int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
                        const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
                        float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h, void* enc_k_h,
-                       float* xyzdir_k, int64_t n_rays, void* stream);
+                       float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, void* stream);
 /* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min); offsets_k != NULL
  * writes d_sraw / d_rgb in packed row order (row offsets_k[ray] + j) instead of the loose positions. */
 int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx, const float* trans,

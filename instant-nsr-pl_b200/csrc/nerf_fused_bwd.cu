@@ -82,7 +82,9 @@ __device__ __forceinline__ void relu_mask_pack(const float (&acc)[1][8][4], cons
 // every row (written by nsr_pack_kept; buffers padded by one tile).  All global inputs of tile t+1 are then fetched with cp.async
 // into the second smem buffer while tile t computes: no load of the kernel sits in front of the math any more (ncu before:
 // 37 % of the stall samples were long-scoreboard waits on the row_pos -> enc / ray_indices -> rays chains and on the tile's loads).
-template <bool PACKED>
+// SCATTER = false (split backward, nsr_nerf_field_bwd_split): d(encoding) leaves the kernel as fp16 pairs [n][16 levels] (still multiplied by
+// the loss scale) and a second, high-occupancy kernel (nerf_table_scatter_kernel) turns it into table REDs with warp-wide run merging.
+template <bool PACKED, bool SCATTER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __grid_constant__ nsr_nerf_t P, const float* __restrict__ rays,
                                                                const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                                                                const float* __restrict__ t_ends, const __half* __restrict__ enc_save,
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
                                                                const float* __restrict__ d_sraw, const float* __restrict__ d_rgb,
                                                                float* __restrict__ grad_dparams, float* __restrict__ grad_cparams,
                                                                float loss_scale, const float* __restrict__ amax_ptr, int64_t n_cap, const int64_t* __restrict__ n_dev,
-                                                               const int64_t* __restrict__ row_pos, const float* __restrict__ xyzdir) {
+                                                               const int64_t* __restrict__ row_pos, const float* __restrict__ xyzdir, uint32_t* __restrict__ denc_out) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   extern __shared__ __align__(16) __half smem[];
   __half* T = smem + NF_W_TOTAL;
@@ -276,8 +278,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
     // Levels 0..7 (nt < 2): consecutive samples of a ray stay in one cell for several steps, so the 8 lanes that hold the
     // same level for 8 consecutive samples first merge runs of equal cells with a segmented shuffle scan and only the
     // last lane of each run issues the 8 REDs (-40 % REDs overall, far less same-address contention in L2).
+    if (!SCATTER) {  // split backward: 4 lanes (c = 0..3) x 4-byte stores = 16 contiguous bytes per (row, nt)
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < 2; ++hh) {
+        const int64_t i = hh ? ib : ia;
+        if (i < n) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) denc_out[i * 16 + nt * 4 + c] = nsr_pack_h2(accE[0][nt][hh * 2], accE[0][nt][hh * 2 + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < (SCATTER ? 2 : 0); ++hh) {
       const int64_t i = hh ? ib : ia;
       const bool ok = i < n;
       float x = 0.f, y = 0.f, z = 0.f, dx, dy, dz;
@@ -369,23 +381,108 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) nerf_bwd_kernel(const __
 
 }  // namespace
 
-extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
-                                  const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
-                                  const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
-                                  const float* amax, int64_t k, const int64_t* k_dev, const int64_t* row_pos, const float* xyzdir,
-                                  void* stream) {
-  NSR_REQUIRE(f != nullptr, "nsr_nerf_field_bwd: field descriptor is NULL");
+namespace {
+
+// Table half of the split backward: rows = kept samples in packed (ray-major) order, thread per row, a warp = 32 consecutive rows.
+// Per level: corner weights x d(feature pair); on levels < kMergeLevels runs of rows that sit in the same cell (consecutive samples of
+// a ray on the coarse levels) are summed with a segmented shuffle scan over the whole warp and only the run's last lane issues REDs;
+// x-adjacent corners that are neighbours in memory (hashed levels: cell x even; dense levels: entry index even) leave as ONE 16-byte
+// red.global.add.v4.f32.  48 registers, no shared memory: 64 warps per SM keep the RED path of the SM full (tools/gather_bench.py,
+// profiles/r2_scatter_microbench.md: 92 us for 267 k samples against 264 us for the plain 8-byte form).
+constexpr int kMergeLevels = 8;
+
+__global__ void __launch_bounds__(256) nerf_table_scatter_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ xyz, int stride,
+                                                                 const __half2* __restrict__ denc, float loss_scale,
+                                                                 const float* __restrict__ amax_ptr, float* __restrict__ grad_table,
+                                                                 int64_t n_cap, const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  if (loss_scale <= 0.f) {  // the same automatic scale as nerf_bwd_kernel derives from the same amax
+    const float amax = fmaxf(__ldg(amax_ptr), 1e-30f);
+    loss_scale = exp2f(fminf(fmaxf(floorf(log2f(256.f / amax)), -24.f), 60.f));
+  }
+  const float inv_scale = 1.f / loss_scale;
+  const int lane = threadIdx.x & 31;
+  const int64_t n32 = (n + 31) & ~31ll;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n32; i += (int64_t)gridDim.x * 256) {
+    const bool ok = i < n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (ok) {
+      x = xyz[i * stride];
+      y = xyz[i * stride + 1];
+      z = xyz[i * stride + 2];
+    }
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) {
+      float2 d = make_float2(0.f, 0.f);
+      if (ok) {
+        d = __half22float2(denc[i * 16 + l]);
+        d.x *= inv_scale;
+        d.y *= inv_scale;
+      }
+      const LevelInfo li = nsr_level(g, l);
+      uint32_t cx, cy, cz, idx[8];
+      float fx, fy, fz;
+      nsr_pos_fract(x, li.scale, cx, fx);
+      nsr_pos_fract(y, li.scale, cy, fy);
+      nsr_pos_fract(z, li.scale, cz, fz);
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float w = nsr_corner_weight(c, fx, fy, fz);
+        v[2 * c] = w * d.x;
+        v[2 * c + 1] = w * d.y;
+      }
+      bool issue = ok && (d.x != 0.f || d.y != 0.f);
+      if (l < kMergeLevels) {  // res^3 < 2^32 on these levels (base 16 .. 32, growth <= 1.45): the cell index is a unique key
+        const uint32_t key = ok ? (cx + li.res * (cy + li.res * cz)) : (0xFFFFFF00u + lane);
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || prev != key;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // first lane of my run
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        int maxrun = lane - my_head + 1;  // the longest run of the warp bounds the number of scan steps (warp-uniform)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxrun = max(maxrun, __shfl_xor_sync(0xffffffffu, maxrun, o));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          if (o < maxrun) {
+            const bool take = lane - o >= my_head;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float u = __shfl_up_sync(0xffffffffu, v[e], o);
+              if (take) v[e] += u;
+            }
+          }
+        }
+        issue = ok && tail;
+      }
+      if (issue) {
+        nsr_corner_indices(li, cx, cy, cz, idx);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) nsr_red_corner_pair(grad_table, idx[c], idx[c + 1], v[2 * c], v[2 * c + 1], v[2 * c + 2], v[2 * c + 3]);
+      }
+    }
+  }
+}
+
+int field_bwd_launch(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                     const void* enc_save_h, const void* dparams_h, const void* cparams_h, const float* d_sraw, const float* d_rgb,
+                     float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k, const int64_t* k_dev,
+                     const int64_t* row_pos, const float* xyzdir, void* denc_out, void* stream, const char* who) {
+  NSR_REQUIRE(f != nullptr, "%s: field descriptor is NULL", who);
   NSR_REQUIRE(f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 && f->color_hidden == 2,
-              "nsr_nerf_field_bwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
-  NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_nerf_field_bwd: loss_scale <= 0 (automatic) needs the amax pointer");
+              "%s: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2", who);
+  NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "%s: loss_scale <= 0 (automatic) needs the amax pointer", who);
   if (k == 0) return 0;
-  NSR_REQUIRE(xyzdir == nullptr || row_pos == nullptr, "nsr_nerf_field_bwd: packed inputs (xyzdir) and row_pos are mutually exclusive");
+  NSR_REQUIRE(xyzdir == nullptr || row_pos == nullptr, "%s: packed inputs (xyzdir) and row_pos are mutually exclusive", who);
+  NSR_REQUIRE(denc_out == nullptr || xyzdir != nullptr, "%s: the split form needs the packed inputs (xyzdir)", who);
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nerf_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(nerf_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
-      nsr_set_error("nsr_nerf_field_bwd: cannot reserve %zu B shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+      nsr_set_error("%s: cannot reserve %zu B shared memory: %s", who, kSmemBytes, cudaGetErrorString(e));
       return 2;
     }
     attr_set = true;
@@ -393,14 +490,43 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
   const int64_t tiles = (k + kRows - 1) / kRows;
   int grid = (int)min((int64_t)nsr_sm_count() * kCtasPerSm, tiles);
   if (k_dev != nullptr) grid = nsr_sm_count() * kCtasPerSm;
-  if (xyzdir != nullptr)
-    nerf_bwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
-                                                                                (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                                grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
+#define NSR_BWD_ARGS                                                                                                                        \
+  *f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h, (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,    \
+      grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir, (uint32_t*)denc_out
+  if (denc_out != nullptr)
+    nerf_bwd_kernel<true, false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(NSR_BWD_ARGS);
+  else if (xyzdir != nullptr)
+    nerf_bwd_kernel<true, true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(NSR_BWD_ARGS);
   else
-    nerf_bwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, rays, ray_indices, t_starts, t_ends, (const __half*)enc_save_h,
-                                                                                 (const __half*)dparams_h, (const __half*)cparams_h, d_sraw, d_rgb,
-                                                                                 grad_dparams, grad_cparams, loss_scale, amax, k, k_dev, row_pos, xyzdir);
-  NSR_CHECK_LAUNCH("nsr_nerf_field_bwd");
+    nerf_bwd_kernel<false, true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(NSR_BWD_ARGS);
+#undef NSR_BWD_ARGS
+  NSR_CHECK_LAUNCH(who);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const int32_t* ray_indices, const float* t_starts,
+                                  const float* t_ends, const void* enc_save_h, const void* dparams_h, const void* cparams_h,
+                                  const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
+                                  const float* amax, int64_t k, const int64_t* k_dev, const int64_t* row_pos, const float* xyzdir,
+                                  void* stream) {
+  return field_bwd_launch(f, rays, ray_indices, t_starts, t_ends, enc_save_h, dparams_h, cparams_h, d_sraw, d_rgb, grad_dparams, grad_cparams,
+                          loss_scale, amax, k, k_dev, row_pos, xyzdir, nullptr, stream, "nsr_nerf_field_bwd");
+}
+
+// Split form of the same backward (packed inputs only): kernel 1 = MLP recompute + dgrad + wgrad, d(encoding) -> denc_h (fp16 [k,32],
+// still multiplied by the loss scale); kernel 2 = nerf_table_scatter_kernel over the same rows (grad_dparams + NF_DENSITY_PARAMS).
+extern "C" int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h,
+                                        const float* d_sraw, const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale,
+                                        const float* amax, int64_t k, const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream) {
+  NSR_REQUIRE(denc_h != nullptr && xyzdir != nullptr, "nsr_nerf_field_bwd_split: denc / xyzdir is NULL");
+  const int rc = field_bwd_launch(f, nullptr, nullptr, nullptr, nullptr, enc_k_h, dparams_h, cparams_h, d_sraw, d_rgb, grad_dparams, grad_cparams,
+                                  loss_scale, amax, k, k_dev, nullptr, xyzdir, denc_h, stream, "nsr_nerf_field_bwd_split");
+  if (rc != 0 || k == 0) return rc;
+  const int grid = (int)min((int64_t)nsr_sm_count() * 8, (k + 255) / 256);
+  nerf_table_scatter_kernel<<<k_dev ? nsr_sm_count() * 8 : grid, 256, 0, (cudaStream_t)stream>>>(f->grid, xyzdir, 6, (const __half2*)denc_h, loss_scale, amax,
+                                                                                                 grad_dparams + NF_DENSITY_PARAMS, k, k_dev);
+  NSR_CHECK_LAUNCH("nsr_nerf_field_bwd_split (scatter)");
   return 0;
 }

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
                                                         float* __restrict__ ts_k, float* __restrict__ te_k, float* __restrict__ w_k,
                                                         int64_t* __restrict__ loose_pos, const __grid_constant__ nsr_nerf_t P,
                                                         const float* __restrict__ rays, const uint4* __restrict__ enc_loose,
-                                                        uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int64_t n_rays) {
+                                                        uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int enc_tiled, int64_t n_rays) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
   int64_t dst, cnt;
@@ -317,8 +317,16 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
       o[0] = x; o[1] = y; o[2] = z; o[3] = dx; o[4] = dy; o[5] = dz;
     }
   }
-  if (enc_k) {  // 64 B rows: 4 lanes per row => every warp iteration moves 8 whole rows with fully used sectors
+  if (enc_k && !enc_tiled) {  // 64 B rows: 4 lanes per row => every warp iteration moves 8 whole rows with fully used sectors
     for (int64_t v = lane; v < cnt * 4; v += 32) enc_k[dst * 4 + v] = enc_loose[src * 4 + v];
+  } else if (enc_k) {
+    // canonical UMMA tile layout for the tcgen05 backward (csrc/nerf_bwd_tc.cu): packed row R lives in tile R / 128 (8 KB each); inside a
+    // tile the 16-byte chunk (row r, k chunk kc) sits at ((r / 8) * 4 + kc) * 128 + (r % 8) * 16 bytes -- ONE cp.async.bulk then fetches a tile
+    for (int64_t v = lane; v < cnt * 4; v += 32) {
+      const int64_t R = dst + (v >> 2);
+      const int kc = (int)(v & 3), r = (int)(R & 127);
+      enc_k[(R >> 7) * 512 + ((r >> 3) * 4 + kc) * 8 + (r & 7)] = enc_loose[src * 4 + v];
+    }
   }
 }
 
@@ -426,7 +434,7 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
 extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                              const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k,
                              int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h, void* enc_k_h,
-                             float* xyzdir_k, int64_t n_rays, void* stream) {
+                             float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, void* stream) {
   if (n_rays == 0) return 0;
   NSR_REQUIRE(xyzdir_k == nullptr || (f != nullptr && rays != nullptr), "nsr_pack_kept: xyzdir_k needs the field descriptor and the rays");
   NSR_REQUIRE(enc_k_h == nullptr || enc_loose_h != nullptr, "nsr_pack_kept: enc_k needs the loose encoding buffer");
@@ -436,7 +444,7 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
   pack_kept_kernel<false><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, nullptr, nullptr, t_min, step, kidx, weights,
                                                                                    ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
                                                                                    f ? *f : dummy, rays, (const uint4*)enc_loose_h,
-                                                                                   (uint4*)enc_k_h, xyzdir_k, n_rays);
+                                                                                   (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays);
   NSR_CHECK_LAUNCH("nsr_pack_kept");
   return 0;
 }
@@ -444,7 +452,7 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
 extern "C" int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
                                   const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
                                   float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h,
-                                  void* enc_k_h, float* xyzdir_k, int64_t n_rays, void* stream) {
+                                  void* enc_k_h, float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, void* stream) {
   NSR_REQUIRE(kept != nullptr && offsets_k_out != nullptr, "nsr_pack_kept_scan: kept / offsets_k_out is NULL");
   if (n_rays == 0) {
     cudaMemsetAsync(offsets_k_out, 0, sizeof(int64_t), (cudaStream_t)stream);
@@ -458,7 +466,7 @@ extern "C" int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept,
   pack_kept_kernel<true><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, nullptr, kept, offsets_k_out, t_min, step, kidx, weights,
                                                                                   ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
                                                                                   f ? *f : dummy, rays, (const uint4*)enc_loose_h,
-                                                                                  (uint4*)enc_k_h, xyzdir_k, n_rays);
+                                                                                  (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays);
   NSR_CHECK_LAUNCH("nsr_pack_kept_scan");
   return 0;
 }

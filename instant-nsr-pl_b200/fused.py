@@ -111,16 +111,18 @@ class _NerfRenderRays(torch.autograd.Function):
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
         # plus (training, tile backward) the backward's inputs in packed row order: encodings, unit-cube position + view direction
         ri, ts, te, pos = i32(cap), f32(cap), f32(cap), i64(cap)
-        packed_bwd = need_grad and fused.bwd_kernel == 'tiles' and fused.packed_bwd_inputs
-        # (+64 rows: the tile backward prefetches whole 64-row tiles with cp.async, the last one may reach past K)
-        enc_k = torch.empty(cap + 64, 32, dtype=torch.float16, device=dev) if packed_bwd else None
-        xyzdir = f32(cap + 64, 6) if packed_bwd else None
+        packed_bwd = need_grad and fused.bwd_kernel in ('tiles', 'tiles_split', 'tc') and fused.packed_bwd_inputs
+        tiled = 1 if fused.bwd_kernel == 'tc' else 0   # tcgen05 backward: encodings in canonical 128-row UMMA tiles (one TMA bulk copy per tile)
+        # (+pad rows: the tile backwards prefetch whole tiles -- 64 rows with cp.async, 128 rows with cp.async.bulk -- the last one may reach past K)
+        pad = 256 - cap % 128 if tiled else 64
+        enc_k = torch.empty(cap + pad, 32, dtype=torch.float16, device=dev) if packed_bwd else None
+        xyzdir = f32(cap + pad, 6) if packed_bwd else None
         if fused.fuse_kept_scan:   # the packed offsets are computed inside the pack kernel (one launch and a one-CTA scan less)
             lib.call('nsr_pack_kept_scan', ptr(offsets_m), ptr(kept), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts),
-                     ptr(te), None, ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
+                     ptr(te), None, ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), tiled, n, stream())
         else:
             lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
-                     ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), n, stream())
+                     ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), tiled, n, stream())
         ctx.fused, ctx.n_rays, ctx.cap = fused, n, cap
         ctx.set_materialize_grads(False)
         if packed_bwd:
@@ -149,14 +151,27 @@ class _NerfRenderRays(torch.autograd.Function):
                          ptr(f32(g_w)), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), float(fused.t_bound), ptr(tick), n, stream())
             else:
                 packed = enc_k is not None
-                d_sraw = torch.empty(cap + 64, device=dev)
-                d_rgb = torch.empty(cap + 64, 3, device=dev)   # gradients + encodings in packed row order: no index chains in front of the tile math
+                pad = 256 - cap % 128 if fused.bwd_kernel == 'tc' else 64
+                d_sraw = torch.empty(cap + pad, device=dev)
+                d_rgb = torch.empty(cap + pad, 3, device=dev)   # gradients + encodings in packed row order: no index chains in front of the tile math
                 lib.call('nsr_nerf_ray_bwd_loose', ptr(offsets_m), ptr(kept), ptr(t_min), step, ptr(kidx), ptr(trans), ptr(weights), ptr(sig),
                          ptr(rgbs), ptr(f32(g_rgb)), ptr(f32(g_op)), ptr(f32(g_depth)), ptr(f32(g_w)), ptr(d_sraw), ptr(d_rgb), ptr(amax),
                          ptr(offsets_k) if packed else None, n, stream())
-                lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc_k if packed else enc), ptr(dh), ptr(ch),
-                         ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]),
-                         None if packed else ptr(pos), ptr(xyzdir), stream())
+                if packed and fused.bwd_kernel == 'tc':
+                    # Blackwell-native backward: tcgen05 GEMM chain + TMA-staged tiles + scatter warps in one kernel (csrc/nerf_bwd_tc.cu)
+                    if fused._tc_status is None or fused._tc_status.device != dev:
+                        fused._tc_status = torch.zeros(1, dtype=torch.int32, device=dev)
+                    lib.call('nsr_nerf_field_bwd_tc', fused.ref(), ptr(enc_k), ptr(dh), ptr(ch), ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc),
+                             float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(xyzdir), ptr(fused._tc_status), stream())
+                elif packed and fused.bwd_kernel == 'tiles_split':
+                    # network half + table half as two launches: the REDs come from a kernel with 64 light warps per SM (csrc/nerf_fused_bwd.cu)
+                    denc = torch.empty(cap, 32, dtype=torch.float16, device=dev)
+                    lib.call('nsr_nerf_field_bwd_split', fused.ref(), ptr(enc_k), ptr(dh), ptr(ch), ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc),
+                             float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(xyzdir), ptr(denc), stream())
+                else:
+                    lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc_k if packed else enc), ptr(dh), ptr(ch),
+                             ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]),
+                             None if packed else ptr(pos), ptr(xyzdir), stream())
         return gd, gc, None, None, None
 
 
@@ -189,7 +204,11 @@ class NerfFused:
         self.packed_bwd_inputs = True   # tile backward reads its inputs in packed row order (written by nsr_pack_kept)
         from .config import experimental
         self.fuse_kept_scan = experimental('pack_scan')   # nsr_pack_kept_scan instead of nsr_scan_counts + nsr_pack_kept (not yet timed)
-        self.bwd_kernel = 'tiles'  # 'tiles' (sample-tile backward through the packed->loose index) | 'rays' (single per-ray backward kernel)
+        # 'tiles' (one sample-tile backward kernel, REDs from the MMA warps) | 'tiles_split' (network half + high-occupancy table scatter) |
+        # 'rays' (single per-ray backward kernel)
+        import os
+        self.bwd_kernel = os.environ.get('NSR_BWD_KERNEL', 'tiles')
+        self._tc_status = None
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 
     @staticmethod

@@ -89,8 +89,8 @@ _SIGNATURES = {
     'nsr_scan_counts_order': [P, P, P, I64, P],
     'nsr_march_rays_expand': [P, P, I32, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_fwd': [P, P, P, I32, P, P, P, F32, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_pack_kept': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
-    'nsr_pack_kept_scan': [P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
+    'nsr_pack_kept': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I32, I64, P],
+    'nsr_pack_kept_scan': [P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I32, I64, P],
     'nsr_nerf_ray_bwd_loose': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P, F32, P, I64, P],
     'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P, P],
@@ -125,6 +125,8 @@ _SIGNATURES = {
     'nsr_nerf_render_fwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P],
     'nsr_nerf_ray_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_field_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
+    'nsr_nerf_field_bwd_split': [P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
+    'nsr_nerf_field_bwd_tc': [P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
 }
 
 
@@ -182,7 +184,7 @@ lib = _Lib()
 
 
 # entry points that launch more than one kernel (lib.launches counts kernels, not calls)
-_KERNELS_PER_CALL = {'nsr_nerf_loss_fwd': 2, 'nsr_neus_loss_fwd': 2, 'nsr_occgrid_update': 2, 'nsr_mc_count': 2, 'nsr_mc_emit': 2}
+_KERNELS_PER_CALL = {'nsr_nerf_field_bwd_split': 2, 'nsr_nerf_loss_fwd': 2, 'nsr_neus_loss_fwd': 2, 'nsr_occgrid_update': 2, 'nsr_mc_count': 2, 'nsr_mc_emit': 2}
 
 
 def register_signatures(sigs):

@@ -380,7 +380,8 @@ def test_product_never_imports_the_oracle_or_reads_the_reference():
         assert '/root/reference' not in text, path
     bench = open(os.path.join(ROOT, 'bench.py')).read()
     assert not re.search(r'^(from|import)\s+oracle\b', bench, flags=re.M)          # no module-level import: only inside cpu_workload()
-    assert len(re.findall(r'^\s+from oracle import', bench, flags=re.M)) == 1 and 'def cpu_workload' in bench
+    # exactly the two CPU-baseline legs import it, function-locally: cpu_workload() (C2 port) and time_cpu_c1() (BASELINE config 1)
+    assert len(re.findall(r'^\s+from oracle import', bench, flags=re.M)) == 2 and 'def cpu_workload' in bench and 'def time_cpu_c1' in bench
     entry = open(os.path.join(ROOT, '__graft_entry__.py')).read()
     assert entry.index('from oracle import') > entry.index('def smoke()')
 

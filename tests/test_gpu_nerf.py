@@ -29,7 +29,7 @@ def build(fused, n_rays=600, seed=0, peak=10.0):
     if fused:
         mode = fused if isinstance(fused, str) else 'per_ray'
         model._fused.mode = 'two_pass' if mode == 'two_pass' else 'per_ray'
-        model._fused.bwd_kernel = 'rays' if mode == 'per_ray_bwd' else 'tiles'
+        model._fused.bwd_kernel = {'per_ray_bwd': 'rays', 'per_ray_split': 'tiles_split', 'per_ray_tc': 'tc'}.get(mode, 'tiles')
     net = model.geometry.encoding_with_network
     g = torch.Generator().manual_seed(7)
     with torch.no_grad():
@@ -60,18 +60,21 @@ def oracle_run(model, binary, rays, jitter, bg, target):
     return out, loss, dflat.grad, cflat.grad
 
 
-@pytest.mark.parametrize('fused', ['per_ray', 'per_ray_bwd', 'two_pass', False])
+@pytest.mark.parametrize('fused', ['per_ray', 'per_ray_split', 'per_ray_tc', 'per_ray_bwd', 'two_pass', False])
 def test_nerf_model_forward_backward_parity(fused):
-    """per_ray: per-ray forward kernel + tile backward (default); per_ray_bwd: per-ray forward AND backward kernels;
+    """per_ray: per-ray forward kernel + tile backward; per_ray_split: the tile backward as network half + table-scatter half;
+    per_ray_tc: the tcgen05 / TMA backward (csrc/nerf_bwd_tc.cu);
+    per_ray_bwd: per-ray forward AND backward kernels;
     two_pass: pre-pass + sample-tile kernels; False: per-op composition"""
     check_parity(fused, 600)
 
 
-def test_nerf_full_size_c2_8192_rays_parity():
+@pytest.mark.parametrize('fused', ['per_ray', 'per_ray_split', 'per_ray_tc'])
+def test_nerf_full_size_c2_8192_rays_parity(fused):
     """BASELINE.json config 2 at its full size (8192 rays, ~440 k marched / ~270 k kept samples: the bench workload's density peak): the
     persistent per-ray kernel's longest-first ticket order, the 64-word lattice masks and the tile backward's grid-stride loop are only
     exercised at this size.  Same tolerances as the 600-ray cases."""
-    check_parity('per_ray', 8192, seed=11, peak=None, min_marched=300000)
+    check_parity(fused, 8192, seed=11, peak=None, min_marched=300000)
 
 
 def check_parity(fused, n_rays, seed=0, peak=10.0, min_marched=10000):
