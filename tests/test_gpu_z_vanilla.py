@@ -2,9 +2,14 @@
 [feature | SH4 | normal] -> 64 -> 64 -> 3, all nn.Linear WITH biases, fp32) through the C ABI: nsr_mlp_vanilla_fwd/_bwd and
 nsr_radiance_vanilla_fwd/_bwd.
 
-Checker: oracle.mlp.VanillaMLP (the reference's own fp32 arithmetic, pinned by tests/test_oracle_golden.py) + oracle.sh on the CPU, fp64
-autograd for the gradients.  Tolerances (fp16 tensor-core operands with fp32 accumulation against fp32 GEMMs): outputs 2e-2 relative to the
-largest output (measured error is ~1e-3); weight / bias gradients (sums over all rows) cosine >= 0.999 and 3e-2 of the largest entry;
+Checker: oracle.mlp.VanillaMLP (the reference's own fp32 arithmetic, pinned by tests/test_oracle_golden.py) + oracle.sh on the CPU, fp32
+autograd for the gradients, evaluated twice: exactly (the reference's numbers) and with the kernels' operand rounding emulated
+(`_emulated`: inputs, weights and hidden activations rounded to fp16, fp32 accumulation starting from the fp32 bias -- same layers, same
+parameters).  Tolerances (fp16 tensor-core operands with fp32 accumulation against fp32 GEMMs): outputs 2e-2 relative to the
+largest output (measured error is ~1e-3); weight / bias gradients (sums over all rows) cosine >= 0.999 against the exact oracle and within
+1.5e-2 of the largest entry of the EMULATED oracle (against the exact one the max-abs form measures ReLU-mask flips, not arithmetic: with
+random inputs a weight gradient is a random-sign sum over ~4 k rows, ~0.04 % of the hidden units change sign under fp16 rounding and each
+flip moves an entry by ~1/64 of its magnitude: seen on B200 as cosine 0.9997 with max error 3-5 % of the largest entry);
 per-row INPUT gradients cosine >= 0.999 (measured on B200: 0.9996 - 0.99998) with 99 % of the entries within 3e-2 of the largest entry
 and every entry within 1.0 of it (the measured quantiles are printed).  The input-gradient tail is ReLU masks: rounding the operands to fp16 flips the sign of a
 pre-activation that sits within ~5e-4 of zero for about one hidden unit in a thousand, and a flipped unit changes that row's gradient by
@@ -42,6 +47,31 @@ def close_rows(a, b, rel, frac=0.99, worst=1.0):
     print(f'input-gradient error / max|ref|: q50 {float(torch.quantile(err, 0.5)) / top:.2e} q99 {float(torch.quantile(err, 0.99)) / top:.2e} '
           f'q99.9 {float(torch.quantile(err, 0.999)) / top:.2e} max {float(err.max()) / top:.2e}')
     return float(torch.quantile(err, frac)) <= rel * top + 1e-12 and float(err.max()) <= worst * top + 1e-12
+
+
+def _emulated(ref, x):
+    """ref (oracle VanillaMLP) evaluated with the fused kernels' operand precision: A and B operands of every layer rounded to fp16
+    (values only, identity backward), products accumulated in fp32 on top of the fp32 bias, ReLU in fp32."""
+    h = x
+    for m in ref.layers:
+        if hasattr(m, 'bias'):
+            W = torch._weight_norm(m.weight_v, m.weight_g, 0) if hasattr(m, 'weight_g') else m.weight
+            h = omlp.round_half(h) @ omlp.round_half(W).t() + m.bias
+        else:
+            h = torch.relu(h)
+    return ref.output_activation(h)
+
+
+def _grads_emulated(ref, x, go, post=lambda t: t):
+    """parameter gradients of sum(post(_emulated(ref, x)) * go) by name; leaves ref's .grad as it found them"""
+    saved = {n: p.grad for n, p in ref.named_parameters()}
+    for p in ref.parameters():
+        p.grad = None
+    (post(_emulated(ref, x)) * go).sum().backward()
+    out = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in ref.named_parameters():
+        p.grad = saved[n]
+    return out
 
 
 def _oracle_mlp(n_in, n_out, n_hidden, weight_norm, seed):
@@ -84,9 +114,10 @@ def test_vanilla_mlp_matches_oracle_forward_and_backward(n_in, n_out, n_hidden, 
     assert close(y.detach(), y64.detach(), 2e-2)
     assert cos(xd.grad, x64.grad) > 0.999 and close_rows(xd.grad.float(), x64.grad, 3e-2)
     ref_grads = dict(ref.named_parameters())
+    emu_grads = _grads_emulated(ref, x.clone(), go)
     for name, p in net.named_parameters():
         gr = ref_grads[name].grad
-        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, gr, 3e-2), name
+        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 1.5e-2), name
     assert net(xd[:0].detach()).shape == (0, n_out)
     # fused=False pins the torch layers: same numbers to fp16-operand accuracy
     net_t = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=n_hidden, output_activation='none', weight_norm=weight_norm, fused=False))
@@ -130,9 +161,11 @@ def test_vanilla_radiance_matches_oracle_forward_and_backward(n_feat, n_extra, c
     if n_extra:
         assert cos(ed[0].grad, e64.grad) > 0.999
     ref_grads = dict(ref.named_parameters())
+    emu_grads = _grads_emulated(ref, torch.cat([feat, emb.detach()] + ([extra] if n_extra else []), dim=-1), go,
+                                post=torch.sigmoid if color_act else (lambda t: t))
     for name, p in tex.network.named_parameters():
         gr = ref_grads[name].grad
-        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, gr, 3e-2), name
+        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 1.5e-2), name
     assert tex(fd[:0].detach(), dirs[:0].to(D), *[x[:0].detach() for x in ed]).shape == (0, 3)
 
 
