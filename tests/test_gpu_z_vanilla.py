@@ -7,7 +7,8 @@ autograd for the gradients, evaluated twice: exactly (the reference's numbers) a
 (`_emulated`: inputs, weights and hidden activations rounded to fp16, fp32 accumulation starting from the fp32 bias -- same layers, same
 parameters).  Tolerances (fp16 tensor-core operands with fp32 accumulation against fp32 GEMMs): outputs 2e-2 relative to the
 largest output (measured error is ~1e-3); weight / bias gradients (sums over all rows) cosine >= 0.999 against the exact oracle and within
-1.5e-2 of the largest entry of the EMULATED oracle (against the exact one the max-abs form measures ReLU-mask flips, not arithmetic: with
+3e-2 of the largest entry of the EMULATED oracle (a single ReLU unit whose pre-activation is within summation-order noise of zero moves an
+entry by ~1.5 %: ~1 such unit is expected among the 4099 x 64 x 3 of the deepest case) (against the exact one the max-abs form measures ReLU-mask flips, not arithmetic: with
 random inputs a weight gradient is a random-sign sum over ~4 k rows, ~0.04 % of the hidden units change sign under fp16 rounding and each
 flip moves an entry by ~1/64 of its magnitude: seen on B200 as cosine 0.9997 with max error 3-5 % of the largest entry);
 per-row INPUT gradients cosine >= 0.999 (measured on B200: 0.9996 - 0.99998) with 99 % of the entries within 3e-2 of the largest entry
@@ -117,7 +118,7 @@ def test_vanilla_mlp_matches_oracle_forward_and_backward(n_in, n_out, n_hidden, 
     emu_grads = _grads_emulated(ref, x.clone(), go)
     for name, p in net.named_parameters():
         gr = ref_grads[name].grad
-        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 1.5e-2), name
+        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 3e-2), name
     assert net(xd[:0].detach()).shape == (0, n_out)
     # fused=False pins the torch layers: same numbers to fp16-operand accuracy
     net_t = VanillaMLP(n_in, n_out, dict(n_neurons=64, n_hidden_layers=n_hidden, output_activation='none', weight_norm=weight_norm, fused=False))
@@ -165,7 +166,7 @@ def test_vanilla_radiance_matches_oracle_forward_and_backward(n_feat, n_extra, c
                                 post=torch.sigmoid if color_act else (lambda t: t))
     for name, p in tex.network.named_parameters():
         gr = ref_grads[name].grad
-        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 1.5e-2), name
+        assert p.grad is not None and cos(p.grad, gr) > 0.999 and close(p.grad, emu_grads[name], 3e-2), name
     assert tex(fd[:0].detach(), dirs[:0].to(D), *[x[:0].detach() for x in ed]).shape == (0, 3)
 
 
