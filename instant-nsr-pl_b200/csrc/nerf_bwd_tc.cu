@@ -19,6 +19,7 @@
 // Shared memory (110 KB): weights of both networks, canonical [out][in] (one copy serves the forward GEMMs as K-major B and the dgrad
 // GEMMs as MN-major B); activation tiles H1, CI, G1, G2 which the dgrad epilogues overwrite in place with dH1, dG1, dG2; dC3, dO;
 // two stages of tile inputs.  Tensor memory (256 columns): 64 chain accumulator + 32 d(encoding) + 160 weight gradients.
+#include <stdlib.h>
 #include "nerf_fused.cuh"
 
 namespace {
@@ -156,6 +157,7 @@ struct TcArgs {
   int64_t n_cap;
   float loss_scale;
   int* status;
+  int dbg;  // development A/B switches (NSR_TC_DEBUG): 1 = no REDs, 2 = scatter warps do not wait for the chain, 4 = scatter warps idle
 };
 
 // epilogue of a 64-wide hidden layer: ACC[row][0..63] -> f(x) -> fp16 row of a canonical K = 64 tile.
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
         umma_commit(bar(B_MMA));
         // 10: dE = dH1 . DW1 ; dDW1 += dH1^T . X0      (the scatter group of the PREVIOUS tile must have drained the DE columns)
         wait_epi();
-        if (it > 0) {
+        if (it > 0 && !(a.dbg & 6)) {
           const int64_t pt = it - 1;
           mbar_wait(bar(B_DEEMPTY0 + (int)(pt & 1)), (uint32_t)((pt >> 1) & 1), a.status, 4);
           tc_fence_after();
@@ -482,7 +484,8 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       const float x = rf[0], y = rf[1], z = rf[2];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EMPTY0 + s));
-      mbar_wait(bar(B_DEFULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 9);
+      if (a.dbg & 4) continue;
+      if (!(a.dbg & 2)) mbar_wait(bar(B_DEFULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 9);
       tc_fence_after();
       uint32_t de[16];  // (feature 0, feature 1) of level l as fp16 pair, still multiplied by the loss scale
       {
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
           }
           issue = ok && tail;
         }
-        if (issue) {
+        if (issue && !(a.dbg & 1)) {
           nsr_corner_indices(li, cx, cy, cz, idx);
 #pragma unroll
           for (int c = 0; c < 8; c += 2) nsr_red_corner_pair(grad_table, idx[c], idx[c + 1], v[2 * c], v[2 * c + 1], v[2 * c + 2], v[2 * c + 3]);
@@ -591,6 +594,8 @@ extern "C" int nsr_nerf_field_bwd_tc(const nsr_nerf_t* f, const void* enc_tiles_
   a.n_cap = k;
   a.loss_scale = loss_scale;
   a.status = status;
+  static const int dbg = [] { const char* v = getenv("NSR_TC_DEBUG"); return v ? atoi(v) : 0; }();
+  a.dbg = dbg;
   const int64_t tiles = (k + kRows - 1) / kRows;
   int grid = (int)min((int64_t)nsr_sm_count() * 2, tiles);
   if (k_dev != nullptr) grid = nsr_sm_count() * 2;
