@@ -456,6 +456,9 @@ def gpu_arm(args):
     if world > 1:
         sync, sync_desc = make_grad_sync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None),
                                          prefer_p2p=os.environ.get('NSR_GRAD_SYNC', 'p2p') != 'nccl')
+    if sync is not None and hasattr(sync, 'bind_direct'):
+        sync.bind_direct(model._fused)   # the backward accumulates straight into the peer-mapped exchange buffer: no copy-in
+        sync_desc += ', zero-copy gradients' + (', one launch' if sync.one_launch else ', barrier + reduce + barrier')
     # inside the graph only what the fused loss reads is materialised (comp_rgb / rays_valid come out of nsr_nerf_loss_fwd itself)
     model._fused.lean_static_outputs = True
     gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
@@ -586,7 +589,7 @@ def gpu_arm(args):
             kp = (o['offsets_packed'][1:] - o['offsets_packed'][:-1]).double()
             evaluated += float(torch.where(kp < tot, torch.minimum(tot, (torch.floor(kp / 32) + 1) * 32), tot).sum()) / POOL
     alg = {'nsr_nerf_prepass': 512.0 * m1, 'nsr_nerf_render_fwd': 512.0 * k1, 'nsr_nerf_field_bwd': 512.0 * k1,
-           'nsr_nerf_field_bwd_tc': 512.0 * k1, 'nsr_nerf_rays_fwd': 512.0 * evaluated}
+           'nsr_nerf_field_bwd_tc': 512.0 * k1, 'nsr_nerf_table_scatter': 512.0 * k1, 'nsr_nerf_rays_fwd': 512.0 * evaluated}
     dom = max((n for n in alg if n in kern), key=lambda n: kern[n]['ms'] * kern[n]['launches_per_step'], default=None)
     roofline = None
     if dom is not None:
@@ -635,7 +638,7 @@ def gpu_arm(args):
     if roofline is not None and dom in ncu_info:
         roofline['traffic'] = ncu_info[dom].get('dram_bytes_per_launch')
         roofline['traffic_source'] = ncu_info.get('source')
-    if roofline is not None and dom in ('nsr_nerf_field_bwd', 'nsr_nerf_field_bwd_tc'):
+    if roofline is not None and dom in ('nsr_nerf_field_bwd', 'nsr_nerf_field_bwd_tc') and dom in ncu_info:
         # the table (25 MB fp16) and its gradient (50 MB fp32) live in the 126 MB L2: the kernel's real ceiling is the L2 atomic unit.
         # ~80 REDs (8-byte red.global.add.v2.f32) per kept sample after run merging = ncu RED sectors / K
         # (profiles/r1_ncu_traffic.json); 140 G RED/s = scatter-only micro-benchmark at full occupancy

@@ -244,6 +244,15 @@ int nsr_nerf_field_bwd_tc(const nsr_nerf_t* f, const void* enc_tiles_h, const vo
 int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
                              const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
                              const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream);
+/* The two halves of nsr_nerf_field_bwd_split as separate calls (same arguments; the split form = net followed by scatter with
+ * xyz = xyzdir, stride = 6, grad_table = grad_dparams + 3072 = the density network's parameter count).  autograd of tcnn's
+ * NetworkWithInputEncoding / Network (models/geometry.py:122-130, models/texture.py:23-30): network half, then the grid backward. */
+int nsr_nerf_field_bwd_net(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
+                           const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
+                           const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream);
+int nsr_nerf_table_scatter(const nsr_grid_t* g, const float* xyz, int32_t stride, const void* denc_h, float loss_scale, const float* amax,
+                           float* grad_table, int64_t k, const int64_t* k_dev, void* stream);
+
 
 /* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
  * nsr_nerf_rays_fwd: masks (nsr_march_rays_mask) -> per-ray colour in ONE kernel: a warp owns a ray (atomic ticket queue),
@@ -386,6 +395,13 @@ int nsr_mc_emit(const float* field, int32_t nx, int32_t ny, int32_t nz, float is
  *   Must be bracketed by barriers: barrier, allreduce, barrier. */
 int nsr_p2p_barrier(const uint64_t* flag_ptrs_host, int32_t* epoch_dev, int32_t* err_dev, int32_t rank, int32_t world, void* stream);
 int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* multicast_ptr, int32_t rank, int32_t world, int64_t n, void* stream);
+/* nsr_p2p_exchange_mean: the same exchange as ONE launch -- entry barrier, reduce-scatter + all-gather, exit barrier inside the kernel
+ *   (what one bucket of DDP's all-reduce is, launch.py:98).  flag arrays need 64 int32 per rank (entry epochs in [32,48), exit epochs in
+ *   [48,64); [0,16) stays nsr_p2p_barrier's); epoch_counter_dev: local int32[2] {last completed epoch, CTA counter}, zeroed once.  No surrounding barriers needed;
+ *   graph-replay safe (the epoch is device state).  When it returns on the stream, every replica holds the mean and no peer reads
+ *   this rank's buffer any more. */
+int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
+                          int32_t* err_dev, int32_t rank, int32_t world, int64_t n, void* stream);
 
 /* ---- occupancy-grid refresh (nerfacc OccupancyGrid._update behind every_n_step: models/nerf.py:45-55,
  * models/neus.py:79-111).  The caller draws the cells (int64 flat indices ix*R*R + iy*R + iz; NULL = every cell once) and the

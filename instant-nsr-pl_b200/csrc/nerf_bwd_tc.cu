@@ -8,7 +8,7 @@
 //   warp 1      MMA issuer: one lane walks the ten dependent GEMMs of a tile -- five forward-recompute layers, five dgrad layers -- and
 //               issues, next to each dgrad, the weight-gradient GEMM of that layer (M = 64, K = 128 samples) whose accumulator stays in
 //               TMEM for the whole kernel; every group ends in tcgen05.commit -> mbarrier
-//   warps 4-7   epilogue: thread = row; tcgen05.ld the accumulator row, activation / ReLU mask (kept as 3 x 64 bits in registers) /
+//   warps 4-7   epilogue: thread = row; tcgen05.ld the accumulator row, activation / ReLU mask (from the fp16 activations the tile holds) /
 //               incoming-gradient injection, re-pack to fp16 and store the row into the next GEMM's A operand in the canonical K-major
 //               layout (which, read through an MN-major descriptor, is also the weight-gradient GEMM's operand: no transposes anywhere)
 //   warps 8-15  scatter, two groups that alternate tiles: thread = row; pull d(encoding) (32 fp32 columns) out of TMEM, then per level
@@ -19,6 +19,7 @@
 // Shared memory (110 KB): weights of both networks, canonical [out][in] (one copy serves the forward GEMMs as K-major B and the dgrad
 // GEMMs as MN-major B); activation tiles H1, CI, G1, G2 which the dgrad epilogues overwrite in place with dH1, dG1, dG2; dC3, dO;
 // two stages of tile inputs.  Tensor memory (256 columns): 64 chain accumulator + 32 d(encoding) + 160 weight gradients.
+#include <stdio.h>
 #include <stdlib.h>
 #include "nerf_fused.cuh"
 
@@ -60,33 +61,34 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // canonical (no-swizzle) UMMA layout of a [rows][K] fp16 tile: 8 x 16-byte core matrices, K chunks 128 B apart, 8-row groups (K/8)*128 B apart
 __device__ __forceinline__ int canon_off(int row, int k, int K) { return ((row >> 3) * (K >> 3) + (k >> 3)) * 128 + (row & 7) * 16 + (k & 7) * 2; }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version of sm_100
-  return d;
-}
-// operand read along K (rows = M/N index, K contiguous): LBO = 128 between the two K chunks of one MMA, SBO = (K/8)*128 between row groups
-__device__ __forceinline__ uint64_t desc_k(uint32_t base, int K, int kk) { return make_desc(base + (uint32_t)kk * 256u, 128u, (uint32_t)(K >> 3) * 128u); }
-// the same physical tile [k rows][C cols] read with M/N along the columns: SBO = 128 between 8-column chunks, LBO = (C/8)*128 between 8-row k groups
-__device__ __forceinline__ uint64_t desc_mn(uint32_t base, int C, int kk) {
-  const uint32_t lbo = (uint32_t)(C >> 3) * 128u;
-  return make_desc(base + (uint32_t)kk * 2u * lbo, lbo, 128u);
-}
+// Shared-memory matrix descriptors (no swizzle, sm_100 version bit 46), written as  lo = (address >> 4) + constant, hi = constant  so that the
+// issuing thread needs ONE add per operand behind a barrier wait (the first version re-derived mask / shift / or chains from the byte address
+// for every MMA: ~40 dependent uniform-datapath instructions per GEMM group, 400-1000 cycles on the critical path of every chain step).
+//   K-major  [rows][K] tile (rows = M/N index, K contiguous): LBO = 128 B between the two 8-wide K chunks of one MMA, SBO = (K/8)*128 B between
+//            8-row groups; MMA kk starts 256 B further            => lo = b16 + (8 << 16) + 16 kk,      hi = K | 0x4000
+//   MN-major the same physical tile [k rows][C cols] read with M/N along the columns: SBO = 128 B between 8-column chunks, LBO = (C/8)*128 B
+//            between 8-row k groups; MMA kk starts 2 LBO further  => lo = b16 + (C << 16) + 2 C kk,     hi = 8 | 0x4000
+__device__ __forceinline__ uint32_t dk_lo(uint32_t b16, int kk) { return b16 + (8u << 16) + 16u * (uint32_t)kk; }
+__device__ __forceinline__ uint32_t dk_hi(int K) { return (uint32_t)K | 0x4000u; }
+__device__ __forceinline__ uint32_t dm_lo(uint32_t b16, int C, int kk) { return b16 + ((uint32_t)C << 16) + 2u * (uint32_t)C * (uint32_t)kk; }
+__device__ __forceinline__ uint32_t dm_hi() { return 8u | 0x4000u; }
 // kind::f16: D f32 (1 @4), A = B = f16, a_major @15, b_major @16 (1 = MN-major), N>>3 @17, M>>4 @24
 __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate,
+                                     int skip = 0) {
+  if (skip) return;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -102,7 +104,8 @@ __device__ __forceinline__ void tma_bulk(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 // bounded wait: a barrier that is never signalled (a bug) sets *status and traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int code) {
+// acc (development, NSR_TC_TRACE): cycles spent in the wait are added to acc[code * 16]
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int code, long long* acc = nullptr) {
   const long long t0 = clock64();
   for (;;) {
     uint32_t ok;
@@ -115,12 +118,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* st
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (ok) return;
+    if (ok) {
+      if (acc != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(acc + code * 16), (unsigned long long)(clock64() - t0));
+      return;
+    }
     if (clock64() - t0 > 4000000000ll) {
       if (status) atomicExch(status, code);
       __trap();
     }
   }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -157,40 +174,72 @@ struct TcArgs {
   int64_t n_cap;
   float loss_scale;
   int* status;
-  int dbg;  // development A/B switches (NSR_TC_DEBUG): 1 = no REDs, 2 = scatter warps do not wait for the chain, 4 = scatter warps idle
+  long long* trace;  // NSR_TC_TRACE: [3 CTAs][16 wait codes][16 warps] cycle counters (row 0: warp lifetime); else NULL
+  int dbg;  // development A/B switches (NSR_TC_DEBUG): 1 = no REDs, 2 = scatter warps do not wait for the chain, 4 = scatter warps idle,
+            // 128 = scatter uses a synthetic non-zero d(encoding) (with 2 / 8: the scatter's own speed at the full RED count),
+            // 32 = hidden-layer epilogues do nothing (no tcgen05.ld, no st.shared), 64 = no tcgen05.mma (commits only): timing experiments,
+            // 16 = epilogue skips fence.proxy.async (timing experiment only: results undefined),
+            // 8 = no GEMM chain (MMA / epilogue warps only keep the stage barriers moving): with 2 the scatter runs alone
 };
 
-// epilogue of a 64-wide hidden layer: ACC[row][0..63] -> f(x) -> fp16 row of a canonical K = 64 tile.
-//   MODE 0: ReLU, records the mask of the fp16 results;  MODE 1: multiply by the recorded mask (dgrad through ReLU)
+// wait for the tcgen05.ld results; the registers are in/out operands so that no use of them can be scheduled in front of the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                 "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+// 16 accumulator columns [c0, c0 + 16) of the thread's row -> two 16-byte chunks of the canonical K = 64 tile
+//   MODE 0: ReLU on the packed pair (round, then max with +0: same value as rounding max(x, 0))
+//   MODE 1: dgrad through ReLU, IN PLACE: the tile still holds this layer's fp16 activations; a gradient survives where its activation
+//           is > 0 (__hgt2_mask: ordered compare, a NaN activation masks like the fp32 test did)
 template <int MODE>
-__device__ __forceinline__ void epi_hidden(uint32_t lane_addr, uint8_t* tile, int row, bool live, uint64_t& mask) {
-  uint64_t m = MODE == 0 ? 0ull : mask;
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], uint8_t* tile, int row, int c0, uint32_t keep) {
+  const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t v[16];
-    tmem_ld16(lane_addr + T_ACC + (uint32_t)c0, v);
-    tmem_ld_wait();
-    uint32_t pk[8];
+  for (int q = 0; q < 2; ++q) {
+    uint4* dst = reinterpret_cast<uint4*>(tile + canon_off(row, c0 + 8 * q, 64));
+    uint32_t pk[4];
+    uint4 act = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE == 1) act = *dst;
+    const uint32_t am[4] = {act.x, act.y, act.z, act.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = __floats2half2_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
       if (MODE == 0) {
-        a = live ? fmaxf(a, 0.f) : 0.f;
-        b = live ? fmaxf(b, 0.f) : 0.f;
-        const __half2 h = __floats2half2_rn(a, b);
-        if (__low2float(h) > 0.f) m |= 1ull << (c0 + 2 * j);
-        if (__high2float(h) > 0.f) m |= 1ull << (c0 + 2 * j + 1);
-        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        const __half2 r = __hmax2(h, zero);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&r) & keep;
       } else {
-        a = ((m >> (c0 + 2 * j)) & 1ull) ? a : 0.f;
-        b = ((m >> (c0 + 2 * j + 1)) & 1ull) ? b : 0.f;
-        pk[j] = nsr_pack_h2(a, b);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h) & __hgt2_mask(*reinterpret_cast<const __half2*>(&am[j]), zero) & keep;
       }
     }
-    *reinterpret_cast<uint4*>(tile + canon_off(row, c0, 64)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(tile + canon_off(row, c0 + 8, 64)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  if (MODE == 0) mask = m;
+}
+
+// epilogue of a 64-wide hidden layer: ACC[row][0..63] -> fp16 row of a canonical K = 64 tile; ~25 instructions per 16 columns, the
+// tcgen05.ld of chunk i+1 in flight while chunk i is converted (the first version spent ~150 instructions per 16 columns on 64-bit ReLU
+// masks kept in registers).  The thread reads and rewrites only its own row, and every tensor-core read of the tile (the dgrad / wgrad
+// GEMMs of this step) has completed (commit -> B_MMA).  Rows past the end of the batch (live == false) are written as zeros.
+template <int MODE>
+__device__ __forceinline__ void epi_hidden(uint32_t lane_addr, uint8_t* tile, int row, bool live, int skip = 0) {
+  if (skip) return;
+  const uint32_t keep = live ? 0xFFFFFFFFu : 0u;
+  uint32_t va[16], vb[16];
+  tmem_ld16(lane_addr + T_ACC, va);
+  tmem_ld_wait16(va);
+  tmem_ld16(lane_addr + T_ACC + 16u, vb);
+  epi_chunk16<MODE>(va, tile, row, 0, keep);
+  tmem_ld_wait16(vb);
+  tmem_ld16(lane_addr + T_ACC + 32u, va);
+  epi_chunk16<MODE>(vb, tile, row, 16, keep);
+  tmem_ld_wait16(va);
+  tmem_ld16(lane_addr + T_ACC + 48u, vb);
+  epi_chunk16<MODE>(va, tile, row, 32, keep);
+  tmem_ld_wait16(vb);
+  epi_chunk16<MODE>(vb, tile, row, 48, keep);
 }
 
 __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_constant__ nsr_nerf_t P, const TcArgs a) {
@@ -237,6 +286,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  // development counters: three CTAs report, one row of 16 per wait code, one column per warp (lane 0 only); row 0 = the warp's lifetime
+  const int tsel = blockIdx.x == 0 ? 0 : ((int)blockIdx.x == (int)gridDim.x / 2 ? 1 : ((int)blockIdx.x == (int)gridDim.x - 1 ? 2 : -1));
+  long long* const acc = (a.trace != nullptr && tsel >= 0 && lane == 0) ? a.trace + tsel * 256 + warp : nullptr;
+  const long long t_begin = clock64();
   const int64_t my_tiles = n_tiles > (int64_t)blockIdx.x ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -245,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int s = (int)(it & 1);
         const int64_t tile = blockIdx.x + it * gridDim.x, row0 = tile * kRows;
-        mbar_wait(bar(B_EMPTY0 + s), (uint32_t)(((it >> 1) & 1) ^ 1), a.status, 1);
+        mbar_wait(bar(B_EMPTY0 + s), (uint32_t)(((it >> 1) & 1) ^ 1), a.status, 1, acc);
         const uint32_t dst = sbase + STAGES + (uint32_t)s * kStageBytes, fb = bar(B_FULL0 + s);
         mbar_expect_tx(fb, kStageBytes);
         tma_bulk(dst + S_X0, a.enc_tiles + tile * (kRows * 32 * 2), kRows * 32 * 2, fb);
@@ -256,99 +309,170 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      uint32_t p_epi = 0;
-      const uint32_t w_dw1 = sbase + W_DW1, w_dw2 = sbase + W_DW2, w_cw1 = sbase + W_CW1, w_cw2 = sbase + W_CW2, w_cw3 = sbase + W_CW3;
-      const uint32_t h1 = sbase + A_H1, ci = sbase + A_CI, g1 = sbase + A_G1, g2 = sbase + A_G2, dc3 = sbase + A_DC3, dO = sbase + A_DO;
-      const uint32_t i_fwd64 = make_idesc(128, 64, 0, 0), i_fwd16 = make_idesc(128, 16, 0, 0);
-      const uint32_t i_dg64 = make_idesc(128, 64, 0, 1), i_dg32 = make_idesc(128, 32, 0, 1), i_dg16 = make_idesc(128, 16, 0, 1);
-      const uint32_t i_wg64 = make_idesc(64, 64, 1, 1), i_wg32 = make_idesc(64, 32, 1, 1), i_wg16 = make_idesc(64, 16, 1, 1);
-      auto wait_epi = [&]() {
-        mbar_wait(bar(B_EPI), p_epi, a.status, 2);
-        p_epi ^= 1u;
-        tc_fence_after();
-      };
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int s = (int)(it & 1);
-        const uint32_t x0 = sbase + STAGES + (uint32_t)s * kStageBytes + S_X0;
-        const uint32_t acc_first = it > 0 ? 1u : 0u;  // weight-gradient accumulators: overwrite on the CTA's first tile, then accumulate
-        mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 3);
-        tc_fence_after();
-        // 1: H1pre = X0 . DW1^T
-        for (int kk = 0; kk < 2; ++kk) umma(tmem + T_ACC, desc_k(x0, 32, kk), desc_k(w_dw1, 32, kk), i_fwd64, kk > 0);
-        umma_commit(bar(B_MMA));
-        // 2: Opre = H1 . DW2^T
-        wait_epi();
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, desc_k(h1, 64, kk), desc_k(w_dw2, 64, kk), i_fwd16, kk > 0);
-        umma_commit(bar(B_MMA));
-        // 3: G1pre = [O | SH] . CW1^T
-        wait_epi();
-        for (int kk = 0; kk < 2; ++kk) umma(tmem + T_ACC, desc_k(ci, 32, kk), desc_k(w_cw1, 32, kk), i_fwd64, kk > 0);
-        umma_commit(bar(B_MMA));
-        // 4: G2pre = G1 . CW2^T
-        wait_epi();
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, desc_k(g1, 64, kk), desc_k(w_cw2, 64, kk), i_fwd64, kk > 0);
-        umma_commit(bar(B_MMA));
-        // 5: rgb_pre = G2 . CW3^T
-        wait_epi();
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, desc_k(g2, 64, kk), desc_k(w_cw3, 64, kk), i_fwd16, kk > 0);
-        umma_commit(bar(B_MMA));
-        // 6: dG2pre = dC3 . CW3 ; dCW3^T += G2^T . dC3
-        wait_epi();
-        umma(tmem + T_ACC, desc_k(dc3, 16, 0), desc_mn(w_cw3, 64, 0), i_dg64, 0u);
-        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW3, desc_mn(g2, 64, kk), desc_mn(dc3, 16, kk), i_wg16, kk > 0 ? 1u : acc_first);
-        umma_commit(bar(B_MMA));
-        // 7: dG1pre = dG2 . CW2 ; dCW2 += dG2^T . G1
-        wait_epi();
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, desc_k(g2, 64, kk), desc_mn(w_cw2, 64, kk), i_dg64, kk > 0);
-        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW2, desc_mn(g2, 64, kk), desc_mn(g1, 64, kk), i_wg64, kk > 0 ? 1u : acc_first);
-        umma_commit(bar(B_MMA));
-        // 8: dOpre = dG1 . CW1[:, 0:16] ; dCW1 += dG1^T . CI
-        wait_epi();
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, desc_k(g1, 64, kk), desc_mn(w_cw1, 32, kk), i_dg16, kk > 0);
-        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW1, desc_mn(g1, 64, kk), desc_mn(ci, 32, kk), i_wg32, kk > 0 ? 1u : acc_first);
-        umma_commit(bar(B_MMA));
-        // 9: dH1pre = dO . DW2 ; dDW2^T += H1^T . dO
-        wait_epi();
-        umma(tmem + T_ACC, desc_k(dO, 16, 0), desc_mn(w_dw2, 64, 0), i_dg64, 0u);
-        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WDW2, desc_mn(h1, 64, kk), desc_mn(dO, 16, kk), i_wg16, kk > 0 ? 1u : acc_first);
-        umma_commit(bar(B_MMA));
-        // 10: dE = dH1 . DW1 ; dDW1 += dH1^T . X0      (the scatter group of the PREVIOUS tile must have drained the DE columns)
-        wait_epi();
-        if (it > 0 && !(a.dbg & 6)) {
-          const int64_t pt = it - 1;
-          mbar_wait(bar(B_DEEMPTY0 + (int)(pt & 1)), (uint32_t)((pt >> 1) & 1), a.status, 4);
-          tc_fence_after();
+    // The whole warp walks the loop (converged: every lane waits on the barriers) and ONE elected lane issues each group: behind
+    // elect.sync the compiler emits the tcgen05 instructions straight from uniform registers.  (Issuing under `if (lane == 0)` made it wrap
+    // every UTCHMMA in an ELECT / BRA.U.ANY loop: ~55 cycles per MMA, 600-850 cycles per GEMM group in the first version's trace.)
+    uint32_t p_epi = 0;
+    const uint32_t sb16 = (sbase & 0x3FFFFu) >> 4;   // every tile offset is a multiple of 16 bytes: descriptors are sb16 + constants
+    const uint32_t w_dw1 = sb16 + W_DW1 / 16, w_dw2 = sb16 + W_DW2 / 16, w_cw1 = sb16 + W_CW1 / 16, w_cw2 = sb16 + W_CW2 / 16, w_cw3 = sb16 + W_CW3 / 16;
+    const uint32_t h1 = sb16 + A_H1 / 16, ci = sb16 + A_CI / 16, g1 = sb16 + A_G1 / 16, g2 = sb16 + A_G2 / 16, dc3 = sb16 + A_DC3 / 16, dO = sb16 + A_DO / 16;
+    const uint32_t i_fwd64 = make_idesc(128, 64, 0, 0), i_fwd16 = make_idesc(128, 16, 0, 0);
+    const uint32_t i_dg64 = make_idesc(128, 64, 0, 1), i_dg32 = make_idesc(128, 32, 0, 1), i_dg16 = make_idesc(128, 16, 0, 1);
+    const uint32_t i_wg64 = make_idesc(64, 64, 1, 1), i_wg32 = make_idesc(64, 32, 1, 1), i_wg16 = make_idesc(64, 16, 1, 1);
+    int tr_n = 1024;   // development: CTA 0, tiles 2..5: clock stamps of the hand-off loop (tools/tc_trace.py)
+    int64_t tr_it = 0;
+    auto stamp = [&]() {
+      if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_it >= 2 && tr_n < 2048) a.trace[tr_n++] = clock64();
+    };
+    auto wait_epi = [&]() {
+      stamp();   // previous group issued + committed
+      mbar_wait(bar(B_EPI), p_epi, a.status, 2, acc);
+      p_epi ^= 1u;
+      tc_fence_after();
+      stamp();   // operand tile ready
+    };
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it & 1);
+      const uint32_t x0 = sb16 + (STAGES + S_X0) / 16 + (uint32_t)s * (kStageBytes / 16);
+      const uint32_t acc_first = it > 0 ? 1u : 0u;  // weight-gradient accumulators: overwrite on the CTA's first tile, then accumulate
+      tr_it = it;
+      mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 3, acc);
+      tc_fence_after();
+      if (a.dbg & 8) {
+        if (elect_one()) {
+          umma_commit(bar(B_DEFULL0 + s));
+          umma_commit(bar(B_EMPTY0 + s));
         }
-        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_DE, desc_k(h1, 64, kk), desc_mn(w_dw1, 32, kk), i_dg32, kk > 0);
-        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WDW1, desc_mn(h1, 64, kk), desc_mn(x0, 32, kk), i_wg32, kk > 0 ? 1u : acc_first);
+        __syncwarp();
+        continue;
+      }
+      // 1: H1pre = X0 . DW1^T
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) umma(tmem + T_ACC, dk_lo(x0, kk), dk_hi(32), dk_lo(w_dw1, kk), dk_hi(32), i_fwd64, kk > 0, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 2: Opre = H1 . DW2^T
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, dk_lo(h1, kk), dk_hi(64), dk_lo(w_dw2, kk), dk_hi(64), i_fwd16, kk > 0, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 3: G1pre = [O | SH] . CW1^T
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) umma(tmem + T_ACC, dk_lo(ci, kk), dk_hi(32), dk_lo(w_cw1, kk), dk_hi(32), i_fwd64, kk > 0, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 4: G2pre = G1 . CW2^T
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, dk_lo(g1, kk), dk_hi(64), dk_lo(w_cw2, kk), dk_hi(64), i_fwd64, kk > 0, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 5: rgb_pre = G2 . CW3^T
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, dk_lo(g2, kk), dk_hi(64), dk_lo(w_cw3, kk), dk_hi(64), i_fwd16, kk > 0, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 6: dG2pre = dC3 . CW3 ; dCW3^T += G2^T . dC3
+      wait_epi();
+      if (elect_one()) {
+        umma(tmem + T_ACC, dk_lo(dc3, 0), dk_hi(16), dm_lo(w_cw3, 64, 0), dm_hi(), i_dg64, 0u, a.dbg & 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW3, dm_lo(g2, 64, kk), dm_hi(), dm_lo(dc3, 16, kk), dm_hi(), i_wg16, kk > 0 ? 1u : acc_first, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 7: dG1pre = dG2 . CW2 ; dCW2 += dG2^T . G1
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, dk_lo(g2, kk), dk_hi(64), dm_lo(w_cw2, 64, kk), dm_hi(), i_dg64, kk > 0, a.dbg & 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW2, dm_lo(g2, 64, kk), dm_hi(), dm_lo(g1, 64, kk), dm_hi(), i_wg64, kk > 0 ? 1u : acc_first, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 8: dOpre = dG1 . CW1[:, 0:16] ; dCW1 += dG1^T . CI
+      wait_epi();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_ACC, dk_lo(g1, kk), dk_hi(64), dm_lo(w_cw1, 32, kk), dm_hi(), i_dg16, kk > 0, a.dbg & 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WCW1, dm_lo(g1, 64, kk), dm_hi(), dm_lo(ci, 32, kk), dm_hi(), i_wg32, kk > 0 ? 1u : acc_first, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 9: dH1pre = dO . DW2 ; dDW2^T += H1^T . dO
+      wait_epi();
+      if (elect_one()) {
+        umma(tmem + T_ACC, dk_lo(dO, 0), dk_hi(16), dm_lo(w_dw2, 64, 0), dm_hi(), i_dg64, 0u, a.dbg & 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WDW2, dm_lo(h1, 64, kk), dm_hi(), dm_lo(dO, 16, kk), dm_hi(), i_wg16, kk > 0 ? 1u : acc_first, a.dbg & 64);
+        umma_commit(bar(B_MMA));
+      }
+      __syncwarp();
+      // 10: dE = dH1 . DW1 ; dDW1 += dH1^T . X0      (the scatter group of the PREVIOUS tile must have drained the DE columns)
+      wait_epi();
+      if (it > 0 && !(a.dbg & 6)) {
+        const int64_t pt = it - 1;
+        mbar_wait(bar(B_DEEMPTY0 + (int)(pt & 1)), (uint32_t)((pt >> 1) & 1), a.status, 4, acc);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma(tmem + T_DE, dk_lo(h1, kk), dk_hi(64), dm_lo(w_dw1, 32, kk), dm_hi(), i_dg32, kk > 0, a.dbg & 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma(tmem + T_WDW1, dm_lo(h1, 64, kk), dm_hi(), dm_lo(x0, 32, kk), dm_hi(), i_wg32, kk > 0 ? 1u : acc_first, a.dbg & 64);
         umma_commit(bar(B_DEFULL0 + s));
         umma_commit(bar(B_EMPTY0 + s));  // the stage's encodings are not read any more
       }
-      umma_commit(bar(B_WG));  // every weight-gradient GEMM of this CTA has completed
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(bar(B_WG));  // every weight-gradient GEMM of this CTA has completed
+    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ================================ epilogue ================================
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t p_mma = 0;
+    int tr_n = 2048;
+    int64_t tr_it = 0;
+    auto stamp = [&]() {
+      if (a.trace != nullptr && blockIdx.x == 0 && tid == 128 && tr_it >= 2 && tr_n < 4096) a.trace[tr_n++] = clock64();
+    };
     auto wait_mma = [&]() {
-      mbar_wait(bar(B_MMA), p_mma, a.status, 5);
+      mbar_wait(bar(B_MMA), p_mma, a.status, 5, acc);
       p_mma ^= 1u;
       tc_fence_after();
+      stamp();   // accumulator ready
     };
     auto signal = [&]() {  // my TMEM reads are done and my smem writes are visible to the tensor core
+      stamp();   // row computed and stored
       tc_fence_before();
-      proxy_fence();
+      if (!(a.dbg & 16)) proxy_fence();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EPI));
+      stamp();   // handed back
     };
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int s = (int)(it & 1);
       const int64_t tile = blockIdx.x + it * gridDim.x, grow = tile * kRows + row;
       const bool live = grow < n;
       uint8_t* st = smem + STAGES + s * kStageBytes;
-      mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 6);
+      tr_it = it;
+      mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 6, acc);
       const float* rf = reinterpret_cast<const float*>(st + S_XYZ) + row * 6;
       const float dirx = rf[3], diry = rf[4], dirz = rf[5];
       const float* rg = reinterpret_cast<const float*>(st + S_DRGB) + row * 3;
@@ -360,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EMPTY0 + s));
+      if (a.dbg & 8) continue;
       {  // SH of the view direction -> columns 16..31 of the colour network's input
         uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
         if (live) {
@@ -371,10 +496,9 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
         *reinterpret_cast<uint4*>(smem + A_CI + canon_off(row, 16, 32)) = s0;
         *reinterpret_cast<uint4*>(smem + A_CI + canon_off(row, 24, 32)) = s1;
       }
-      uint64_t m_h1 = 0, m_g1 = 0, m_g2 = 0;
       // 1: H1 = relu(.)
       wait_mma();
-      epi_hidden<0>(lane_addr, smem + A_H1, row, live, m_h1);
+      epi_hidden<0>(lane_addr, smem + A_H1, row, live, a.dbg & 32);
       signal();
       // 2: out16 (fp16) -> columns 0..15 of the colour input
       wait_mma();
@@ -391,10 +515,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       signal();
       // 3, 4: colour hidden layers
       wait_mma();
-      epi_hidden<0>(lane_addr, smem + A_G1, row, live, m_g1);
+      epi_hidden<0>(lane_addr, smem + A_G1, row, live, a.dbg & 32);
       signal();
       wait_mma();
-      epi_hidden<0>(lane_addr, smem + A_G2, row, live, m_g2);
+      epi_hidden<0>(lane_addr, smem + A_G2, row, live, a.dbg & 32);
       signal();
       // 5: d(rgb pre-activation) = d_rgb * s (1 - s), s = sigmoid(fp16(raw)); columns 0..2, the rest of the 16-wide operand is zero
       wait_mma();
@@ -416,10 +540,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       signal();
       // 6, 7: dgrad through the colour hidden layers (in place over G2, G1)
       wait_mma();
-      epi_hidden<1>(lane_addr, smem + A_G2, row, live, m_g2);
+      epi_hidden<1>(lane_addr, smem + A_G2, row, live, a.dbg & 32);
       signal();
       wait_mma();
-      epi_hidden<1>(lane_addr, smem + A_G1, row, live, m_g1);
+      epi_hidden<1>(lane_addr, smem + A_G1, row, live, a.dbg & 32);
       signal();
       // 8: d(out16) = colour path + d sigma_raw on column 0
       wait_mma();
@@ -442,12 +566,12 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       signal();
       // 9: dgrad through the density hidden layer (in place over H1)
       wait_mma();
-      epi_hidden<1>(lane_addr, smem + A_H1, row, live, m_h1);
+      epi_hidden<1>(lane_addr, smem + A_H1, row, live, a.dbg & 32);
       signal();
     }
     // ---- weight gradients: TMEM -> global (M = 64 accumulators live in lanes 0..15 of every 32-lane quarter: row = 16 * quarter + lane)
-    if (my_tiles > 0) {
-      mbar_wait(bar(B_WG), 0u, a.status, 7);
+    if (my_tiles > 0 && !(a.dbg & 8)) {
+      mbar_wait(bar(B_WG), 0u, a.status, 7, acc);
       tc_fence_after();
       const int q = warp & 3, m = 16 * q + lane;
       auto flush = [&](uint32_t col0, int ncols, float* dst, int stride_m, int stride_c) {
@@ -479,13 +603,13 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       const int64_t tile = blockIdx.x + it * gridDim.x, grow = tile * kRows + row;
       const bool ok = grow < n;
       const uint8_t* st = smem + STAGES + s * kStageBytes;
-      mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 8);
+      mbar_wait(bar(B_FULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 8, acc);
       const float* rf = reinterpret_cast<const float*>(st + S_XYZ) + row * 6;
       const float x = rf[0], y = rf[1], z = rf[2];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EMPTY0 + s));
       if (a.dbg & 4) continue;
-      if (!(a.dbg & 2)) mbar_wait(bar(B_DEFULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 9);
+      if (!(a.dbg & 2)) mbar_wait(bar(B_DEFULL0 + s), (uint32_t)((it >> 1) & 1), a.status, 9, acc);
       tc_fence_after();
       uint32_t de[16];  // (feature 0, feature 1) of level l as fp16 pair, still multiplied by the loss scale
       {
@@ -498,6 +622,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) de[8 + j] = nsr_pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      }
+      if (a.dbg & 128) {  // timing experiments without the chain: a non-zero synthetic gradient so that every RED is issued
+#pragma unroll
+        for (int j = 0; j < 16; ++j) de[j] = 0x2C003400u + (uint32_t)((row + j) & 7);
       }
       tc_fence_before();
       __syncwarp();
@@ -552,6 +680,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_bwd_tc_kernel(const __grid_c
       }
     }
   }
+  if (acc != nullptr) acc[0] = clock64() - t_begin;
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
@@ -596,10 +725,26 @@ extern "C" int nsr_nerf_field_bwd_tc(const nsr_nerf_t* f, const void* enc_tiles_
   a.status = status;
   static const int dbg = [] { const char* v = getenv("NSR_TC_DEBUG"); return v ? atoi(v) : 0; }();
   a.dbg = dbg;
+  static const char* trace_path = getenv("NSR_TC_TRACE");   // development aid: dump CTA 0's pipeline time stamps after a synchronised launch
+  static long long* trace_dev = nullptr;
+  if (trace_path != nullptr && trace_dev == nullptr) {
+    cudaMalloc(&trace_dev, 4096 * sizeof(long long));
+  }
+  if (trace_dev != nullptr) cudaMemsetAsync(trace_dev, 0, 4096 * sizeof(long long), (cudaStream_t)stream);
+  a.trace = trace_dev;
   const int64_t tiles = (k + kRows - 1) / kRows;
   int grid = (int)min((int64_t)nsr_sm_count() * 2, tiles);
   if (k_dev != nullptr) grid = nsr_sm_count() * 2;
   nerf_bwd_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd_tc");
+  if (trace_dev != nullptr) {
+    static long long host[4096];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int i = 0; i < 4096; ++i) fprintf(f, "%lld\n", host[i]);
+      fclose(f);
+    }
+  }
   return 0;
 }

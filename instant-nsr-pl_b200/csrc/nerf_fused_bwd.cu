@@ -515,6 +515,34 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
                           loss_scale, amax, k, k_dev, row_pos, xyzdir, nullptr, stream, "nsr_nerf_field_bwd");
 }
 
+// The two halves of the split backward as separate entry points (what the Python side calls, so that each half shows up with its own
+// duration in bench.py's per-kernel table):
+//   nsr_nerf_field_bwd_net   : MLP recompute + dgrad + wgrad over the packed rows; d(encoding) -> denc_h (fp16 [k,32], still multiplied by
+//                              the loss scale); grad_dparams receives only the density network's weight gradients
+//   nsr_nerf_table_scatter   : denc_h -> fp32 REDs into grad_table (= grad_dparams + the density network's parameter count); xyz = the
+//                              packed unit-cube positions with row stride `stride` floats (6 for the xyzdir buffer of nsr_pack_kept)
+extern "C" int nsr_nerf_field_bwd_net(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
+                                      const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
+                                      const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream) {
+  NSR_REQUIRE(denc_h != nullptr && xyzdir != nullptr, "nsr_nerf_field_bwd_net: denc / xyzdir is NULL");
+  return field_bwd_launch(f, nullptr, nullptr, nullptr, nullptr, enc_k_h, dparams_h, cparams_h, d_sraw, d_rgb, grad_dparams, grad_cparams, loss_scale,
+                          amax, k, k_dev, nullptr, xyzdir, denc_h, stream, "nsr_nerf_field_bwd_net");
+}
+
+extern "C" int nsr_nerf_table_scatter(const nsr_grid_t* g, const float* xyz, int32_t stride, const void* denc_h, float loss_scale, const float* amax,
+                                      float* grad_table, int64_t k, const int64_t* k_dev, void* stream) {
+  NSR_REQUIRE(g != nullptr && xyz != nullptr && denc_h != nullptr && grad_table != nullptr, "nsr_nerf_table_scatter: NULL argument");
+  NSR_REQUIRE(g->n_levels == 16 && g->n_features == 2, "nsr_nerf_table_scatter: needs L=16, F=2");
+  NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_nerf_table_scatter: loss_scale <= 0 (automatic) needs the amax pointer");
+  NSR_REQUIRE(stride >= 3, "nsr_nerf_table_scatter: stride must be >= 3");
+  if (k == 0) return 0;
+  const int grid = (int)min((int64_t)nsr_sm_count() * 8, (k + 255) / 256);
+  nerf_table_scatter_kernel<<<k_dev ? nsr_sm_count() * 8 : grid, 256, 0, (cudaStream_t)stream>>>(*g, xyz, stride, (const __half2*)denc_h, loss_scale, amax,
+                                                                                                 grad_table, k, k_dev);
+  NSR_CHECK_LAUNCH("nsr_nerf_table_scatter");
+  return 0;
+}
+
 // Split form of the same backward (packed inputs only): kernel 1 = MLP recompute + dgrad + wgrad, d(encoding) -> denc_h (fp16 [k,32],
 // still multiplied by the loss scale); kernel 2 = nerf_table_scatter_kernel over the same rows (grad_dparams + NF_DENSITY_PARAMS).
 extern "C" int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h,

@@ -106,6 +106,133 @@ __global__ void __launch_bounds__(256) p2p_allreduce_mean_multimem_kernel(float*
   }
 }
 
+// ---- one-launch exchange: entry barrier + reduce-scatter + all-gather + exit barrier in ONE kernel ------------------------------------
+// (round 1 used three launches -- barrier, reduce, barrier -- plus a 50 MB copy into the symmetric buffer; the step's backward now
+//  accumulates straight into that buffer and this kernel is the whole exchange.)
+//   entry : CTA 0 publishes "rank's gradients are complete" (epoch e) into every peer's flag array; EVERY CTA waits until all peers have
+//           published e (their backward kernels are behind them) -- no grid-wide sync needed, each CTA polls the local flags itself
+//   data  : rank r owns chunk r; U 16-byte columns per thread are in flight before the first is consumed
+//             multicast: multimem.ld_reduce (the NVSwitch adds the replicas) -> scale -> multimem.st (the switch broadcasts)
+//             P2P      : ld.cv from every peer in rank order -> scale -> st to every peer
+//   exit  : every CTA fences its stores; the LAST CTA to finish (self-resetting counter) publishes "rank r is done reading and writing"
+//           and waits for the same from every peer, so kernel completion == every replica holds the complete mean and nobody still reads
+//           this rank's buffer (the next step may zero it).  The epoch lives in device memory => CUDA-graph replay safe.
+constexpr int kEntrySlot = 32, kExitSlot = 48;
+struct XchgArgs {
+  float4* peer[kMaxWorld];
+  int32_t* flags[kMaxWorld];  // int32[64] per rank: [32, 48) entry epochs by source rank, [48, 64) exit epochs ([0, 16) belongs to nsr_p2p_barrier)
+  float* mc;
+  int32_t* epoch;    // last completed exchange
+  int32_t* counter;  // CTAs that finished their share (returns to 0)
+  int32_t* err;
+  int rank, world;
+  int64_t n4;
+  float inv;
+};
+
+__device__ __forceinline__ void xchg_signal_wait(const XchgArgs& a, int slot0, int e) {
+  const int p = threadIdx.x;
+  if (p < a.world) {
+    int32_t* dst = a.flags[p] + slot0 + a.rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
+  }
+}
+__device__ __forceinline__ void xchg_wait(const XchgArgs& a, int slot0, int e) {
+  const int p = threadIdx.x;
+  if (p < a.world) {
+    const int32_t* src = a.flags[a.rank] + slot0 + p;
+    long long spins = 0;
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    } while (v - e < 0 && ++spins < kSpinLimit);
+    if (v - e < 0) atomicExch(a.err, 1);
+  }
+}
+
+template <int U, bool MC>
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(const XchgArgs a) {
+  __shared__ int s_last;
+  const int e = *reinterpret_cast<volatile int32_t*>(a.epoch) + 1;  // every CTA reads it before the last one to finish advances it
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    xchg_signal_wait(a, kEntrySlot, e);
+  }
+  xchg_wait(a, kEntrySlot, e);
+  __syncthreads();
+  const int64_t chunk = (a.n4 + a.world - 1) / a.world;
+  const int64_t lo = a.rank * chunk, hi = min(a.n4, lo + chunk);
+  const int64_t span = 256ll * U;
+  for (int64_t base = lo + blockIdx.x * span; base < hi; base += (int64_t)gridDim.x * span) {
+    float4 acc[U];
+    if (MC) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = base + u * 256 + threadIdx.x;
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < hi)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                       : "l"(a.mc + i * 4)
+                       : "memory");
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = base + u * 256 + threadIdx.x;
+        if (i < hi)
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + i * 4), "f"(acc[u].x * a.inv),
+                       "f"(acc[u].y * a.inv), "f"(acc[u].z * a.inv), "f"(acc[u].w * a.inv)
+                       : "memory");
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < kMaxWorld; ++q) {
+        if (q < a.world) {  // fixed summation order 0..world-1; the owner broadcasts ONE result, so all replicas stay bit-identical
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * 256 + threadIdx.x;
+            v[u] = i < hi ? __ldcv(a.peer[q] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            acc[u].x += v[u].x;
+            acc[u].y += v[u].y;
+            acc[u].z += v[u].z;
+            acc[u].w += v[u].w;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = base + u * 256 + threadIdx.x;
+        if (i < hi) {
+          const float4 r = make_float4(acc[u].x * a.inv, acc[u].y * a.inv, acc[u].z * a.inv, acc[u].w * a.inv);
+#pragma unroll
+          for (int q = 0; q < kMaxWorld; ++q)
+            if (q < a.world) a.peer[q][i] = r;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    xchg_signal_wait(a, kExitSlot, e);
+    xchg_wait(a, kExitSlot, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *a.counter = 0;
+      *a.epoch = e;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int nsr_p2p_barrier(const uint64_t* flag_ptrs_host, int32_t* epoch_dev, int32_t* err_dev, int32_t rank, int32_t world, void* stream) {
@@ -141,5 +268,44 @@ extern "C" int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* mult
     p2p_allreduce_mean_kernel<kU><<<grid, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, n4, inv);
   }
   NSR_CHECK_LAUNCH("nsr_p2p_allreduce_mean");
+  return 0;
+}
+
+// The whole exchange as ONE launch (see p2p_exchange_kernel).  flag_ptrs_host: every rank's peer-mapped flag array (int32[64], zeroed
+// once at start-up; slots [32, 64) are this entry point's); epoch_counter_dev: two local int32 {last completed epoch, CTA counter}, zeroed once; grid is capped at the number of
+// CTAs that are resident at once (the CTAs poll flags, so they must not wait for each other's SMs).
+extern "C" int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
+                                     int32_t* err_dev, int32_t rank, int32_t world, int64_t n, void* stream) {
+  NSR_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "nsr_p2p_exchange_mean: bad rank / world (max %d)", kMaxWorld);
+  NSR_REQUIRE(n % 4 == 0, "nsr_p2p_exchange_mean: n must be a multiple of 4 floats");
+  NSR_REQUIRE(peer_ptrs_host != nullptr && flag_ptrs_host != nullptr && epoch_counter_dev != nullptr && err_dev != nullptr,
+              "nsr_p2p_exchange_mean: NULL argument");
+  if (n == 0 || world == 1) return 0;
+  XchgArgs a;
+  for (int q = 0; q < kMaxWorld; ++q) {
+    a.peer[q] = q < world ? reinterpret_cast<float4*>(peer_ptrs_host[q]) : nullptr;
+    a.flags[q] = q < world ? reinterpret_cast<int32_t*>(flag_ptrs_host[q]) : nullptr;
+  }
+  a.mc = (float*)multicast_ptr;
+  a.epoch = epoch_counter_dev;
+  a.counter = epoch_counter_dev + 1;
+  a.err = err_dev;
+  a.rank = rank;
+  a.world = world;
+  a.n4 = n / 4;
+  a.inv = 1.f / (float)world;
+  const int64_t chunk = (a.n4 + world - 1) / world;
+  static const int ctas_per_sm = [] {   // tuning knob (default 2): NSR_P2P_CTAS_PER_SM=1..8 (all CTAs must be resident: 256 threads, <= 64 registers)
+    const char* v = getenv("NSR_P2P_CTAS_PER_SM");
+    const int n = v ? atoi(v) : 2;
+    return n >= 1 && n <= 8 ? n : 2;
+  }();
+  constexpr int kU = 8;
+  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * ctas_per_sm, (chunk + 256 * kU - 1) / (256 * kU)));
+  if (multicast_ptr != nullptr)
+    p2p_exchange_kernel<kU, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else
+    p2p_exchange_kernel<4, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  NSR_CHECK_LAUNCH("nsr_p2p_exchange_mean");
   return 0;
 }

@@ -139,8 +139,14 @@ class _NerfRenderRays(torch.autograd.Function):
         dev = rays.device
         n, cap = ctx.n_rays, ctx.cap
         step = float(fused.model.render_step_size)
-        gd = torch.zeros(fused.n_dparams, device=dev)
-        gc = torch.zeros(fused.n_cparams, device=dev)
+        direct = fused.direct_grads
+        if direct is not None:   # accumulate straight into caller-owned buffers (the symmetric exchange buffer): autograd is bypassed
+            gd, gc = direct
+            gd.zero_()
+            gc.zero_()
+        else:
+            gd = torch.zeros(fused.n_dparams, device=dev)
+            gc = torch.zeros(fused.n_cparams, device=dev)
         if (enc is not None or enc_k is not None) and n > 0:
             f32 = lambda t: None if t is None else contig(t, torch.float32)
             amax = amax0   # zeroed together with the forward's ticket (a retained-graph second backward only makes the scale smaller)
@@ -166,12 +172,16 @@ class _NerfRenderRays(torch.autograd.Function):
                 elif packed and fused.bwd_kernel == 'tiles_split':
                     # network half + table half as two launches: the REDs come from a kernel with 64 light warps per SM (csrc/nerf_fused_bwd.cu)
                     denc = torch.empty(cap, 32, dtype=torch.float16, device=dev)
-                    lib.call('nsr_nerf_field_bwd_split', fused.ref(), ptr(enc_k), ptr(dh), ptr(ch), ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc),
+                    lib.call('nsr_nerf_field_bwd_net', fused.ref(), ptr(enc_k), ptr(dh), ptr(ch), ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc),
                              float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(xyzdir), ptr(denc), stream())
+                    lib.call('nsr_nerf_table_scatter', ctypes.byref(fused.struct.grid), ptr(xyzdir), 6, ptr(denc), float(fused.loss_scale), ptr(amax),
+                             ptr(gd[fused.net.mlp.n_params:]), cap, ptr(offsets_k[n:]), stream())
                 else:
                     lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc_k if packed else enc), ptr(dh), ptr(ch),
                              ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]),
                              None if packed else ptr(pos), ptr(xyzdir), stream())
+        if direct is not None:
+            return None, None, None, None, None
         return gd, gc, None, None, None
 
 
@@ -204,11 +214,14 @@ class NerfFused:
         self.packed_bwd_inputs = True   # tile backward reads its inputs in packed row order (written by nsr_pack_kept)
         from .config import experimental
         self.fuse_kept_scan = experimental('pack_scan')   # nsr_pack_kept_scan instead of nsr_scan_counts + nsr_pack_kept (not yet timed)
-        # 'tiles' (one sample-tile backward kernel, REDs from the MMA warps) | 'tiles_split' (network half + high-occupancy table scatter) |
-        # 'rays' (single per-ray backward kernel)
+        # 'tiles_split' (default: network half + high-occupancy table scatter, 189 us) | 'tiles' (one sample-tile backward kernel, REDs from the
+        # MMA warps, 202 us) | 'tc' (tcgen05 / TMA warp-specialised kernel, 208 us: csrc/nerf_bwd_tc.cu) | 'rays' (single per-ray backward kernel)
         import os
-        self.bwd_kernel = os.environ.get('NSR_BWD_KERNEL', 'tiles')
+        self.bwd_kernel = os.environ.get('NSR_BWD_KERNEL', 'tiles_split')
         self._tc_status = None
+        # (gd, gc) flat fp32 buffers the backward zeroes and accumulates into INSTEAD of handing gradients to autograd (per-ray path only;
+        # set by parallel.P2PGradSync.bind_direct: the buffers are views of the peer-mapped exchange buffer and become .grad after the exchange)
+        self.direct_grads = None
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 
     @staticmethod

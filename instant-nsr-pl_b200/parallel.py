@@ -44,9 +44,9 @@ class GradSync:
 
 class P2PGradSync:
     """The same mean, as OUR kernels over NVLink peer memory instead of NCCL (csrc/p2p.cu): the flat gradient vector of every rank
-    lives in a symmetric (peer-mapped) buffer; ``all_reduce_mean`` = copy-in, barrier, one in-place reduce-scatter + all-gather
-    kernel (rank r sums chunk r over the peers -- in the NVSwitch when the buffer has a multicast mapping -- and writes it into
-    every replica), barrier; afterwards ``p.grad`` IS the view of the symmetric buffer that holds the mean (no copy-out).
+    lives in a symmetric (peer-mapped) buffer; ``all_reduce_mean`` = ONE kernel: entry barrier, in-place reduce-scatter + all-gather
+    (rank r sums chunk r over the peers -- in the NVSwitch when the buffer has a multicast mapping -- and writes it into every replica),
+    exit barrier.  ``bind_direct`` makes the fused backward accumulate straight into the buffer (no copy-in); afterwards ``p.grad`` IS the view of the symmetric buffer that holds the mean (no copy-out).
     Capturable into the step's CUDA graph (no NCCL call inside).  Needs torch.distributed._symmetric_memory (CUDA backend) and P2P
     access between the ranks' GPUs; ``make_grad_sync`` falls back to NCCL when that is not available."""
 
@@ -70,6 +70,8 @@ class P2PGradSync:
         self.buf.zero_()
         self.flags.zero_()
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch2 = torch.zeros(2, dtype=torch.int32, device=dev)   # one-launch exchange: {last completed epoch, CTA counter}
+        self.direct = set()
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.views, off = [], 0
         for p, sz in zip(self.params, sizes):
@@ -83,6 +85,8 @@ class P2PGradSync:
         # loads/stores 0.118 ms vs 0.17 ms through the multicast mapping for the 50 MB exchange, so auto uses it only from 4 ranks up
         # (in-switch reduction moves 1/world of the bytes per GPU).
         import os
+        # NSR_P2P_EXCHANGE = fused (default: barriers inside the one reduce kernel, nsr_p2p_exchange_mean) | legacy (barrier, reduce, barrier)
+        self.one_launch = os.environ.get('NSR_P2P_EXCHANGE', 'fused') != 'legacy'
         want = os.environ.get('NSR_P2P_MULTIMEM', 'auto')
         use_mc = mc != 0 and (want == '1' or (want == 'auto' and self.world >= 4))
         self.multicast_available = mc != 0
@@ -90,19 +94,38 @@ class P2PGradSync:
         torch.cuda.synchronize()
         dist.barrier(group)   # every rank has zeroed its flags before anyone signals
 
+    def view_of(self, param):
+        """the slice of the symmetric buffer that holds (and after the exchange IS) this parameter's gradient"""
+        for p, v in zip(self.params, self.views):
+            if p is param:
+                return v
+        raise KeyError('parameter is not part of this exchange')
+
+    def bind_direct(self, fused):
+        """let the fused NeRF backward accumulate straight into the symmetric buffer (NerfFused.direct_grads): no 50 MB copy-in per step.
+        The backward then zeroes + fills the views itself and autograd is bypassed for these two parameters."""
+        net, cnet = fused.net.params, fused.cnet.params
+        fused.direct_grads = (self.view_of(net), self.view_of(cnet))
+        self.direct = {id(net), id(cnet)}
+
     def all_reduce_mean(self):
         import ctypes
         from .lib import lib, ptr, stream
         for p, v in zip(self.params, self.views):
+            if id(p) in self.direct:
+                continue   # the backward kernels accumulated into the view already
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
-        bar = lambda: lib.call('nsr_p2p_barrier', self._fpeer, ptr(self.epoch), ptr(self.err), self.rank, self.world, stream())
-        bar()
-        lib.call('nsr_p2p_allreduce_mean', self._peer, ctypes.c_void_p(self.multicast) if self.multicast else None, self.rank, self.world,
-                 self.n, stream())
-        bar()
+        mc = ctypes.c_void_p(self.multicast) if self.multicast else None
+        if self.one_launch:
+            lib.call('nsr_p2p_exchange_mean', self._peer, self._fpeer, mc, ptr(self.epoch2), ptr(self.err), self.rank, self.world, self.n, stream())
+        else:
+            bar = lambda: lib.call('nsr_p2p_barrier', self._fpeer, ptr(self.epoch), ptr(self.err), self.rank, self.world, stream())
+            bar()
+            lib.call('nsr_p2p_allreduce_mean', self._peer, mc, self.rank, self.world, self.n, stream())
+            bar()
         for p, v in zip(self.params, self.views):
             p.grad = v
 
