@@ -456,13 +456,21 @@ def gpu_arm(args):
     if world > 1:
         sync, sync_desc = make_grad_sync(params, world, comm_dtype=(torch.bfloat16 if comm == 'bf16' else None),
                                          prefer_p2p=os.environ.get('NSR_GRAD_SYNC', 'p2p') != 'nccl')
+    post_backward = sync.all_reduce_mean if sync is not None else None
     if sync is not None and hasattr(sync, 'bind_direct'):
-        sync.bind_direct(model._fused)   # the backward accumulates straight into the peer-mapped exchange buffer: no copy-in
-        sync_desc += ', zero-copy gradients' + (', one launch' if sync.one_launch else ', barrier + reduce + barrier')
+        # the backward accumulates straight into the peer-mapped exchange buffer (no copy-in); NSR_P2P_OVERLAP=1 (default): the table gradient
+        # is scattered level group by level group and each finished group is exchanged beside the next group's scatter
+        if os.environ.get('NSR_P2P_OVERLAP', '1') == '1' and sync.one_launch and model._fused.bwd_kernel == 'tiles_split':
+            sync.bind_pipelined(model._fused)
+            post_backward = sync.finish
+            sync_desc += ', zero-copy gradients, exchange pipelined with the table scatter in 3 level groups (one launch per group)'
+        else:
+            sync.bind_direct(model._fused)
+            sync_desc += ', zero-copy gradients' + (', one launch' if sync.one_launch else ', barrier + reduce + barrier')
     # inside the graph only what the fused loss reads is materialised (comp_rgb / rays_valid come out of nsr_nerf_loss_fwd itself)
     model._fused.lean_static_outputs = True
     gstep = GraphedStep(model, loss_fn, N_RAYS, batch_spec={'rgb': (3,)}, device=dev, warmup=3,
-                        post_backward=(sync.all_reduce_mean if sync is not None else None))
+                        post_backward=post_backward)
 
     model._fused.lean_static_outputs = False   # (captured already; the eager API below returns the full dict)
 
@@ -564,6 +572,7 @@ def gpu_arm(args):
             os._exit(0)
 
     # ---- rank 0: eager-API timing and per-kernel durations (CUDA events around every C-ABI call; same workload)
+    model._fused.exchange_hook = model._fused.level_groups = model._fused.direct_grads = None   # single-rank eager steps from here on: no exchange
     nprof = min(args.steps, 20)
     for i in range(3):
         eager_step(rays_dev[i % POOL], tgt_dev[i % POOL])

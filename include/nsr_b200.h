@@ -245,13 +245,15 @@ int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h, const voi
                              const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
                              const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream);
 /* The two halves of nsr_nerf_field_bwd_split as separate calls (same arguments; the split form = net followed by scatter with
- * xyz = xyzdir, stride = 6, grad_table = grad_dparams + 3072 = the density network's parameter count).  autograd of tcnn's
+ * xyz = xyzdir, stride = 6, grad_table = grad_dparams + 3072 = the density network's parameter count, levels [0, 16), ctas_per_sm 0 = 8).
+ * The data-parallel step scatters level groups in separate launches so that the exchange of a finished group overlaps the next group.  autograd of tcnn's
  * NetworkWithInputEncoding / Network (models/geometry.py:122-130, models/texture.py:23-30): network half, then the grid backward. */
 int nsr_nerf_field_bwd_net(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
                            const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
                            const int64_t* k_dev, const float* xyzdir, void* denc_h, void* stream);
 int nsr_nerf_table_scatter(const nsr_grid_t* g, const float* xyz, int32_t stride, const void* denc_h, float loss_scale, const float* amax,
-                           float* grad_table, int64_t k, const int64_t* k_dev, void* stream);
+                           float* grad_table, int64_t k, const int64_t* k_dev, int32_t level_begin, int32_t level_end, int32_t ctas_per_sm,
+                           void* stream);
 
 
 /* ---- persistent per-ray kernels (the default fused path) -------------------------------------------------------
@@ -402,6 +404,12 @@ int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* multicast_ptr, 
  *   this rank's buffer any more. */
 int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
                           int32_t* err_dev, int32_t rank, int32_t world, int64_t n, void* stream);
+/* the same over floats [begin, begin + count) of the buffer (both multiples of 4 * world), on `channel` (0..3: own flag slots
+ * [32 + 32 channel, 64 + 32 channel) of a 256-int32 flag array and own epoch_counter_dev pair) so that exchanges of different ranges may be
+ * in flight at the same time on different streams; ctas_per_sm: 0 = default. */
+int nsr_p2p_exchange_mean_range(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
+                                int32_t* err_dev, int32_t rank, int32_t world, int64_t begin, int64_t count, int32_t channel, int32_t ctas_per_sm,
+                                void* stream);
 
 /* ---- occupancy-grid refresh (nerfacc OccupancyGrid._update behind every_n_step: models/nerf.py:45-55,
  * models/neus.py:79-111).  The caller draws the cells (int64 flat indices ix*R*R + iy*R + iz; NULL = every cell once) and the

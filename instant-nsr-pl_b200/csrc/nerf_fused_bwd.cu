@@ -394,7 +394,7 @@ constexpr int kMergeLevels = 8;
 __global__ void __launch_bounds__(256) nerf_table_scatter_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ xyz, int stride,
                                                                  const __half2* __restrict__ denc, float loss_scale,
                                                                  const float* __restrict__ amax_ptr, float* __restrict__ grad_table,
-                                                                 int64_t n_cap, const int64_t* __restrict__ n_dev) {
+                                                                 int64_t n_cap, const int64_t* __restrict__ n_dev, int l_begin, int l_end) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   if (loss_scale <= 0.f) {  // the same automatic scale as nerf_bwd_kernel derives from the same amax
     const float amax = fmaxf(__ldg(amax_ptr), 1e-30f);
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) nerf_table_scatter_kernel(const __grid_co
       z = xyz[i * stride + 2];
     }
 #pragma unroll 1
-    for (int l = 0; l < 16; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {  // the data-parallel step scatters level groups in separate launches (gradient exchange overlap)
       float2 d = make_float2(0.f, 0.f);
       if (ok) {
         d = __half22float2(denc[i * 16 + l]);
@@ -519,7 +519,7 @@ extern "C" int nsr_nerf_field_bwd(const nsr_nerf_t* f, const float* rays, const 
 // duration in bench.py's per-kernel table):
 //   nsr_nerf_field_bwd_net   : MLP recompute + dgrad + wgrad over the packed rows; d(encoding) -> denc_h (fp16 [k,32], still multiplied by
 //                              the loss scale); grad_dparams receives only the density network's weight gradients
-//   nsr_nerf_table_scatter   : denc_h -> fp32 REDs into grad_table (= grad_dparams + the density network's parameter count); xyz = the
+//   nsr_nerf_table_scatter   : levels [level_begin, level_end) of denc_h -> fp32 REDs into grad_table (= grad_dparams + the density network's parameter count); xyz = the
 //                              packed unit-cube positions with row stride `stride` floats (6 for the xyzdir buffer of nsr_pack_kept)
 extern "C" int nsr_nerf_field_bwd_net(const nsr_nerf_t* f, const void* enc_k_h, const void* dparams_h, const void* cparams_h, const float* d_sraw,
                                       const float* d_rgb, float* grad_dparams, float* grad_cparams, float loss_scale, const float* amax, int64_t k,
@@ -530,15 +530,18 @@ extern "C" int nsr_nerf_field_bwd_net(const nsr_nerf_t* f, const void* enc_k_h, 
 }
 
 extern "C" int nsr_nerf_table_scatter(const nsr_grid_t* g, const float* xyz, int32_t stride, const void* denc_h, float loss_scale, const float* amax,
-                                      float* grad_table, int64_t k, const int64_t* k_dev, void* stream) {
+                                      float* grad_table, int64_t k, const int64_t* k_dev, int32_t level_begin, int32_t level_end, int32_t ctas_per_sm,
+                                      void* stream) {
   NSR_REQUIRE(g != nullptr && xyz != nullptr && denc_h != nullptr && grad_table != nullptr, "nsr_nerf_table_scatter: NULL argument");
   NSR_REQUIRE(g->n_levels == 16 && g->n_features == 2, "nsr_nerf_table_scatter: needs L=16, F=2");
   NSR_REQUIRE(loss_scale > 0.f || amax != nullptr, "nsr_nerf_table_scatter: loss_scale <= 0 (automatic) needs the amax pointer");
   NSR_REQUIRE(stride >= 3, "nsr_nerf_table_scatter: stride must be >= 3");
-  if (k == 0) return 0;
-  const int grid = (int)min((int64_t)nsr_sm_count() * 8, (k + 255) / 256);
-  nerf_table_scatter_kernel<<<k_dev ? nsr_sm_count() * 8 : grid, 256, 0, (cudaStream_t)stream>>>(*g, xyz, stride, (const __half2*)denc_h, loss_scale, amax,
-                                                                                                 grad_table, k, k_dev);
+  NSR_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= 16, "nsr_nerf_table_scatter: bad level range [%d, %d)", level_begin, level_end);
+  if (k == 0 || level_begin == level_end) return 0;
+  const int per_sm = ctas_per_sm >= 1 && ctas_per_sm <= 8 ? ctas_per_sm : 8;   // < 8 leaves room for a kernel running beside it (the exchange)
+  const int grid = (int)min((int64_t)nsr_sm_count() * per_sm, (k + 255) / 256);
+  nerf_table_scatter_kernel<<<k_dev ? nsr_sm_count() * per_sm : grid, 256, 0, (cudaStream_t)stream>>>(*g, xyz, stride, (const __half2*)denc_h, loss_scale,
+                                                                                                      amax, grad_table, k, k_dev, level_begin, level_end);
   NSR_CHECK_LAUNCH("nsr_nerf_table_scatter");
   return 0;
 }
@@ -554,7 +557,7 @@ extern "C" int nsr_nerf_field_bwd_split(const nsr_nerf_t* f, const void* enc_k_h
   if (rc != 0 || k == 0) return rc;
   const int grid = (int)min((int64_t)nsr_sm_count() * 8, (k + 255) / 256);
   nerf_table_scatter_kernel<<<k_dev ? nsr_sm_count() * 8 : grid, 256, 0, (cudaStream_t)stream>>>(f->grid, xyzdir, 6, (const __half2*)denc_h, loss_scale, amax,
-                                                                                                 grad_dparams + NF_DENSITY_PARAMS, k, k_dev);
+                                                                                                 grad_dparams + NF_DENSITY_PARAMS, k, k_dev, 0, 16);
   NSR_CHECK_LAUNCH("nsr_nerf_field_bwd_split (scatter)");
   return 0;
 }

@@ -117,16 +117,18 @@ __global__ void __launch_bounds__(256) p2p_allreduce_mean_multimem_kernel(float*
 //   exit  : every CTA fences its stores; the LAST CTA to finish (self-resetting counter) publishes "rank r is done reading and writing"
 //           and waits for the same from every peer, so kernel completion == every replica holds the complete mean and nobody still reads
 //           this rank's buffer (the next step may zero it).  The epoch lives in device memory => CUDA-graph replay safe.
-constexpr int kEntrySlot = 32, kExitSlot = 48;
+constexpr int kChannelSlot0 = 32, kChannelSlots = 32;   // flag slots of channel c: [32 + 32 c, 64 + 32 c)
 struct XchgArgs {
   float4* peer[kMaxWorld];
-  int32_t* flags[kMaxWorld];  // int32[64] per rank: [32, 48) entry epochs by source rank, [48, 64) exit epochs ([0, 16) belongs to nsr_p2p_barrier)
+  int32_t* flags[kMaxWorld];  // int32[256] per rank; [0, 16) belongs to nsr_p2p_barrier, channel c of this kernel owns [32 + 32 c, 64 + 32 c)
   float* mc;
   int32_t* epoch;    // last completed exchange
   int32_t* counter;  // CTAs that finished their share (returns to 0)
   int32_t* err;
   int rank, world;
-  int64_t n4;
+  int64_t n4;   // float4 elements of the range
+  int64_t o4;   // first float4 of the range
+  int slot;     // first flag slot of the channel: entry epochs [slot, slot + 16), exit epochs [slot + 16, slot + 32)
   float inv;
 };
 
@@ -151,17 +153,17 @@ __device__ __forceinline__ void xchg_wait(const XchgArgs& a, int slot0, int e) {
 }
 
 template <int U, bool MC>
-__global__ void __launch_bounds__(256) p2p_exchange_kernel(const XchgArgs a) {
+__global__ void __launch_bounds__(256, U <= 4 ? 4 : (U <= 8 ? 2 : 1)) p2p_exchange_kernel(const XchgArgs a) {
   __shared__ int s_last;
   const int e = *reinterpret_cast<volatile int32_t*>(a.epoch) + 1;  // every CTA reads it before the last one to finish advances it
   if (blockIdx.x == 0) {
     __threadfence_system();
-    xchg_signal_wait(a, kEntrySlot, e);
+    xchg_signal_wait(a, a.slot, e);
   }
-  xchg_wait(a, kEntrySlot, e);
+  xchg_wait(a, a.slot, e);
   __syncthreads();
   const int64_t chunk = (a.n4 + a.world - 1) / a.world;
-  const int64_t lo = a.rank * chunk, hi = min(a.n4, lo + chunk);
+  const int64_t lo = a.o4 + a.rank * chunk, hi = a.o4 + min(a.n4, (a.rank + 1) * chunk);
   const int64_t span = 256ll * U;
   for (int64_t base = lo + blockIdx.x * span; base < hi; base += (int64_t)gridDim.x * span) {
     float4 acc[U];
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const XchgArgs a) {
   __syncthreads();
   if (s_last) {
     __threadfence_system();
-    xchg_signal_wait(a, kExitSlot, e);
-    xchg_wait(a, kExitSlot, e);
+    xchg_signal_wait(a, a.slot + kMaxWorld, e);
+    xchg_wait(a, a.slot + kMaxWorld, e);
     __syncthreads();
     if (threadIdx.x == 0) {
       *a.counter = 0;
@@ -271,16 +273,20 @@ extern "C" int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* mult
   return 0;
 }
 
-// The whole exchange as ONE launch (see p2p_exchange_kernel).  flag_ptrs_host: every rank's peer-mapped flag array (int32[64], zeroed
-// once at start-up; slots [32, 64) are this entry point's); epoch_counter_dev: two local int32 {last completed epoch, CTA counter}, zeroed once; grid is capped at the number of
-// CTAs that are resident at once (the CTAs poll flags, so they must not wait for each other's SMs).
-extern "C" int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
-                                     int32_t* err_dev, int32_t rank, int32_t world, int64_t n, void* stream) {
+// The whole exchange as ONE launch (see p2p_exchange_kernel) over floats [begin, begin + count) of the symmetric buffer.  flag_ptrs_host: every
+// rank's peer-mapped flag array (int32[256], zeroed once at start-up; channel c owns slots [32 + 32 c, 64 + 32 c)); epoch_counter_dev: two local
+// int32 {last completed epoch, CTA counter} PER CHANNEL, zeroed once.  Exchanges on different channels may run concurrently (different
+// streams); the grid is capped at the number of CTAs that are resident at once (the CTAs poll flags, so they must not wait for each
+// other's SMs).
+extern "C" int nsr_p2p_exchange_mean_range(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
+                                           int32_t* err_dev, int32_t rank, int32_t world, int64_t begin, int64_t count, int32_t channel,
+                                           int32_t ctas_per_sm, void* stream) {
   NSR_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "nsr_p2p_exchange_mean: bad rank / world (max %d)", kMaxWorld);
-  NSR_REQUIRE(n % 4 == 0, "nsr_p2p_exchange_mean: n must be a multiple of 4 floats");
+  NSR_REQUIRE(begin % 4 == 0 && count % 4 == 0 && begin >= 0 && count >= 0, "nsr_p2p_exchange_mean: begin / count must be multiples of 4 floats");
+  NSR_REQUIRE(channel >= 0 && channel < 4, "nsr_p2p_exchange_mean: channel must be 0..3");
   NSR_REQUIRE(peer_ptrs_host != nullptr && flag_ptrs_host != nullptr && epoch_counter_dev != nullptr && err_dev != nullptr,
               "nsr_p2p_exchange_mean: NULL argument");
-  if (n == 0 || world == 1) return 0;
+  if (count == 0 || world == 1) return 0;
   XchgArgs a;
   for (int q = 0; q < kMaxWorld; ++q) {
     a.peer[q] = q < world ? reinterpret_cast<float4*>(peer_ptrs_host[q]) : nullptr;
@@ -292,20 +298,40 @@ extern "C" int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint6
   a.err = err_dev;
   a.rank = rank;
   a.world = world;
-  a.n4 = n / 4;
+  a.n4 = count / 4;
+  a.o4 = begin / 4;
+  a.slot = kChannelSlot0 + kChannelSlots * channel;
   a.inv = 1.f / (float)world;
   const int64_t chunk = (a.n4 + world - 1) / world;
-  static const int ctas_per_sm = [] {   // tuning knob (default 2): NSR_P2P_CTAS_PER_SM=1..8 (all CTAs must be resident: 256 threads, <= 64 registers)
+  static const int env_ctas = [] {   // tuning knob: NSR_P2P_CTAS_PER_SM=1..8 (all CTAs must be resident: 256 threads, <= 64 registers)
     const char* v = getenv("NSR_P2P_CTAS_PER_SM");
-    const int n = v ? atoi(v) : 2;
-    return n >= 1 && n <= 8 ? n : 2;
+    const int n = v ? atoi(v) : 0;
+    return n >= 1 && n <= 8 ? n : 0;
   }();
-  constexpr int kU = 8;
-  const int grid = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * ctas_per_sm, (chunk + 256 * kU - 1) / (256 * kU)));
-  if (multicast_ptr != nullptr)
-    p2p_exchange_kernel<kU, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  else
-    p2p_exchange_kernel<4, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  const int per_sm = ctas_per_sm >= 1 && ctas_per_sm <= 8 ? ctas_per_sm : (env_ctas ? env_ctas : 2);
+  static const int env_u = [] {   // tuning knob: 16-byte columns in flight per thread (NSR_P2P_UNROLL = 4 | 8 | 16; default 8)
+    const char* v = getenv("NSR_P2P_UNROLL");
+    const int n = v ? atoi(v) : 8;
+    return n == 4 || n == 16 ? n : 8;
+  }();
+  // beside a scatter launch (ctas_per_sm == 1) the CTA must fit into the 16 K registers that launch leaves free: P2P form with 4 columns
+  const int u = (ctas_per_sm == 1 && multicast_ptr == nullptr) ? 4 : env_u;
+  const int grid_u = (int)max((int64_t)1, min((int64_t)nsr_sm_count() * per_sm, (chunk + 256 * u - 1) / (256 * u)));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (multicast_ptr != nullptr) {
+    if (u == 4) p2p_exchange_kernel<4, true><<<grid_u, 256, 0, st>>>(a);
+    else if (u == 16) p2p_exchange_kernel<16, true><<<grid_u, 256, 0, st>>>(a);
+    else p2p_exchange_kernel<8, true><<<grid_u, 256, 0, st>>>(a);
+  } else {
+    if (u == 4) p2p_exchange_kernel<4, false><<<grid_u, 256, 0, st>>>(a);
+    else if (u == 16) p2p_exchange_kernel<16, false><<<grid_u, 256, 0, st>>>(a);
+    else p2p_exchange_kernel<8, false><<<grid_u, 256, 0, st>>>(a);
+  }
   NSR_CHECK_LAUNCH("nsr_p2p_exchange_mean");
   return 0;
+}
+
+extern "C" int nsr_p2p_exchange_mean(const uint64_t* peer_ptrs_host, const uint64_t* flag_ptrs_host, void* multicast_ptr, int32_t* epoch_counter_dev,
+                                     int32_t* err_dev, int32_t rank, int32_t world, int64_t n, void* stream) {
+  return nsr_p2p_exchange_mean_range(peer_ptrs_host, flag_ptrs_host, multicast_ptr, epoch_counter_dev, err_dev, rank, world, 0, n, 0, 0, stream);
 }

@@ -174,8 +174,15 @@ class _NerfRenderRays(torch.autograd.Function):
                     denc = torch.empty(cap, 32, dtype=torch.float16, device=dev)
                     lib.call('nsr_nerf_field_bwd_net', fused.ref(), ptr(enc_k), ptr(dh), ptr(ch), ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc),
                              float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]), ptr(xyzdir), ptr(denc), stream())
-                    lib.call('nsr_nerf_table_scatter', ctypes.byref(fused.struct.grid), ptr(xyzdir), 6, ptr(denc), float(fused.loss_scale), ptr(amax),
-                             ptr(gd[fused.net.mlp.n_params:]), cap, ptr(offsets_k[n:]), stream())
+                    # table half; data-parallel runs scatter level groups in separate launches and hand each finished group to the gradient
+                    # exchange (parallel.P2PGradSync.bind_pipelined), whose kernel runs beside the next group's scatter (which leaves it one CTA slot per SM)
+                    groups = fused.level_groups or ((0, 16),)
+                    for gi, (l0, l1) in enumerate(groups):
+                        lib.call('nsr_nerf_table_scatter', ctypes.byref(fused.struct.grid), ptr(xyzdir), 6, ptr(denc), float(fused.loss_scale), ptr(amax),
+                                 ptr(gd[fused.net.mlp.n_params:]), cap, ptr(offsets_k[n:]), l0, l1, 4 if (fused.exchange_hook is not None and gi > 0) else 0,
+                                 stream())
+                        if fused.exchange_hook is not None:
+                            fused.exchange_hook(gi)
                 else:
                     lib.call('nsr_nerf_field_bwd', fused.ref(), ptr(rays), ptr(ri), ptr(ts), ptr(te), ptr(enc_k if packed else enc), ptr(dh), ptr(ch),
                              ptr(d_sraw), ptr(d_rgb), ptr(gd), ptr(gc), float(fused.loss_scale), ptr(amax), cap, ptr(offsets_k[n:]),
@@ -222,6 +229,8 @@ class NerfFused:
         # (gd, gc) flat fp32 buffers the backward zeroes and accumulates into INSTEAD of handing gradients to autograd (per-ray path only;
         # set by parallel.P2PGradSync.bind_direct: the buffers are views of the peer-mapped exchange buffer and become .grad after the exchange)
         self.direct_grads = None
+        self.level_groups = None    # ((l0, l1), ...): the split backward's table scatter as one launch per level group (top levels first)
+        self.exchange_hook = None   # callable(group index): called behind each group's scatter launch (the gradient exchange of that group)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
 
     @staticmethod

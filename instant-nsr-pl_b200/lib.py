@@ -108,6 +108,7 @@ _SIGNATURES = {
     'nsr_p2p_barrier': [P, P, P, I32, I32, P],
     'nsr_p2p_allreduce_mean': [P, P, I32, I32, I64, P],
     'nsr_p2p_exchange_mean': [P, P, P, P, P, I32, I32, I64, P],
+    'nsr_p2p_exchange_mean_range': [P, P, P, P, P, I32, I32, I64, I64, I32, I32, P],
     'nsr_occgrid_points': [P, P, P, P, P, I64, P],
     'nsr_occgrid_update': [P, P, P, P, F32, P, I64, I64, P],
     'nsr_occgrid_binarize': [P, P, F32, P, P, P, I32, I64, P],
@@ -128,7 +129,7 @@ _SIGNATURES = {
     'nsr_nerf_field_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
     'nsr_nerf_field_bwd_split': [P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
     'nsr_nerf_field_bwd_net': [P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
-    'nsr_nerf_table_scatter': [P, P, I32, P, F32, P, P, I64, P, P],
+    'nsr_nerf_table_scatter': [P, P, I32, P, F32, P, P, I64, P, I32, I32, I32, P],
     'nsr_nerf_field_bwd_tc': [P, P, P, P, P, P, P, P, F32, P, I64, P, P, P, P],
 }
 

@@ -54,6 +54,7 @@ class P2PGradSync:
         import ctypes
         import torch.distributed._symmetric_memory as symm
         self.params = [p for p in params if p.requires_grad and p.numel() > 0]
+        self.params.sort(key=lambda p: p.numel())   # the hash table (largest) LAST: its level groups are then contiguous tails of the buffer
         if not self.params or not self.params[0].is_cuda:
             raise RuntimeError('P2PGradSync needs CUDA parameters')
         group = group if group is not None else dist.group.WORLD
@@ -65,12 +66,13 @@ class P2PGradSync:
         self.n = (sum(sizes) + 4 * self.world - 1) // (4 * self.world) * (4 * self.world)   # equal float4 chunks per rank
         self.buf = symm.empty(self.n, dtype=torch.float32, device=dev)
         self.hdl = symm.rendezvous(self.buf, group)
-        self.flags = symm.empty(64, dtype=torch.int32, device=dev)
+        self.flags = symm.empty(256, dtype=torch.int32, device=dev)   # [0,16) nsr_p2p_barrier, channel c of nsr_p2p_exchange_mean_range [32 + 32 c, 64 + 32 c)
         self.fhdl = symm.rendezvous(self.flags, group)
         self.buf.zero_()
         self.flags.zero_()
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.epoch2 = torch.zeros(2, dtype=torch.int32, device=dev)   # one-launch exchange: {last completed epoch, CTA counter}
+        self.epoch2 = torch.zeros(4, 2, dtype=torch.int32, device=dev)   # one-launch exchange, per channel: {last completed epoch, CTA counter}
+        self.ranges, self.side, self._pending = None, [], []
         self.direct = set()
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.views, off = [], 0
@@ -108,6 +110,57 @@ class P2PGradSync:
         fused.direct_grads = (self.view_of(net), self.view_of(cnet))
         self.direct = {id(net), id(cnet)}
 
+    def bind_pipelined(self, fused, level_groups=((12, 16), (8, 12), (0, 8))):
+        """bind_direct + overlap: the fused backward scatters the table gradient level group by level group (highest levels first) and calls
+        ``exchange_group(i)`` behind each launch; the exchange of a finished group runs on a side stream beside the next group's scatter
+        (the scatter launches leave one CTA slot per SM free for it), the last range -- everything below the first groups: the other
+        parameters, the network weights, the coarse levels -- runs on the main stream, which then joins the side streams.
+        What DDP does with gradient buckets (launch.py:98), for the one big tensor of this model."""
+        self.bind_direct(fused)
+        net = fused.net
+        if self.params[-1] is not net.params:
+            raise RuntimeError('bind_pipelined: the hash-grid parameter must be the largest parameter of the exchange')
+        groups = [tuple(g) for g in level_groups]
+        ok = groups and groups[0][1] == 16 and groups[-1][0] == 0 and all(groups[i][0] == groups[i + 1][1] for i in range(len(groups) - 1))
+        if not ok or len(groups) > 4:
+            raise ValueError('level_groups must partition [0, 16) from the top down in at most 4 groups, e.g. ((12, 16), (8, 12), (0, 8))')
+        base = self.view_of(net.params).data_ptr() - self.buf.data_ptr()
+        assert base % 16 == 0
+        off = lambda l: base // 4 + net.mlp.n_params + 2 * int(fused.grid.offset[l])   # first float of level l inside the symmetric buffer
+        self.ranges = []
+        for i, (l0, l1) in enumerate(groups):
+            begin = 0 if i == len(groups) - 1 else off(l0)
+            end = self.n if i == 0 else off(l1)
+            assert begin % 4 == 0 and end % 4 == 0
+            self.ranges.append((begin, end - begin))
+        self.side = [torch.cuda.Stream(device=self.buf.device) for _ in groups[:-1]]
+        fused.level_groups = groups
+        fused.exchange_hook = self.exchange_group
+
+    def exchange_group(self, i):
+        """exchange of range i (called by the backward right behind the scatter launch of level group i)"""
+        import ctypes
+        from .lib import lib, ptr
+        mc = ctypes.c_void_p(self.multicast) if self.multicast else None
+        begin, count = self.ranges[i]
+        cur = torch.cuda.current_stream()
+        last = i == len(self.ranges) - 1
+        st = cur if last else self.side[i]
+        if not last:
+            st.wait_stream(cur)
+        lib.call('nsr_p2p_exchange_mean_range', self._peer, self._fpeer, mc, ptr(self.epoch2[i]), ptr(self.err), self.rank, self.world, begin, count,
+                 i, 1 if not last else 0, ctypes.c_void_p(st.cuda_stream))
+        if last:
+            for sd in self.side:
+                cur.wait_stream(sd)
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+
+    def finish(self):
+        """post-backward hook of the pipelined mode: the exchanges were launched from inside the backward; gradients are the views"""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
     def all_reduce_mean(self):
         import ctypes
         from .lib import lib, ptr, stream
@@ -120,7 +173,7 @@ class P2PGradSync:
                 v.copy_(p.grad)
         mc = ctypes.c_void_p(self.multicast) if self.multicast else None
         if self.one_launch:
-            lib.call('nsr_p2p_exchange_mean', self._peer, self._fpeer, mc, ptr(self.epoch2), ptr(self.err), self.rank, self.world, self.n, stream())
+            lib.call('nsr_p2p_exchange_mean', self._peer, self._fpeer, mc, ptr(self.epoch2[0]), ptr(self.err), self.rank, self.world, self.n, stream())
         else:
             bar = lambda: lib.call('nsr_p2p_barrier', self._fpeer, ptr(self.epoch), ptr(self.err), self.rank, self.world, stream())
             bar()

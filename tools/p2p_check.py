@@ -61,6 +61,26 @@ try:
             ts.append(e0.elapsed_time(e1))
         out[variant + '_no_copy_ms'] = round(sorted(ts[2:])[len(ts[2:]) // 2], 4)
         sync.check()
+        # three ranges on three channels, two of them on side streams (what bind_pipelined does), against the NCCL result
+        import ctypes
+        from nsr_b200.lib import lib, ptr
+        for p, x in zip(params, grads):
+            sync.view_of(p).copy_(x)
+        torch.cuda.synchronize(); dist.barrier()
+        cuts = [0, (sync.n // 3) // (4 * world) * (4 * world), (2 * sync.n // 3) // 64 * 64, sync.n]
+        mcp = ctypes.c_void_p(sync.multicast) if sync.multicast else None
+        side = [torch.cuda.Stream(), torch.cuda.Stream()]
+        cur = torch.cuda.current_stream()
+        for ch in (2, 1, 0):
+            st = cur if ch == 0 else side[ch - 1]
+            st.wait_stream(cur)
+            lib.call('nsr_p2p_exchange_mean_range', sync._peer, sync._fpeer, mcp, ptr(sync.epoch2[ch]), ptr(sync.err), sync.rank, sync.world,
+                     cuts[ch], cuts[ch + 1] - cuts[ch], ch, 1, ctypes.c_void_p(st.cuda_stream))
+        for sd in side:
+            cur.wait_stream(sd)
+        torch.cuda.synchronize()
+        sync.check()
+        out[variant + '_ranges_max_err'] = max(float((sync.view_of(p) - r).abs().max()) for p, r in zip(params, ref))
 except Exception as e:
     out['error'] = f'{type(e).__name__}: {e}'[:300]
 print(json.dumps(out), flush=True)
