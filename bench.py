@@ -594,7 +594,7 @@ def gpu_arm(args):
     with torch.no_grad():
         for j in range(POOL):
             o = model.forward_(rays_dev[j], static=True)
-            tot = (o['offsets_loose'][1:] - o['offsets_loose'][:-1]).double()
+            tot = o['counts_loose'].double()
             kp = (o['offsets_packed'][1:] - o['offsets_packed'][:-1]).double()
             evaluated += float(torch.where(kp < tot, torch.minimum(tot, (torch.floor(kp / 32) + 1) * 32), tot).sum()) / POOL
     alg = {'nsr_nerf_prepass': 512.0 * m1, 'nsr_nerf_render_fwd': 512.0 * k1, 'nsr_nerf_field_bwd': 512.0 * k1,

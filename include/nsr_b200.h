@@ -186,6 +186,13 @@ int nsr_accumulate(const float* weights, const float* values, const int64_t* off
  * stores the per-ray occupancy masks [n_rays, words], t_min and the per-ray sample counts.
  * nsr_scan_counts_order: exclusive scan of the counts + a longest-rays-first processing order (rays bucketed by their
  * number of 32-sample chunks) for the per-ray kernel.  nsr_march_rays_expand turns the masks into packed samples. */
+/* nsr_march_rays_alloc: nsr_march_rays_mask + slice allocation + queue binning in the same launch (replaces nsr_scan_counts_order):
+ *   offsets[ray] = atomic reservation of counts[ray] rows (completion order, not ray order; *alloc_total (uint64, zero on entry) ends as the
+ *   number of marched samples); bin_counts int32[8] (zero on entry) / order_bins int32[8 * n]: rays grouped by 32-sample chunk count
+ *   (>= 17, 13-16, 9-12, 5-8, 3-4, 2, 1, 0), the queue of nsr_nerf_rays_fwd (pass counts + bin_counts there). */
+int nsr_march_rays_alloc(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
+                         uint32_t* masks, int32_t words, float* t_min, int32_t* counts, int64_t* offsets, void* alloc_total,
+                         int32_t* bin_counts, int32_t* order_bins, int64_t n, void* stream);
 int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
                         uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts, int64_t n_rays, void* stream);
 int nsr_scan_counts_order(const int32_t* counts, int64_t* offsets, int32_t* order, int64_t n, void* stream);
@@ -266,7 +273,8 @@ int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* ma
                       const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h,
                       const void* cparams_h,
                       void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx, float* acc_rgb,
-                      float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays, void* stream);
+                      float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays, const int32_t* counts,
+                      const int32_t* bin_counts, void* stream);
 /* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
 int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                   const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k /* may be NULL */,

@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
                                                                            const uint32_t* __restrict__ bits,
                                                                            const uint32_t* __restrict__ coarse, uint32_t* __restrict__ masks,
                                                                            int words, float* __restrict__ t_min_out,
-                                                                           int32_t* __restrict__ counts, int64_t n_rays) {
+                                                                           int32_t* __restrict__ counts, int64_t n_rays,
+                                                                           int64_t* __restrict__ offsets, unsigned long long* __restrict__ alloc_total,
+                                                                           int32_t* __restrict__ bin_counts, int32_t* __restrict__ order_bins) {
   __shared__ uint32_t s_coarse[1024];  // (R/4)^3 bits, R <= 128
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Rc = p.res >> 2;
@@ -237,6 +239,14 @@ __global__ void __launch_bounds__(kMarchWarps * 32) march_rays_mask_kernel(nsr_m
     if (lane == 0) {
       counts[ray] = cnt;
       t_min_out[ray] = tmin;
+      if (alloc_total != nullptr) {
+        // nsr_march_rays_alloc: the ray reserves its slice of the sample buffers and its place in the longest-rays-first queue HERE (two
+        // atomics per ray) instead of in a one-CTA scan kernel behind the marcher.  The slices are then in completion order, not ray order:
+        // every consumer addresses samples as offsets[ray] + j, the ray-ordered view is the PACKED one (nsr_pack_kept).
+        offsets[ray] = (int64_t)atomicAdd(alloc_total, (unsigned long long)cnt);
+        const int b = nsr_chunk_bin(cnt);
+        order_bins[(int64_t)b * n_rays + atomicAdd(bin_counts + b, 1)] = (int32_t)ray;
+      }
     }
   }
 }
@@ -341,6 +351,24 @@ extern "C" int nsr_scan_counts_order(const int32_t* counts, int64_t* offsets, in
   return launch_scan(counts, offsets, order, n, (cudaStream_t)stream, "nsr_scan_counts_order");
 }
 
+// march + slice allocation + queue binning in one launch (see march_rays_mask_kernel).  alloc_total (uint64, zero on entry) ends as the number
+// of marched samples; bin_counts int32[8] (zero on entry) / order_bins int32[8 * n]: rays grouped by 32-sample chunk count, longest group first.
+extern "C" int nsr_march_rays_alloc(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits, const uint32_t* coarse_bits,
+                                    uint32_t* masks, int32_t words, float* t_min, int32_t* counts, int64_t* offsets, void* alloc_total,
+                                    int32_t* bin_counts, int32_t* order_bins, int64_t n, void* stream) {
+  NSR_REQUIRE(p != nullptr && p->contraction == 0 && p->cone_angle == 0.f, "nsr_march_rays_alloc: AABB roi and cone_angle == 0 only");
+  NSR_REQUIRE(p->step > 0.f && p->res >= 1 && p->res <= 1024, "nsr_march_rays_alloc: bad step / resolution");
+  NSR_REQUIRE(coarse_bits == nullptr || (p->res % 4 == 0 && p->res <= 128), "nsr_march_rays_alloc: coarse bits need res %% 4 == 0, res <= 128");
+  NSR_REQUIRE(offsets != nullptr && alloc_total != nullptr && bin_counts != nullptr && order_bins != nullptr, "nsr_march_rays_alloc: NULL output");
+  NSR_REQUIRE(words >= 1, "nsr_march_rays_alloc: words must be >= 1");
+  if (n == 0) return 0;
+  march_rays_mask_kernel<<<nsr_blocks(n, kMarchWarps), kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, rays, jitter, bits, coarse_bits, masks, words, t_min,
+                                                                                                  counts, n, offsets, (unsigned long long*)alloc_total,
+                                                                                                  bin_counts, order_bins);
+  NSR_CHECK_LAUNCH("nsr_march_rays_alloc");
+  return 0;
+}
+
 extern "C" int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, const float* jitter, const uint32_t* bits,
                                    const uint32_t* coarse_bits, uint32_t* masks, int32_t words, float* t_min_out, int32_t* counts,
                                    int64_t n_rays, void* stream) {
@@ -351,7 +379,7 @@ extern "C" int nsr_march_rays_mask(const nsr_march_t* p, const float* rays, cons
   if (n_rays == 0) return 0;
   const int64_t blocks = (n_rays + kMarchWarps - 1) / kMarchWarps;
   march_rays_mask_kernel<<<(int)blocks, kMarchWarps * 32, 0, (cudaStream_t)stream>>>(*p, rays, jitter, bits, coarse_bits, masks, words,
-                                                                                     t_min_out, counts, n_rays);
+                                                                                     t_min_out, counts, n_rays, nullptr, nullptr, nullptr, nullptr);
   NSR_CHECK_LAUNCH("nsr_march_rays_mask");
   return 0;
 }

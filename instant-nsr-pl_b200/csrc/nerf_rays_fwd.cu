@@ -28,7 +28,9 @@ struct RaysFwdArgs {
   const uint32_t* masks;       // [n_rays, words]
   const float* t_min;          // [n_rays]
   const int64_t* offsets_m;    // [n_rays+1] marched offsets (loose layout base of every ray)
-  const int32_t* order;        // [n_rays] processing order (longest rays first) or NULL
+  const int32_t* order;        // [n_rays] processing order (longest rays first) or NULL; with bin_counts: [8][n_rays] rays grouped by chunk count
+  const int32_t* bin_counts;   // int32[8] (nsr_march_rays_alloc) or NULL
+  const int32_t* counts;       // [n_rays] marched samples per ray, or NULL: offsets_m[ray + 1] - offsets_m[ray]
   const __half* dparams;
   const __half* cparams;
   __half* enc_save;            // [cap,32] or NULL
@@ -74,18 +76,32 @@ __global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __g
   const __half2* table = reinterpret_cast<const __half2*>(a.dparams + NF_DENSITY_PARAMS);
   nf_stage_weights(smem, a.dparams, a.cparams, true);
   __syncthreads();
+  int bins[NSR_ORDER_BINS];   // binned queue: ticket t belongs to the first group whose running total exceeds it
+#pragma unroll
+  for (int b = 0; b < NSR_ORDER_BINS; ++b) bins[b] = a.bin_counts != nullptr ? __ldg(a.bin_counts + b) : 0;
 
   for (;;) {
     int64_t ray = 0;
     if (lane == 0) ray = atomicAdd(a.ticket, 1u);
     ray = __shfl_sync(0xffffffffu, ray, 0);
     if (ray >= a.n_rays) break;
-    if (a.order != nullptr) ray = __ldg(a.order + ray);
+    if (a.bin_counts != nullptr) {
+      int t = (int)ray, b = 0;
+#pragma unroll
+      for (int q = 0; q < NSR_ORDER_BINS - 1; ++q) {
+        const bool next = b == q && t >= bins[q];
+        t -= next ? bins[q] : 0;
+        b += next ? 1 : 0;
+      }
+      ray = __ldg(a.order + (int64_t)b * a.n_rays + t);
+    } else if (a.order != nullptr) {
+      ray = __ldg(a.order + ray);
+    }
     // ---- the ray's occupancy mask: lane w holds words w and w+32
     const uint32_t mw0 = lane < a.words ? __ldg(a.masks + ray * a.words + lane) : 0u;
     const uint32_t mw1 = lane + 32 < a.words ? __ldg(a.masks + ray * a.words + lane + 32) : 0u;
     const int64_t base = a.offsets_m[ray];
-    const int total = (int)(a.offsets_m[ray + 1] - base);
+    const int total = a.counts != nullptr ? __ldg(a.counts + ray) : (int)(a.offsets_m[ray + 1] - base);
     float o_acc = 0.f, d_acc = 0.f, r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
     int kept = 0;
     if (total > 0) {
@@ -394,7 +410,8 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
                                  const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
                                  void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx,
                                  float* acc_rgb, float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays,
-                                 void* stream) {
+                                 const int32_t* counts, const int32_t* bin_counts, void* stream) {
+  NSR_REQUIRE(bin_counts == nullptr || (order != nullptr && counts != nullptr), "nsr_nerf_rays_fwd: the binned queue needs order [8][n] and counts");
   NSR_REQUIRE(f != nullptr && f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 &&
                   f->color_hidden == 2,
               "nsr_nerf_rays_fwd: fused path needs L=16, F=2, feature_dim=16, hidden layers 1/2");
@@ -416,7 +433,7 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
     attr_set = true;
   }
   RaysFwdArgs a;
-  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order;
+  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order; a.bin_counts = bin_counts; a.counts = counts;
   a.dparams = (const __half*)dparams_h; a.cparams = (const __half*)cparams_h; a.enc_save = (__half*)enc_save_h;
   a.sigmas = sigmas; a.rgbs = rgbs; a.weights = weights; a.trans = trans; a.kidx_out = kidx;
   a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.ticket = ticket;

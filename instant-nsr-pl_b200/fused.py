@@ -90,22 +90,30 @@ class _NerfRenderRays(torch.autograd.Function):
         f32 = lambda *k: torch.empty(*k, dtype=torch.float32, device=dev)
         i64 = lambda k: torch.empty(k, dtype=torch.int64, device=dev)
         words = (fused.cap_per_ray + 31) // 32
-        masks, t_min, counts, order = i32(n * words), f32(n), i32(n), i32(n)
-        offsets_m = i64(n + 1)
-        lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), n, stream())
-        lib.call('nsr_scan_counts_order', ptr(counts), ptr(offsets_m), ptr(order), n, stream())
+        masks, t_min, counts = i32(n * words), f32(n), i32(n)
+        # one fill: the forward's ray ticket, the backward's gradient amax, the marcher's row allocator and its 8 queue-group counters
+        zz = torch.zeros(12, dtype=torch.int32, device=dev)
+        tick, amax0, m_total, bin_counts = zz[0:1], zz[1:2].view(torch.float32), zz[2:4].view(torch.int64), zz[4:12]
+        if fused.march_alloc:
+            # the marcher reserves every ray's rows and its place in the longest-first queue itself (atomics): no scan kernel behind it
+            offsets_m, order = i64(n), i32(8 * n)
+            lib.call('nsr_march_rays_alloc', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), ptr(offsets_m),
+                     ptr(m_total), ptr(bin_counts), ptr(order), n, stream())
+        else:
+            offsets_m, order = i64(n + 1), i32(n)
+            lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), n, stream())
+            lib.call('nsr_scan_counts_order', ptr(counts), ptr(offsets_m), ptr(order), n, stream())
+            m_total = offsets_m[n:]
         need_grad = dparams.requires_grad or cparams.requires_grad
         enc = torch.empty(cap, 32, dtype=torch.float16, device=dev) if need_grad else None
         sig, rgbs, weights, trans, kidx = f32(cap), f32(cap, 3), f32(cap), f32(cap), i32(cap)
         acc_rgb, opacity, depth, kept = f32(n, 3), f32(n, 1), f32(n, 1), i32(n)
         offsets_k = i64(n + 1)
         dh, ch = fused.dparams_half(), fused.cparams_half()
-        zz = torch.zeros(2, dtype=torch.int32, device=dev)   # one fill: the forward's ray ticket + the backward's gradient amax
-        tick, amax0 = zz[0:1], zz[1:2].view(torch.float32)
         step = float(m.render_step_size)
         lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
-                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, stream())
+                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, ptr(counts), ptr(bin_counts) if fused.march_alloc else None, stream())
         if not fused.fuse_kept_scan:
             lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
@@ -129,8 +137,8 @@ class _NerfRenderRays(torch.autograd.Function):
             enc = None   # the loose copy is not needed any more
         ctx.save_for_backward(rays, t_min, offsets_m, offsets_k, kept, enc, sig, rgbs, weights, trans, kidx, ri, ts, te, pos, dh, ch,
                               enc_k, xyzdir, amax0)
-        ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k)
-        return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k
+        ctx.mark_non_differentiable(ri, ts, te, pos, offsets_m, offsets_k, m_total, counts)
+        return acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, m_total, counts
 
     @staticmethod
     def backward(ctx, g_rgb, g_op, g_depth, g_w, *_):
@@ -228,6 +236,8 @@ class NerfFused:
         self._tc_status = None
         # (gd, gc) flat fp32 buffers the backward zeroes and accumulates into INSTEAD of handing gradients to autograd (per-ray path only;
         # set by parallel.P2PGradSync.bind_direct: the buffers are views of the peer-mapped exchange buffer and become .grad after the exchange)
+        # the marcher allocates every ray's rows and queue slot itself (nsr_march_rays_alloc) instead of a one-CTA scan kernel behind it
+        self.march_alloc = os.environ.get('NSR_MARCH_ALLOC', '1') == '1'
         self.direct_grads = None
         self.level_groups = None    # ((l0, l1), ...): the split backward's table scatter as one launch per level group (top levels first)
         self.exchange_hook = None   # callable(group index): called behind each group's scatter launch (the gradient exchange of that group)
@@ -327,10 +337,10 @@ class NerfFused:
         rays = contig(rays, torch.float32)
         if self.mode == 'two_pass':
             return self._render_two_pass(rays, jitter, static)
-        acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k = _NerfRenderRays.apply(
+        acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, m_total, counts_m = _NerfRenderRays.apply(
             self.net.params, self.cnet.params, self, rays, jitter)
         n = rays.shape[0]
-        counts = (offsets_m[n:], offsets_k[n:])   # (marched, kept) on the device
+        counts = (m_total, offsets_k[n:])   # (marched, kept) on the device
         if static and self.lean_static_outputs:
             # graph capture with the fused loss: comp_rgb / rays_valid come out of nsr_nerf_loss_fwd, nothing else reads them
             out = {'opacity': opacity, 'depth': depth, 'num_samples_dev': counts[1]}
@@ -344,8 +354,10 @@ class NerfFused:
             if m.training:
                 # capacity-length buffers, first num_samples entries valid: packed t_starts / t_ends / ray_indices; `weights` is in the
                 # loose layout (ray r's kept samples at offsets_loose[r] + j); packed row j lives at loose position loose_pos[j]
+                # offsets_loose[r]: first row of ray r in the loose buffers (NOT monotonic in r when the marcher allocates, fused.march_alloc);
+                # counts_loose[r]: its marched samples
                 out.update({'weights': weights, 't_starts': ts, 't_ends': te, 'ray_indices': ri, 'loose_pos': pos,
-                            'offsets_loose': offsets_m, 'offsets_packed': offsets_k})
+                            'offsets_loose': offsets_m, 'counts_loose': counts_m, 'offsets_packed': offsets_k})
             return out
         n_marched, k = torch.cat(counts).tolist()
         self.last_stats = {'n_marched': n_marched, 'n_kept': k}
