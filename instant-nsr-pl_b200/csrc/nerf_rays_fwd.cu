@@ -75,10 +75,9 @@ __global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __g
   float* s_rgb = s_sig + 32;
   const __half2* table = reinterpret_cast<const __half2*>(a.dparams + NF_DENSITY_PARAMS);
   nf_stage_weights(smem, a.dparams, a.cparams, true);
+  __shared__ int bins[NSR_ORDER_BINS];   // binned queue: ticket t belongs to the first group whose running total exceeds it
+  if (threadIdx.x < NSR_ORDER_BINS) bins[threadIdx.x] = a.bin_counts != nullptr ? __ldg(a.bin_counts + threadIdx.x) : 0;
   __syncthreads();
-  int bins[NSR_ORDER_BINS];   // binned queue: ticket t belongs to the first group whose running total exceeds it
-#pragma unroll
-  for (int b = 0; b < NSR_ORDER_BINS; ++b) bins[b] = a.bin_counts != nullptr ? __ldg(a.bin_counts + b) : 0;
 
   for (;;) {
     int64_t ray = 0;
