@@ -90,6 +90,24 @@ class _NerfRenderRays(torch.autograd.Function):
         f32 = lambda *k: torch.empty(*k, dtype=torch.float32, device=dev)
         i64 = lambda k: torch.empty(k, dtype=torch.int64, device=dev)
         words = (fused.cap_per_ray + 31) // 32
+        need_grad = (dparams.requires_grad or cparams.requires_grad) and fused._want_grad   # (grad mode is always off inside Function.forward)
+        # The backward accumulates into zeroed flat gradient buffers (50 MB for the table).  Zero them NOW on a side stream: the fill runs
+        # beside the marcher / forward kernels instead of in front of the backward's first kernel; the backward joins the side stream.
+        ctx.grad_bufs = None
+        if need_grad and fused.prezero_grads:
+            cur = torch.cuda.current_stream()
+            side = fused.side_stream(dev)
+            if fused.direct_grads is not None:
+                gd0, gc0 = fused.direct_grads
+            else:
+                gd0, gc0 = torch.empty(fused.n_dparams, device=dev), torch.empty(fused.n_cparams, device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gd0.zero_()
+                gc0.zero_()
+            gd0.record_stream(side)
+            gc0.record_stream(side)
+            ctx.grad_bufs = (gd0, gc0, side)
         masks, t_min, counts = i32(n * words), f32(n), i32(n)
         # one fill: the forward's ray ticket, the backward's gradient amax, the marcher's row allocator and its 8 queue-group counters
         zz = torch.zeros(12, dtype=torch.int32, device=dev)
@@ -104,7 +122,6 @@ class _NerfRenderRays(torch.autograd.Function):
             lib.call('nsr_march_rays_mask', mref, ptr(rays), ptr(u), ptr(bits), ptr(coarse), ptr(masks), words, ptr(t_min), ptr(counts), n, stream())
             lib.call('nsr_scan_counts_order', ptr(counts), ptr(offsets_m), ptr(order), n, stream())
             m_total = offsets_m[n:]
-        need_grad = dparams.requires_grad or cparams.requires_grad
         enc = torch.empty(cap, 32, dtype=torch.float16, device=dev) if need_grad else None
         sig, rgbs, weights, trans, kidx = f32(cap), f32(cap, 3), f32(cap), f32(cap), i32(cap)
         acc_rgb, opacity, depth, kept = f32(n, 3), f32(n, 1), f32(n, 1), i32(n)
@@ -148,7 +165,11 @@ class _NerfRenderRays(torch.autograd.Function):
         n, cap = ctx.n_rays, ctx.cap
         step = float(fused.model.render_step_size)
         direct = fused.direct_grads
-        if direct is not None:   # accumulate straight into caller-owned buffers (the symmetric exchange buffer): autograd is bypassed
+        pre, ctx.grad_bufs = getattr(ctx, 'grad_bufs', None), None   # (a retained-graph second backward allocates fresh buffers below)
+        if pre is not None and (direct is None or pre[0] is direct[0]):
+            gd, gc, side = pre                     # zeroed on the side stream while the forward ran
+            torch.cuda.current_stream().wait_stream(side)
+        elif direct is not None:   # accumulate straight into caller-owned buffers (the symmetric exchange buffer): autograd is bypassed
             gd, gc = direct
             gd.zero_()
             gc.zero_()
@@ -239,6 +260,9 @@ class NerfFused:
         # the marcher allocates every ray's rows and queue slot itself (nsr_march_rays_alloc) instead of a one-CTA scan kernel behind it
         self.march_alloc = os.environ.get('NSR_MARCH_ALLOC', '1') == '1'
         self.direct_grads = None
+        self.prezero_grads = os.environ.get('NSR_PREZERO_GRADS', '1') == '1'   # zero the backward's gradient buffers beside the forward (side stream)
+        self._side = None
+        self._want_grad = True
         self.level_groups = None    # ((l0, l1), ...): the split backward's table scatter as one launch per level group (top levels first)
         self.exchange_hook = None   # callable(group index): called behind each group's scatter launch (the gradient exchange of that group)
         self.t_bound = 16.0     # bound on the ray parameter t for the loss-scale estimate (depth gradient term)
@@ -259,6 +283,9 @@ class NerfFused:
                   and isinstance(tex.network, tcnn.Network) and tex.network.mlp.n_hidden == 2 and tex.network.mlp.n_in == 32
                   and isinstance(tex.encoding.encoding, tcnn.Encoding) and tex.encoding.encoding.otype == 'SphericalHarmonics'
                   and not tex.encoding.include_xyz and tex.config.input_feature_dim == 16)
+            # the kernels hard-code ReLU hidden layers and a linear density output: anything else runs on the composed path
+            dm, cm = geo.encoding_with_network.mlp.struct, tex.network.mlp.struct
+            ok = ok and dm.activation == 1 and dm.out_activation == 0 and cm.activation == 1
             net_act = str(tex.network.network_config.get('output_activation', 'None')).lower()
             col_act = str(tex.config.get('color_activation', 'none')).lower()
             ok = ok and sorted([net_act, col_act]) == ['none', 'sigmoid']
@@ -268,6 +295,11 @@ class NerfFused:
 
     def ref(self):
         return ctypes.byref(self.struct)
+
+    def side_stream(self, dev):
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
 
     def ticket(self, dev):
         if self._ticket is None or self._ticket.device != dev:
@@ -337,6 +369,7 @@ class NerfFused:
         rays = contig(rays, torch.float32)
         if self.mode == 'two_pass':
             return self._render_two_pass(rays, jitter, static)
+        self._want_grad = torch.is_grad_enabled()
         acc_rgb, opacity, depth, weights, ri, ts, te, pos, offsets_m, offsets_k, m_total, counts_m = _NerfRenderRays.apply(
             self.net.params, self.cnet.params, self, rays, jitter)
         n = rays.shape[0]

@@ -67,6 +67,15 @@ class OccupancyGrid(nn.Module):
             state_dict.pop(prefix + k, None)
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
+    # ... and emit them on save, so that a checkpoint written here loads (strict) into a real nerfacc 0.3.3 OccupancyGrid
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        r = self._res
+        ar = torch.arange(r, device=self.occs.device)
+        coords = torch.stack(torch.meshgrid(ar, ar, ar, indexing='ij'), dim=-1).reshape(-1, 3)
+        destination[prefix + 'grid_coords'] = coords
+        destination[prefix + 'grid_indices'] = torch.arange(self.num_cells, device=self.occs.device)
+
     @property
     def roi_aabb(self):
         return self._roi_aabb

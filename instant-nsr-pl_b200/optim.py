@@ -81,13 +81,16 @@ class FusedAdamW(torch.optim.Optimizer):
                 h = AdamWT()
                 h.lr, h.beta1, h.beta2, h.eps, h.weight_decay = group['lr'], b1, b2, group['eps'], group['weight_decay']
                 h.inv_grad_scale = 1.0
+                # a skipped update (found_inf != 0, GradScaler semantics) must not advance the bias-correction step count
                 if self.capturable:
-                    st['lr_step'][1] += 1.0   # torch op: part of the captured graph
-                    st['step'] += 1.0
+                    inc = 1.0 if self.found_inf is None else (self.found_inf.reshape(()) == 0).to(torch.float32)
+                    st['lr_step'][1] += inc   # torch op: part of the captured graph
+                    st['step'] += inc
                     h.step, dev_state = 0, st['lr_step']
                 else:
-                    st['step'] += 1
-                    h.step, dev_state = int(st['step']), None
+                    if self.found_inf is None or float(self.found_inf) == 0.0:   # host mode: one read when a scaler is attached
+                        st['step'] += 1
+                    h.step, dev_state = max(int(st['step']), 1), None
                 half = None
                 mod = self._shadows.get(p)
                 if mod is not None:
