@@ -274,7 +274,7 @@ int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const uint32_t* ma
                       const void* cparams_h,
                       void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx, float* acc_rgb,
                       float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays, const int32_t* counts,
-                      const int32_t* bin_counts, void* stream);
+                      const int32_t* bin_counts, int32_t* kept_blocks, void* stream);
 /* loose -> packed copy of the kept samples (exact-size ray_indices / t_starts / t_ends / weights of the reference's dict). */
 int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const float* t_min, float step, const int32_t* kidx,
                   const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k, float* weights_k /* may be NULL */,
@@ -290,7 +290,9 @@ int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k, const floa
 int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
                        const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
                        float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h, void* enc_k_h,
-                       float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, void* stream);
+                       float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, const int32_t* kept_blocks, void* stream);
+/* (kept_blocks: NULL, or the per-256-ray sums of `kept` that nsr_nerf_rays_fwd accumulated -- the prefix sum then reads <= 32 + 255 values
+ * per CTA instead of n_rays.) */
 /* compositing backward on the loose layout (same math as nsr_nerf_ray_bwd; t from lattice index + t_min); offsets_k != NULL
  * writes d_sraw / d_rgb in packed row order (row offsets_k[ray] + j) instead of the loose positions. */
 int nsr_nerf_ray_bwd_loose(const int64_t* offsets_m, const int32_t* kept, const float* t_min, float step, const int32_t* kidx, const float* trans,

@@ -43,6 +43,7 @@ struct RaysFwdArgs {
   float* opacity;              // [n_rays]
   float* depth;                // [n_rays]
   int32_t* kept;               // [n_rays]
+  int32_t* kept_blocks;        // [ceil(n_rays / 256)] sums of kept over 256-ray blocks (zero on entry) or NULL: lets nsr_pack_kept_scan skip most of its prefix sum
   uint32_t* ticket;            // ray queue head (zero on entry)
   float step, early_stop_eps;
   int words;
@@ -63,9 +64,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// MINB = resident CTAs per SM the register allocation is sized for: 2 (default: 128 registers, no spills) or 3 (80 registers, ~0.5 KB of
-// spills per thread, 24 instead of 16 warps per SM to hide the gather latency; opt-in through NSR_FWD_CTAS=3 until it has been timed)
-template <int MINB>
+// MINB = resident CTAs per SM the register allocation is sized for: 2 (128 registers).  (A 3-CTA instantiation -- 80 registers, 0.5 KB of
+// spills per thread, 24 warps per SM -- was timed in round 2: 196 us against 131 us, and removed.)
+template <int MINB, int NB>
 __global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __grid_constant__ nsr_nerf_t P, const RaysFwdArgs a) {
   extern __shared__ __align__(16) __half smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __g
         if (valid) {
           const float x = (fmaf(dx, mid, ox) + P.radius) * inv, y = (fmaf(dy, mid, oy) + P.radius) * inv,
                       z = (fmaf(dz, mid, oz) + P.radius) * inv;
-          nf_gather_batched<16, 4>(P.grid, table, x, y, z, f);
+          nf_gather_batched<16, NB>(P.grid, table, x, y, z, f);   // NB levels = 8 NB loads per lane in flight
         } else {
 #pragma unroll
           for (int l = 0; l < 16; ++l) f[l] = 0u;
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, MINB) nerf_rays_fwd_kernel(const __g
       a.acc_rgb[ray * 3 + 1] = g_acc;
       a.acc_rgb[ray * 3 + 2] = b_acc;
       a.kept[ray] = kept;
+      if (a.kept_blocks != nullptr && kept > 0) atomicAdd(a.kept_blocks + (ray >> 8), kept);
     }
     __syncwarp();
   }
@@ -286,7 +288,8 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
                                                         float* __restrict__ ts_k, float* __restrict__ te_k, float* __restrict__ w_k,
                                                         int64_t* __restrict__ loose_pos, const __grid_constant__ nsr_nerf_t P,
                                                         const float* __restrict__ rays, const uint4* __restrict__ enc_loose,
-                                                        uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int enc_tiled, int64_t n_rays) {
+                                                        uint4* __restrict__ enc_k, float* __restrict__ xyzdir_k, int enc_tiled, int64_t n_rays,
+                                                        const int32_t* __restrict__ kept_blocks) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * 8ll + (threadIdx.x >> 5);
   int64_t dst, cnt;
@@ -294,7 +297,13 @@ __global__ void __launch_bounds__(256) pack_kept_kernel(const int64_t* __restric
     __shared__ int64_t s_part[8];
     const int64_t ray0 = blockIdx.x * 8ll;
     int64_t sum = 0;
-    for (int64_t r = threadIdx.x; r < ray0; r += 256) sum += __ldg(kept + r);
+    if (kept_blocks != nullptr) {  // whole 256-ray blocks in front come as sums from the forward kernel: <= 32 + 255 loads instead of n_rays
+      const int64_t nb = ray0 >> 8;
+      for (int64_t b = threadIdx.x; b < nb; b += 256) sum += __ldg(kept_blocks + b);
+      for (int64_t r = (nb << 8) + threadIdx.x; r < ray0; r += 256) sum += __ldg(kept + r);
+    } else {
+      for (int64_t r = threadIdx.x; r < ray0; r += 256) sum += __ldg(kept + r);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_part[threadIdx.x >> 5] = sum;
@@ -409,7 +418,7 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
                                  const int64_t* offsets_m, const int32_t* order, float step, float early_stop_eps, const void* dparams_h, const void* cparams_h,
                                  void* enc_save_h, float* sigmas, float* rgbs, float* weights, float* trans, int32_t* kidx,
                                  float* acc_rgb, float* opacity, float* depth, int32_t* kept, uint32_t* ticket, int64_t n_rays,
-                                 const int32_t* counts, const int32_t* bin_counts, void* stream) {
+                                 const int32_t* counts, const int32_t* bin_counts, int32_t* kept_blocks, void* stream) {
   NSR_REQUIRE(bin_counts == nullptr || (order != nullptr && counts != nullptr), "nsr_nerf_rays_fwd: the binned queue needs order [8][n] and counts");
   NSR_REQUIRE(f != nullptr && f->grid.n_levels == 16 && f->grid.n_features == 2 && f->feature_dim == 16 && f->density_hidden == 1 &&
                   f->color_hidden == 2,
@@ -417,14 +426,14 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
   NSR_REQUIRE(words >= 1 && words <= kMaxWords, "nsr_nerf_rays_fwd: words must be in [1,%d]", kMaxWords);
   NSR_REQUIRE(ticket != nullptr && kept != nullptr, "nsr_nerf_rays_fwd: ticket / kept are required");
   if (n_rays == 0) return 0;
-  static const int ctas_per_sm = [] {
-    const char* v = getenv("NSR_FWD_CTAS");
-    return (v != nullptr && v[0] == '3') ? 3 : 2;
+  static const int gather_batch = [] {   // levels whose 8 corner loads are issued together: 4 (default) or 8 (NSR_FWD_BATCH=8; 120 B of spills)
+    const char* v = getenv("NSR_FWD_BATCH");
+    return (v != nullptr && v[0] == '8') ? 8 : 4;
   }();
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = ctas_per_sm == 3 ? cudaFuncSetAttribute(nerf_rays_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)
-                                     : cudaFuncSetAttribute(nerf_rays_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(nerf_rays_fwd_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_rays_fwd_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
       nsr_set_error("nsr_nerf_rays_fwd: cannot reserve %zu B shared memory: %s", kSmemBytes, cudaGetErrorString(e));
       return 2;
@@ -432,17 +441,17 @@ extern "C" int nsr_nerf_rays_fwd(const nsr_nerf_t* f, const float* rays, const u
     attr_set = true;
   }
   RaysFwdArgs a;
-  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order; a.bin_counts = bin_counts; a.counts = counts;
+  a.rays = rays; a.masks = masks; a.t_min = t_min; a.offsets_m = offsets_m; a.order = order; a.bin_counts = bin_counts; a.counts = counts; a.kept_blocks = kept_blocks;
   a.dparams = (const __half*)dparams_h; a.cparams = (const __half*)cparams_h; a.enc_save = (__half*)enc_save_h;
   a.sigmas = sigmas; a.rgbs = rgbs; a.weights = weights; a.trans = trans; a.kidx_out = kidx;
   a.acc_rgb = acc_rgb; a.opacity = opacity; a.depth = depth; a.kept = kept; a.ticket = ticket;
   a.step = step; a.early_stop_eps = early_stop_eps; a.words = words; a.n_rays = n_rays;
   const int64_t want = (n_rays + kWarps - 1) / kWarps;
-  int grid = (int)min((int64_t)nsr_sm_count() * ctas_per_sm, want > 0 ? want : (int64_t)1);
-  if (ctas_per_sm == 3)
-    nerf_rays_fwd_kernel<3><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
+  int grid = (int)min((int64_t)nsr_sm_count() * 2, want > 0 ? want : (int64_t)1);
+  if (gather_batch == 8)
+    nerf_rays_fwd_kernel<2, 8><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
   else
-    nerf_rays_fwd_kernel<2><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
+    nerf_rays_fwd_kernel<2, 4><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(*f, a);
   NSR_CHECK_LAUNCH("nsr_nerf_rays_fwd");
   return 0;
 }
@@ -460,7 +469,7 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
   pack_kept_kernel<false><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, offsets_k, nullptr, nullptr, t_min, step, kidx, weights,
                                                                                    ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
                                                                                    f ? *f : dummy, rays, (const uint4*)enc_loose_h,
-                                                                                   (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays);
+                                                                                   (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays, nullptr);
   NSR_CHECK_LAUNCH("nsr_pack_kept");
   return 0;
 }
@@ -468,7 +477,7 @@ extern "C" int nsr_pack_kept(const int64_t* offsets_m, const int64_t* offsets_k,
 extern "C" int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept, int64_t* offsets_k_out, const float* t_min, float step,
                                   const int32_t* kidx, const float* weights, int32_t* ray_indices_k, float* t_starts_k, float* t_ends_k,
                                   float* weights_k, int64_t* loose_pos, const nsr_nerf_t* f, const float* rays, const void* enc_loose_h,
-                                  void* enc_k_h, float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, void* stream) {
+                                  void* enc_k_h, float* xyzdir_k, int32_t enc_tiled, int64_t n_rays, const int32_t* kept_blocks, void* stream) {
   NSR_REQUIRE(kept != nullptr && offsets_k_out != nullptr, "nsr_pack_kept_scan: kept / offsets_k_out is NULL");
   if (n_rays == 0) {
     cudaMemsetAsync(offsets_k_out, 0, sizeof(int64_t), (cudaStream_t)stream);
@@ -482,7 +491,7 @@ extern "C" int nsr_pack_kept_scan(const int64_t* offsets_m, const int32_t* kept,
   pack_kept_kernel<true><<<nsr_blocks(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(offsets_m, nullptr, kept, offsets_k_out, t_min, step, kidx, weights,
                                                                                   ray_indices_k, t_starts_k, t_ends_k, weights_k, loose_pos,
                                                                                   f ? *f : dummy, rays, (const uint4*)enc_loose_h,
-                                                                                  (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays);
+                                                                                  (uint4*)enc_k_h, xyzdir_k, enc_tiled, n_rays, kept_blocks);
   NSR_CHECK_LAUNCH("nsr_pack_kept_scan");
   return 0;
 }

@@ -110,8 +110,10 @@ class _NerfRenderRays(torch.autograd.Function):
             ctx.grad_bufs = (gd0, gc0, side)
         masks, t_min, counts = i32(n * words), f32(n), i32(n)
         # one fill: the forward's ray ticket, the backward's gradient amax, the marcher's row allocator and its 8 queue-group counters
-        zz = torch.zeros(12, dtype=torch.int32, device=dev)
+        nb = (n + 255) // 256
+        zz = torch.zeros(12 + nb, dtype=torch.int32, device=dev)
         tick, amax0, m_total, bin_counts = zz[0:1], zz[1:2].view(torch.float32), zz[2:4].view(torch.int64), zz[4:12]
+        kept_blocks = zz[12:] if fused.fuse_kept_scan else None   # per-256-ray sums of the kept counts (the pack kernel's prefix sum)
         if fused.march_alloc:
             # the marcher reserves every ray's rows and its place in the longest-first queue itself (atomics): no scan kernel behind it
             offsets_m, order = i64(n), i32(8 * n)
@@ -130,7 +132,7 @@ class _NerfRenderRays(torch.autograd.Function):
         step = float(m.render_step_size)
         lib.call('nsr_nerf_rays_fwd', fused.ref(), ptr(rays), ptr(masks), words, ptr(t_min), ptr(offsets_m), ptr(order), step,
                  float(fused.early_stop_eps), ptr(dh), ptr(ch), ptr(enc), ptr(sig), ptr(rgbs), ptr(weights), ptr(trans), ptr(kidx),
-                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, ptr(counts), ptr(bin_counts) if fused.march_alloc else None, stream())
+                 ptr(acc_rgb), ptr(opacity), ptr(depth), ptr(kept), ptr(tick), n, ptr(counts), ptr(bin_counts) if fused.march_alloc else None, ptr(kept_blocks), stream())
         if not fused.fuse_kept_scan:
             lib.call('nsr_scan_counts', ptr(kept), ptr(offsets_k), n, stream())
         # packed view of the kept samples: the reference's per-sample outputs + the row index of the tile backward
@@ -144,7 +146,7 @@ class _NerfRenderRays(torch.autograd.Function):
         xyzdir = f32(cap + pad, 6) if packed_bwd else None
         if fused.fuse_kept_scan:   # the packed offsets are computed inside the pack kernel (one launch and a one-CTA scan less)
             lib.call('nsr_pack_kept_scan', ptr(offsets_m), ptr(kept), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts),
-                     ptr(te), None, ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), tiled, n, stream())
+                     ptr(te), None, ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), tiled, n, ptr(kept_blocks), stream())
         else:
             lib.call('nsr_pack_kept', ptr(offsets_m), ptr(offsets_k), ptr(t_min), step, ptr(kidx), ptr(weights), ptr(ri), ptr(ts), ptr(te), None,
                      ptr(pos), fused.ref(), ptr(rays), ptr(enc), ptr(enc_k), ptr(xyzdir), tiled, n, stream())

@@ -89,9 +89,9 @@ _SIGNATURES = {
     'nsr_scan_counts_order': [P, P, P, I64, P],
     'nsr_march_rays_alloc': [P, P, P, P, P, P, I32, P, P, P, P, P, P, I64, P],
     'nsr_march_rays_expand': [P, P, I32, P, P, P, P, P, I64, P],
-    'nsr_nerf_rays_fwd': [P, P, P, I32, P, P, P, F32, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P, P],
+    'nsr_nerf_rays_fwd': [P, P, P, I32, P, P, P, F32, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P, P, P],
     'nsr_pack_kept': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I32, I64, P],
-    'nsr_pack_kept_scan': [P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I32, I64, P],
+    'nsr_pack_kept_scan': [P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, I32, I64, P, P],
     'nsr_nerf_ray_bwd_loose': [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P],
     'nsr_nerf_rays_bwd': [P, P, P, P, P, F32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P, F32, P, I64, P],
     'nsr_neus_field_fwd': [P, P, P, P, P, P, P, F32, I32, P, P, P, I64, P, P],
