@@ -640,7 +640,9 @@ def gpu_arm(args):
     # because the table and its gradient are L2 resident
     ncu_info = {}
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_traffic.json')) as fh:
+        prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles')
+        name = 'r2_ncu_traffic.json' if os.path.exists(os.path.join(prof, 'r2_ncu_traffic.json')) else 'r1_ncu_traffic.json'
+        with open(os.path.join(prof, name)) as fh:
             ncu_info = json.load(fh)
     except (OSError, ValueError):
         pass
