@@ -10,6 +10,7 @@
 //     dtable[c] += w_c eb_l + q_l scale_l (dw_c/dx . gx)        (ONE 8-byte RED per corner carries both orders)
 // The SDF branch stays fp32 on the CUDA cores (the reference runs it under autocast(False): the NeuS alpha multiplies sdf by
 // inv_s up to 1e3+), weights broadcast from shared memory; only the weight-gradient outer products go through tensor cores.
+#include <stdlib.h>
 #include "mlp_warp.cuh"
 
 namespace {
@@ -158,6 +159,203 @@ __global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_kernel(const __gri
 #pragma unroll
     for (int o = 0; o < NOUTP; ++o)
       if (o < n_out) feat[i * n_out + o] = out[o];
+  }
+}
+
+// ---- forward with the three GEMMs of the SDF network on tensor cores ---------------------------------------------------------
+// ncu (round 2, profiles/r2_ncu_final.md): the thread-per-sample kernel above executes 15.6 k warp instructions per 32 samples, more than
+// half of them the 64 x (36 + 16 + 36) scalar FMAs of  z = W1 e,  out = W2 h,  q = W1^T u  with their weight loads from shared memory.
+// Here a warp owns 32 samples; the gathers stay thread-per-sample, the three products run as m16n8k16 MMAs with fp32 accumulation on
+// operands SPLIT into fp16 hi + lo parts (x = hi + lo, hi = fp16(x), lo = fp16(x - hi)):  x w ~= hi_x hi_w + lo_x hi_w + hi_x lo_w, i.e.
+// ~21 bits of every product survive (the dropped lo_x lo_w term is 2^-22 relative): fp32-level accuracy for the inv_s-amplified SDF,
+// which a single fp16 product (11 bits) would not give.  Same outputs as the scalar kernel to ~1e-6 relative.
+constexpr int TC_K1 = 48;              // 35 inputs padded to three k16 steps
+constexpr int TC_LD1 = TC_K1 + 8;      // 56 halves per row of the E / W1 tiles (ldmatrix conflict-free)
+constexpr int TC_LDQ = 40;             // floats per row of the q tile
+
+struct NeusTcSmem {
+  __half W1hi[NH][TC_LD1], W1lo[NH][TC_LD1];        // [k][j]
+  __half W2hi[NOUTP][NSR_LD64], W2lo[NOUTP][NSR_LD64];  // [o][k]
+  float b1[NH], b2[NOUTP], w2row0[NH];              // w2row0[k] = W2[0][k] (u = s * W2[0])
+  __half Ehi[kThreads / 32][32][TC_LD1], Elo[kThreads / 32][32][TC_LD1];
+  float Q[kThreads / 32][32][TC_LDQ];
+};
+
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+// accumulator tile values f(acc) -> hi / lo A fragments of the next GEMM (MT = 1, 64 columns)
+template <typename F>
+__device__ __forceinline__ void acc_to_split_afrag(const float (&acc)[1][8][4], uint32_t (&ahi)[1][4][4], uint32_t (&alo)[1][4][4], F f) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nt = 2 * k + (j >> 1), i0 = (j & 1) * 2;
+      const float v0 = f(acc[0][nt][i0], nt, i0), v1 = f(acc[0][nt][i0 + 1], nt, i0 + 1);
+      __half h0, l0, h1, l1;
+      split_h(v0, h0, l0);
+      split_h(v1, h1, l1);
+      const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+      ahi[0][k][j] = *reinterpret_cast<const uint32_t*>(&hh);
+      alo[0][k][j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_tc_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
+                                                                        const __half2* __restrict__ table, const float* __restrict__ W1,
+                                                                        const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                        const float* __restrict__ b2, float radius, int n_out,
+                                                                        float* __restrict__ sdf, float* __restrict__ grad,
+                                                                        float* __restrict__ feat, int64_t n_cap,
+                                                                        const int64_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  NeusTcSmem& S = *reinterpret_cast<NeusTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, cq = lane & 3;
+  for (int i = tid; i < NH * TC_LD1; i += kThreads) {
+    const int k = i / TC_LD1, j = i % TC_LD1;
+    split_h(j < NIN ? W1[k * NIN + j] : 0.f, S.W1hi[k][j], S.W1lo[k][j]);
+  }
+  for (int i = tid; i < NOUTP * NSR_LD64; i += kThreads) {
+    const int o = i / NSR_LD64, k = i % NSR_LD64;
+    split_h((o < n_out && k < NH) ? W2[o * NH + k] : 0.f, S.W2hi[o][k], S.W2lo[o][k]);
+  }
+  for (int i = tid; i < NH; i += kThreads) {
+    S.b1[i] = b1[i];
+    S.w2row0[i] = W2[i];
+  }
+  for (int i = tid; i < NOUTP; i += kThreads) S.b2[i] = i < n_out ? b2[i] : 0.f;
+  __syncthreads();
+  const float inv2r = 1.f / (2.f * radius);
+  const int64_t n32 = (n + 31) & ~31ll;
+  for (int64_t base = (blockIdx.x * (int64_t)(kThreads / 32) + warp) * 32; base < n32; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = base + lane;
+    const bool ok = i < n;
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    if (ok) {
+      x = (points[i * 3 + 0] + radius) * inv2r;
+      y = (points[i * 3 + 1] + radius) * inv2r;
+      z = (points[i * 3 + 2] + radius) * inv2r;
+    }
+    {  // ---- encoding row of this thread's sample -> hi / lo fp16 tiles
+      float e[NINP], dummy[NINP];
+      e[0] = 2.f * x - 1.f;
+      e[1] = 2.f * y - 1.f;
+      e[2] = 2.f * z - 1.f;
+      e[NIN] = 0.f;
+      gather_enc<false>(g, table, x, y, z, 0.f, 0.f, 0.f, e, dummy);
+      __half* rh = S.Ehi[warp][lane];
+      __half* rl = S.Elo[warp][lane];
+#pragma unroll
+      for (int j = 0; j < NINP; j += 2) {
+        __half h0, l0, h1, l1;
+        split_h(e[j], h0, l0);
+        split_h(e[j + 1], h1, l1);
+        *reinterpret_cast<__half2*>(rh + j) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(rl + j) = __halves2half2(l0, l1);
+      }
+#pragma unroll
+      for (int j = NINP; j < TC_K1; j += 2) {
+        *reinterpret_cast<__half2*>(rh + j) = __float2half2_rn(0.f);
+        *reinterpret_cast<__half2*>(rl + j) = __float2half2_rn(0.f);
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {  // 16 rows at a time: keeps accumulators + two split fragment sets inside the register budget
+      const int r0 = m * 16;
+      float acc[1][8][4];
+      {
+        uint32_t ahi[1][3][4], alo[1][3][4];
+        nsr_load_afrag<1, 3>(ahi, &S.Ehi[warp][0][0], TC_LD1, r0);
+        nsr_load_afrag<1, 3>(alo, &S.Elo[warp][0][0], TC_LD1, r0);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[0][nt][q] = S.b1[nt * 8 + cq * 2 + (q & 1)];
+        nsr_gemm_w<1, 3, 8>(acc, ahi, &S.W1hi[0][0], TC_LD1);
+        nsr_gemm_w<1, 3, 8>(acc, alo, &S.W1hi[0][0], TC_LD1);
+        nsr_gemm_w<1, 3, 8>(acc, ahi, &S.W1lo[0][0], TC_LD1);
+      }
+      // z -> (h, s); out = W2 h + b2
+      float sg[8][4];
+      uint32_t fhi[1][4][4], flo[1][4][4];
+      acc_to_split_afrag(acc, fhi, flo, [&](float zk, int nt, int q) {
+        float s_;
+        const float h = softplus100(zk, s_);
+        sg[nt][q] = s_;
+        return h;
+      });
+      {
+        float acco[1][2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acco[0][nt][q] = S.b2[nt * 8 + cq * 2 + (q & 1)];
+        nsr_gemm_w<1, 4, 2>(acco, fhi, &S.W2hi[0][0], NSR_LD64);
+        nsr_gemm_w<1, 4, 2>(acco, flo, &S.W2hi[0][0], NSR_LD64);
+        nsr_gemm_w<1, 4, 2>(acco, fhi, &S.W2lo[0][0], NSR_LD64);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t row = base + r0 + gq + ((q >> 1) << 3);
+            const int col = nt * 8 + cq * 2 + (q & 1);
+            if (row < n) {
+              if (col == 0) sdf[row] = acco[0][nt][q];
+              if (col < n_out) feat[row * n_out + col] = acco[0][nt][q];
+            }
+          }
+      }
+      // u = s * W2[0];  q = W1^T u
+      acc_to_split_afrag(acc, fhi, flo, [&](float, int nt, int q) { return sg[nt][q] * S.w2row0[nt * 8 + cq * 2 + (q & 1)]; });
+      {
+        float accq[1][6][4];
+        nsr_zero_acc(accq);
+        nsr_gemm_wt<1, 4, 6>(accq, fhi, &S.W1hi[0][0], TC_LD1);
+        nsr_gemm_wt<1, 4, 6>(accq, flo, &S.W1hi[0][0], TC_LD1);
+        nsr_gemm_wt<1, 4, 6>(accq, fhi, &S.W1lo[0][0], TC_LD1);
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt)  // columns 0..39 (q has 35 live entries)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) S.Q[warp][r0 + gq + ((q >> 1) << 3)][nt * 8 + cq * 2 + (q & 1)] = accq[0][nt][q];
+      }
+    }
+    __syncwarp();
+    // ---- analytic normal: second gather, features weighted by this sample's q
+    if (ok) {
+      const float* qr = S.Q[warp][lane];
+      float gx = 2.f * qr[0], gy = 2.f * qr[1], gz = 2.f * qr[2];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const LevelInfo li = nsr_level(g, l);
+        uint32_t cx, cy, cz, idx[8];
+        float fx, fy, fz;
+        nsr_pos_fract(x, li.scale, cx, fx);
+        nsr_pos_fract(y, li.scale, cy, fy);
+        nsr_pos_fract(z, li.scale, cz, fz);
+        nsr_corner_indices(li, cx, cy, cz, idx);
+        const float q0 = qr[3 + 2 * l], q1 = qr[4 + 2 * l];
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 v = nsr_ld_table(table, idx[c]);
+          const float sv = v.x * q0 + v.y * q1;
+          lx = fmaf(nsr_corner_dweight(c, 0, fx, fy, fz), sv, lx);
+          ly = fmaf(nsr_corner_dweight(c, 1, fx, fy, fz), sv, ly);
+          lz = fmaf(nsr_corner_dweight(c, 2, fx, fy, fz), sv, lz);
+        }
+        gx = fmaf(li.scale, lx, gx);
+        gy = fmaf(li.scale, ly, gy);
+        gz = fmaf(li.scale, lz, gz);
+      }
+      grad[i * 3 + 0] = gx * inv2r;
+      grad[i * 3 + 1] = gy * inv2r;
+      grad[i * 3 + 2] = gz * inv2r;
+    }
+    __syncwarp();  // the tiles are rewritten by the next chunk
   }
 }
 
@@ -433,9 +631,32 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
                                   int64_t n, const int64_t* n_dev, void* stream) {
   if (int e = check(g, n_out, "nsr_neus_field_fwd")) return e;
   if (n == 0) return 0;
-  const int grid = (int)min((int64_t)nsr_sm_count() * 8, (n + kThreads - 1) / kThreads);
-  neus_field_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out, sdf,
-                                                                     grad, feature, n, n_dev);
+  // NSR_NEUS_FWD=tc selects neus_field_fwd_tc_kernel (SDF network on tensor cores, hi / lo split operands: same results to ~1e-6, all NeuS
+  // parity tests green with it).  Measured on B200 (C3, 313 k samples): 0.325 ms against 0.304 ms for the thread-per-sample kernel -- with 12
+  // warps per SM the kernel is bound by the latency of its two gathers, and the scalar MLP's instruction stream was what covered it; the
+  // tensor-core form needs the gathers batched / more warps per SM before it pays.  Default: the thread-per-sample kernel.
+  static const bool scalar = [] {
+    const char* v = getenv("NSR_NEUS_FWD");
+    return !(v != nullptr && v[0] == 't');
+  }();
+  if (scalar) {
+    const int grid = (int)min((int64_t)nsr_sm_count() * 8, (n + kThreads - 1) / kThreads);
+    neus_field_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius, n_out, sdf,
+                                                                       grad, feature, n, n_dev);
+  } else {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(neus_field_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NeusTcSmem));
+      if (e != cudaSuccess) {
+        nsr_set_error("nsr_neus_field_fwd: cannot reserve %zu B shared memory: %s", sizeof(NeusTcSmem), cudaGetErrorString(e));
+        return 2;
+      }
+      attr_set = true;
+    }
+    const int grid = (int)min((int64_t)nsr_sm_count() * 3, (n + kThreads - 1) / kThreads);
+    neus_field_fwd_tc_kernel<<<grid, kThreads, sizeof(NeusTcSmem), (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius,
+                                                                                            n_out, sdf, grad, feature, n, n_dev);
+  }
   NSR_CHECK_LAUNCH("nsr_neus_field_fwd");
   return 0;
 }
