@@ -379,8 +379,11 @@ def test_occupancy_grid_update(nsr):
     grid.every_n_step(step=512, occ_eval_fn=lambda x: torch.zeros(len(x), 1, device=x.device))
     assert (grid.occs <= before + 1e-7).all() and (grid.occs < before).any()
     sd = grid.state_dict()
-    assert set(sd) == {'_roi_aabb', 'resolution', 'occs', '_binary'}
-    sd['grid_coords'] = torch.zeros(1)  # nerfacc checkpoints carry these
+    # the same keys as a nerfacc 0.3.3 OccupancyGrid checkpoint: grid_coords / grid_indices are emitted on save (derived index tables)
+    # and dropped on load, so checkpoints go both ways with strict loading
+    assert set(sd) == {'_roi_aabb', 'resolution', 'occs', '_binary', 'grid_coords', 'grid_indices'}
+    assert sd['grid_coords'].shape == (32 ** 3, 3) and sd['grid_indices'].shape == (32 ** 3,)
+    assert torch.equal(sd['grid_coords'][33].cpu(), torch.tensor([0, 1, 1])) and int(sd['grid_indices'][33]) == 33
     g2 = nerfacc.OccupancyGrid(aabb, 32).to(D)
     g2.load_state_dict(sd)
     assert torch.equal(g2.binary, grid.binary)
