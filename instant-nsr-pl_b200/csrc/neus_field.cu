@@ -171,15 +171,19 @@ __global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_kernel(const __gri
 // which a single fp16 product (11 bits) would not give.  Same outputs as the scalar kernel to ~1e-6 relative.
 constexpr int TC_K1 = 48;              // 35 inputs padded to three k16 steps
 constexpr int TC_LD1 = TC_K1 + 8;      // 56 halves per row of the E / W1 tiles (ldmatrix conflict-free)
-constexpr int TC_LDQ = 40;             // floats per row of the q tile
 
 struct NeusTcSmem {
   __half W1hi[NH][TC_LD1], W1lo[NH][TC_LD1];        // [k][j]
   __half W2hi[NOUTP][NSR_LD64], W2lo[NOUTP][NSR_LD64];  // [o][k]
   float b1[NH], b2[NOUTP], w2row0[NH];              // w2row0[k] = W2[0][k] (u = s * W2[0])
+  // per warp: the 32 encoding rows as fp16 hi / lo tiles; once a 16-row tile's A fragments are loaded its rows are dead and hold the
+  // q vector of the same samples (36 floats: 28 in the row's hi storage, 8 in its lo storage) => 48 KB per CTA, four CTAs per SM
   __half Ehi[kThreads / 32][32][TC_LD1], Elo[kThreads / 32][32][TC_LD1];
-  float Q[kThreads / 32][32][TC_LDQ];
 };
+static_assert(TC_LD1 * 2 == 28 * 4, "a 56-half row holds 28 floats");
+__device__ __forceinline__ float& neus_q_slot(NeusTcSmem& S, int warp, int row, int j) {
+  return j < 28 ? reinterpret_cast<float*>(S.Ehi[warp][row])[j] : reinterpret_cast<float*>(S.Elo[warp][row])[j - 28];
+}
 
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
@@ -203,7 +207,7 @@ __device__ __forceinline__ void acc_to_split_afrag(const float (&acc)[1][8][4], 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_tc_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
+__global__ void __launch_bounds__(kThreads, 4) neus_field_fwd_tc_kernel(const __grid_constant__ nsr_grid_t g, const float* __restrict__ points,
                                                                         const __half2* __restrict__ table, const float* __restrict__ W1,
                                                                         const float* __restrict__ b1, const float* __restrict__ W2,
                                                                         const float* __restrict__ b2, float radius, int n_out,
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_tc_kernel(const __
         uint32_t ahi[1][3][4], alo[1][3][4];
         nsr_load_afrag<1, 3>(ahi, &S.Ehi[warp][0][0], TC_LD1, r0);
         nsr_load_afrag<1, 3>(alo, &S.Elo[warp][0][0], TC_LD1, r0);
+        __syncwarp();   // rows r0 .. r0 + 15 of both tiles are dead from here on: they receive q below
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -318,15 +323,20 @@ __global__ void __launch_bounds__(kThreads, 3) neus_field_fwd_tc_kernel(const __
         nsr_gemm_wt<1, 4, 6>(accq, flo, &S.W1hi[0][0], TC_LD1);
         nsr_gemm_wt<1, 4, 6>(accq, fhi, &S.W1lo[0][0], TC_LD1);
 #pragma unroll
-        for (int nt = 0; nt < 5; ++nt)  // columns 0..39 (q has 35 live entries)
+        for (int nt = 0; nt < 5; ++nt)  // columns 0..35 (q has 35 live entries)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) S.Q[warp][r0 + gq + ((q >> 1) << 3)][nt * 8 + cq * 2 + (q & 1)] = accq[0][nt][q];
+          for (int q = 0; q < 4; ++q) {
+            const int col = nt * 8 + cq * 2 + (q & 1);
+            if (col < NINP) neus_q_slot(S, warp, r0 + gq + ((q >> 1) << 3), col) = accq[0][nt][q];
+          }
       }
     }
     __syncwarp();
     // ---- analytic normal: second gather, features weighted by this sample's q
     if (ok) {
-      const float* qr = S.Q[warp][lane];
+      float qr[NINP];
+#pragma unroll
+      for (int j = 0; j < NINP; ++j) qr[j] = neus_q_slot(S, warp, lane, j);
       float gx = 2.f * qr[0], gy = 2.f * qr[1], gz = 2.f * qr[2];
 #pragma unroll
       for (int l = 0; l < 16; ++l) {
@@ -653,7 +663,7 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
       }
       attr_set = true;
     }
-    const int grid = (int)min((int64_t)nsr_sm_count() * 3, (n + kThreads - 1) / kThreads);
+    const int grid = (int)min((int64_t)nsr_sm_count() * 4, (n + kThreads - 1) / kThreads);
     neus_field_fwd_tc_kernel<<<grid, kThreads, sizeof(NeusTcSmem), (cudaStream_t)stream>>>(*g, points, (const __half2*)table_h, W1, b1, W2, b2, radius,
                                                                                             n_out, sdf, grad, feature, n, n_dev);
   }
