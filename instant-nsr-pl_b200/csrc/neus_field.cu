@@ -641,13 +641,13 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
                                   int64_t n, const int64_t* n_dev, void* stream) {
   if (int e = check(g, n_out, "nsr_neus_field_fwd")) return e;
   if (n == 0) return 0;
-  // NSR_NEUS_FWD=tc selects neus_field_fwd_tc_kernel (SDF network on tensor cores, hi / lo split operands: same results to ~1e-6, all NeuS
-  // parity tests green with it).  Measured on B200 (C3, 313 k samples): 0.325 ms against 0.304 ms for the thread-per-sample kernel -- with 12
-  // warps per SM the kernel is bound by the latency of its two gathers, and the scalar MLP's instruction stream was what covered it; the
-  // tensor-core form needs the gathers batched / more warps per SM before it pays.  Default: the thread-per-sample kernel.
+  // Default: neus_field_fwd_tc_kernel (SDF network on tensor cores, hi / lo split operands; same results to ~1e-6, every NeuS parity test
+  // runs on it).  Measured on B200 (C3, 313 k samples): 0.233 ms against 0.302 ms for the thread-per-sample kernel (NSR_NEUS_FWD=scalar).
+  // Its first version (three CTAs per SM, separate q tile) was SLOWER, 0.325 ms: the kernel is bound by the latency of its two gathers,
+  // and fewer instructions only paid once the freed registers / shared memory bought a fourth CTA per SM (q aliased onto the encoding rows).
   static const bool scalar = [] {
     const char* v = getenv("NSR_NEUS_FWD");
-    return !(v != nullptr && v[0] == 't');
+    return v != nullptr && v[0] == 's';
   }();
   if (scalar) {
     const int grid = (int)min((int64_t)nsr_sm_count() * 8, (n + kThreads - 1) / kThreads);
