@@ -645,6 +645,7 @@ extern "C" int nsr_neus_field_fwd(const nsr_grid_t* g, const float* points, cons
   // runs on it).  Measured on B200 (C3, 313 k samples): 0.233 ms against 0.302 ms for the thread-per-sample kernel (NSR_NEUS_FWD=scalar).
   // Its first version (three CTAs per SM, separate q tile) was SLOWER, 0.325 ms: the kernel is bound by the latency of its two gathers,
   // and fewer instructions only paid once the freed registers / shared memory bought a fourth CTA per SM (q aliased onto the encoding rows).
+  // (Issuing the corner loads of four levels together in both gathers, as the NeRF forward does, was measured too: 0.247 ms, not kept.)
   static const bool scalar = [] {
     const char* v = getenv("NSR_NEUS_FWD");
     return v != nullptr && v[0] == 's';
