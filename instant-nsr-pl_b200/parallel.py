@@ -42,6 +42,32 @@ class GradSync:
             g.mul_(inv)
 
 
+def level_group_ranges(level_groups, level_offsets, table_first_float, n_total):
+    """Pure host logic of P2PGradSync.bind_pipelined: the exchange range (begin, count) in floats of every level group.
+
+    level_groups   ((l0, l1), ...) partitioning [0, L) from the top down, e.g. ((12, 16), (8, 12), (0, 8))
+    level_offsets  entry offset of every level inside the table (L + 1 values, 2 floats per entry)
+    table_first_float  index of the table's first float inside the exchange buffer (the table is the LAST parameter in it)
+    n_total        length of the (padded) exchange buffer
+    Group i covers the floats of its levels; the first group additionally runs to the end of the buffer (padding), the last one starts at 0
+    (everything in front of the table: the other parameters and the density network's weights).  The ranges tile [0, n_total)."""
+    groups = [tuple(g) for g in level_groups]
+    L = len(level_offsets) - 1
+    ok = groups and groups[0][1] == L and groups[-1][0] == 0 and all(groups[i][0] == groups[i + 1][1] for i in range(len(groups) - 1)) \
+        and all(a < b for a, b in groups)
+    if not ok or len(groups) > 4:
+        raise ValueError(f'level_groups must partition [0, {L}) from the top down in at most 4 groups, e.g. ((12, 16), (8, 12), (0, 8))')
+    off = lambda l: table_first_float + 2 * int(level_offsets[l])
+    out = []
+    for i, (l0, l1) in enumerate(groups):
+        begin = 0 if i == len(groups) - 1 else off(l0)
+        end = n_total if i == 0 else off(l1)
+        if begin % 4 or end % 4 or end <= begin:
+            raise ValueError('level group boundaries must be 16-byte aligned and non-empty')
+        out.append((begin, end - begin))
+    return out
+
+
 class P2PGradSync:
     """The same mean, as OUR kernels over NVLink peer memory instead of NCCL (csrc/p2p.cu): the flat gradient vector of every rank
     lives in a symmetric (peer-mapped) buffer; ``all_reduce_mean`` = ONE kernel: entry barrier, in-place reduce-scatter + all-gather
@@ -121,18 +147,9 @@ class P2PGradSync:
         if self.params[-1] is not net.params:
             raise RuntimeError('bind_pipelined: the hash-grid parameter must be the largest parameter of the exchange')
         groups = [tuple(g) for g in level_groups]
-        ok = groups and groups[0][1] == 16 and groups[-1][0] == 0 and all(groups[i][0] == groups[i + 1][1] for i in range(len(groups) - 1))
-        if not ok or len(groups) > 4:
-            raise ValueError('level_groups must partition [0, 16) from the top down in at most 4 groups, e.g. ((12, 16), (8, 12), (0, 8))')
         base = self.view_of(net.params).data_ptr() - self.buf.data_ptr()
         assert base % 16 == 0
-        off = lambda l: base // 4 + net.mlp.n_params + 2 * int(fused.grid.offset[l])   # first float of level l inside the symmetric buffer
-        self.ranges = []
-        for i, (l0, l1) in enumerate(groups):
-            begin = 0 if i == len(groups) - 1 else off(l0)
-            end = self.n if i == 0 else off(l1)
-            assert begin % 4 == 0 and end % 4 == 0
-            self.ranges.append((begin, end - begin))
+        self.ranges = level_group_ranges(groups, fused.grid.offset, base // 4 + net.mlp.n_params, self.n)
         self.side = [torch.cuda.Stream(device=self.buf.device) for _ in groups[:-1]]
         fused.level_groups = groups
         fused.exchange_hook = self.exchange_group
