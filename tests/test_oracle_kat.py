@@ -372,3 +372,32 @@ def test_hashgrid_one_gather_form_matches_the_per_corner_form():
         (b * go).sum().backward()
         np.testing.assert_allclose(b.detach().numpy(), a.detach().numpy(), rtol=0, atol=tol)
         np.testing.assert_allclose(t2.grad.numpy(), t1.grad.numpy(), rtol=0, atol=tol * 10)
+
+
+def test_dense_level_index_wrap_equals_the_modulo_for_every_in_range_cell():
+    """csrc/common.cuh nsr_corner_indices (round 2): on dense levels the table index is wrapped with `i = min(i, 2 size - 1); i -= (i >= size) *
+    size` instead of `i % size` (the integer division was 11 % of the per-ray forward kernel's instructions).  The two agree iff i < 2 size for
+    every corner of every cell a position in [0, 1]^3 can fall into -- checked here exhaustively on the corner extremes for every dense level
+    of the shipped grid configs (tcnn index: x + y res + z res^2, cell = floor(scale x + 0.5) in [0, res - 1], corner offsets 0 / 1)."""
+    from nsr_b200 import configs, ops
+    seen = 0
+    for cfg in (configs.nerf_blender()['geometry']['xyz_encoding_config'], configs.neus_blender()['geometry']['xyz_encoding_config'],
+                configs.neus_dtu()['geometry_bg']['xyz_encoding_config'] if 'geometry_bg' in configs.neus_dtu() else None):
+        if cfg is None:
+            continue
+        g = ops.GridSpec(cfg)
+        for l in range(g.n_levels):
+            if not g.dense[l]:
+                continue
+            r, size = int(g.res[l]), int(g.size[l])
+            assert r >= 2 and r ** 3 <= size
+            # cell coordinates 0 .. r - 1 (scale x + 0.5 <= scale + 0.5 < r), corners add 0 / 1 per axis
+            cells = np.arange(r, dtype=np.int64)
+            top = (cells[:, None, None] + 1) + (cells[None, :, None] + 1) * r + (cells[None, None, :] + 1) * r * r   # the largest corner index per cell
+            assert int(top.max()) == r + r * r + r ** 3 and int(top.max()) < 2 * size
+            i = top.reshape(-1)
+            wrapped = np.minimum(i, 2 * size - 1)
+            wrapped = wrapped - (wrapped >= size) * size
+            assert np.array_equal(wrapped, i % size)
+            seen += 1
+    assert seen >= 5   # nerf-blender: levels 0..4 are dense
