@@ -186,7 +186,9 @@ int nsr_accumulate(const float* weights, const float* values, const int64_t* off
  * stores the per-ray occupancy masks [n_rays, words], t_min and the per-ray sample counts.
  * nsr_scan_counts_order: exclusive scan of the counts + a longest-rays-first processing order (rays bucketed by their
  * number of 32-sample chunks) for the per-ray kernel.  nsr_march_rays_expand turns the masks into packed samples. */
-/* nsr_march_rays_alloc: nsr_march_rays_mask + slice allocation + queue binning in the same launch (replaces nsr_scan_counts_order):
+/* nsr_march_rays_alloc: nsr_march_rays_mask + slice allocation + queue binning in the same launch (replaces nsr_scan_counts_order).
+ * Reference call site: nerfacc.ray_marching in NeRFModel.forward_ (models/nerf.py:82-93) -- what nerfacc does with a host-synchronised exact
+ * allocation (`num_steps.sum().item()`), done on the device:
  *   offsets[ray] = atomic reservation of counts[ray] rows (completion order, not ray order; *alloc_total (uint64, zero on entry) ends as the
  *   number of marched samples); bin_counts int32[8] (zero on entry) / order_bins int32[8 * n]: rays grouped by 32-sample chunk count
  *   (>= 17, 13-16, 9-12, 5-8, 3-4, 2, 1, 0), the queue of nsr_nerf_rays_fwd (pass counts + bin_counts there). */
@@ -407,7 +409,7 @@ int nsr_mc_emit(const float* field, int32_t nx, int32_t ny, int32_t nz, float is
  *   Must be bracketed by barriers: barrier, allreduce, barrier. */
 int nsr_p2p_barrier(const uint64_t* flag_ptrs_host, int32_t* epoch_dev, int32_t* err_dev, int32_t rank, int32_t world, void* stream);
 int nsr_p2p_allreduce_mean(const uint64_t* peer_ptrs_host, void* multicast_ptr, int32_t rank, int32_t world, int64_t n, void* stream);
-/* nsr_p2p_exchange_mean: the same exchange as ONE launch -- entry barrier, reduce-scatter + all-gather, exit barrier inside the kernel
+/* nsr_p2p_exchange_mean (reference: the gradient all-reduce Lightning DDP inserts, launch.py:98 `strategy='ddp'`): the same exchange as ONE launch -- entry barrier, reduce-scatter + all-gather, exit barrier inside the kernel
  *   (what one bucket of DDP's all-reduce is, launch.py:98).  flag arrays need 64 int32 per rank (entry epochs in [32,48), exit epochs in
  *   [48,64); [0,16) stays nsr_p2p_barrier's); epoch_counter_dev: local int32[2] {last completed epoch, CTA counter}, zeroed once.  No surrounding barriers needed;
  *   graph-replay safe (the epoch is device state).  When it returns on the stream, every replica holds the mean and no peer reads
