@@ -5,9 +5,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Headline (`value`, `e2e`, `roofline`): config C2 = nerf-blender HashGrid L16/F2/T2^19 + FullyFused-64 fields, 8192 rays per GPU.
-One "step" = one pass of the hot path over one batch of synthetic rays: lattice-mask march + persistent per-ray forward (hash gather,
-both MLPs, compositing, early termination) + fused masked smooth-L1 loss + per-ray and tile backward to every parameter gradient
-(+ the gradient mean over the ranks when N > 1), replayed as ONE CUDA graph.  The optimizer is outside the path.
+One "step" = one pass of the hot path over one batch of synthetic rays: lattice-mask march (+ row allocation) + persistent per-ray forward
+(hash gather, both MLPs, compositing, early termination) + fused masked smooth-L1 loss + per-ray backward + the field backward as a
+tensor-core network half and a high-occupancy table scatter (+ the gradient mean over the ranks when N > 1: one-launch NVLink exchange,
+pipelined with the scatter's level groups), replayed as ONE CUDA graph.  The optimizer is outside the path.
 `ms_per_step` / `value` use the MEDIAN of the K per-step CUDA-event times, max over ranks; the mean is reported beside it.
 
 At N = 1 the same JSON line also carries
